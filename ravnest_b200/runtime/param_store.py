@@ -1,0 +1,162 @@
+"""Flat, versioned parameter storage for one pipeline stage.
+
+The reference implements PipeDream-style weight stashing by cloning the full ``state_dict`` after
+every backward and swapping ``param.data`` around the recompute (``ravnest/compute.py:47-51``,
+``:191-199``, ``:218-221``, ``:261``, ``:530-540``; ``utils.py:119-125``).  Here a stage owns
+
+  * ``master``  : one flat fp32 buffer (the optimizer's copy; reference "clone params", node.py:207)
+  * ``slots``   : a ring of flat buffers in the compute dtype, one per live weight version
+  * ``grad``    : one flat gradient buffer every version's leaves accumulate into
+
+so stashing a version is "keep using slot i", publishing a new version is one fused cast/copy into
+a free slot (or the fused all-reduce+optimizer kernel writing it directly), and the flat buffers
+are exactly the buckets the NVLink collectives operate on.  Offsets are padded to 128 bytes so the
+vectorised kernels (16 B / thread, multimem v4) never straddle parameters.
+"""
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+_ALIGN_BYTES = 128
+
+
+class Slot:
+    __slots__ = ('index', 'flat', 'leaves', 'param_dict', 'version', 'refs')
+
+    def __init__(self, index, flat, leaves, param_dict):
+        self.index = index
+        self.flat = flat
+        self.leaves = leaves            # List[Tensor] leaf views (requires_grad) in layout order
+        self.param_dict = param_dict    # name -> leaf, for functional_call
+        self.version = -1
+        self.refs = 0
+
+
+class ParamStore:
+    def __init__(self, module: torch.nn.Module, device, n_slots: int = 3, compute_dtype: Optional[torch.dtype] = None,
+                 master_dtype: torch.dtype = torch.float32):
+        self.module = module
+        self.device = torch.device(device)
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        self.names: List[str] = [n for n, _ in named]
+        self.shapes = [tuple(p.shape) for _, p in named]
+        self.numels = [p.numel() for _, p in named]
+        self.compute_dtype = compute_dtype or (named[0][1].dtype if named else torch.float32)
+        self.master_dtype = master_dtype
+        align = 64      # elements: 128 B for bf16, 256 B for fp32
+        self.offsets: List[int] = []
+        off = 0
+        for n in self.numels:
+            self.offsets.append(off)
+            off += (n + align - 1) // align * align
+        self.total = max(off, align)
+        self.master = torch.zeros(self.total, dtype=master_dtype, device=self.device)
+        self.grad = torch.zeros(self.total, dtype=self.compute_dtype, device=self.device)
+        self.master_views = [self.master[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+        self.grad_views = [self.grad[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+        with torch.no_grad():
+            for view, (_, p) in zip(self.master_views, named):
+                view.copy_(p.detach().to(self.device, master_dtype))
+        self.slots: List[Slot] = []
+        for i in range(max(2, n_slots)):
+            self.slots.append(self._make_slot(i))
+        self.version = 0
+        self.current: Slot = self.slots[0]
+        self._publish_into(self.current)
+        self.current.version = 0
+        # optimizer-facing master parameters (leaf tensors sharing the flat master storage)
+        self.master_params = [torch.nn.Parameter(v, requires_grad=True) for v in self.master_views]
+        self._master_grad: Optional[torch.Tensor] = None
+        self.bind_module()
+
+    # ------------------------------------------------------------------ construction helpers
+    def _make_slot(self, index: int) -> Slot:
+        flat = torch.zeros(self.total, dtype=self.compute_dtype, device=self.device)
+        leaves, pdict = [], OrderedDict()
+        for name, o, n, s, g in zip(self.names, self.offsets, self.numels, self.shapes, self.grad_views):
+            leaf = flat[o:o + n].view(s).detach().requires_grad_(True)
+            leaf.grad = g            # every version accumulates into the one flat gradient buffer
+            leaves.append(leaf)
+            pdict[name] = leaf
+        return Slot(index, flat, leaves, pdict)
+
+    def _publish_into(self, slot: Slot) -> None:
+        with torch.no_grad():
+            slot.flat.copy_(self.master)        # fused cast fp32 -> compute dtype (one kernel)
+
+    # ------------------------------------------------------------------ version ring
+    def acquire(self) -> Slot:
+        """Pin the current version for an in-flight forward pass."""
+        self.current.refs += 1
+        return self.current
+
+    def release(self, slot: Slot) -> None:
+        slot.refs -= 1
+        assert slot.refs >= 0
+
+    def free_slot(self) -> Slot:
+        for s in self.slots:
+            if s is not self.current and s.refs == 0:
+                return s
+        s = self._make_slot(len(self.slots))    # ring too small for the staleness in flight: grow it
+        self.slots.append(s)
+        return s
+
+    def publish(self, writer=None) -> Slot:
+        """Make a new weight version current.  ``writer(slot)`` may fill the slot itself (fused
+        kernels write the compute-dtype weights directly); default is cast-copy from master."""
+        slot = self.free_slot() if self.current.refs > 0 else self.current
+        if writer is None:
+            self._publish_into(slot)
+        else:
+            writer(slot)
+        self.version += 1
+        slot.version = self.version
+        self.current = slot
+        return slot
+
+    def live_versions(self) -> Dict[int, int]:
+        return {s.version: s.refs for s in self.slots if s.refs > 0 or s is self.current}
+
+    # ------------------------------------------------------------------ gradients / master sync
+    def master_grad(self) -> torch.Tensor:
+        """Flat gradient in master dtype (alias of ``grad`` when dtypes match)."""
+        if self.compute_dtype == self.master_dtype:
+            return self.grad
+        if self._master_grad is None:
+            self._master_grad = torch.zeros(self.total, dtype=self.master_dtype, device=self.device)
+        self._master_grad.copy_(self.grad)
+        return self._master_grad
+
+    def attach_master_grads(self) -> None:
+        flat = self.master_grad()
+        for p, o, n, s in zip(self.master_params, self.offsets, self.numels, self.shapes):
+            p.grad = flat[o:o + n].view(s)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    # ------------------------------------------------------------------ module <-> store
+    def bind_module(self) -> None:
+        """Point the module's own Parameters at the current version (state_dict / save / eval)."""
+        lookup = dict(self.module.named_parameters())
+        for name, leaf in self.current.param_dict.items():
+            lookup[name].data = leaf.detach()
+
+    def load_master_from(self, tensors: Dict[str, torch.Tensor]) -> None:
+        with torch.no_grad():
+            for name, view in zip(self.names, self.master_views):
+                if name in tensors:
+                    view.copy_(tensors[name].to(self.device, self.master_dtype))
+
+    def master_state(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((n, v) for n, v in zip(self.names, self.master_views))
+
+    def index_of(self, name: str) -> int:
+        return self.names.index(name)
+
+    def range_of(self, first: str, last: str) -> slice:
+        """Flat element range covering parameters ``first..last`` inclusive (DP ring ranges)."""
+        i, j = self.names.index(first), self.names.index(last)
+        return slice(self.offsets[i], self.offsets[j] + self.numels[j])

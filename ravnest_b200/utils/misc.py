@@ -1,0 +1,76 @@
+"""Seeding, fusion, housekeeping helpers (reference ``ravnest/utils.py:196-255``, ``reset.py``)."""
+import os
+import random
+import shutil
+
+import numpy as np
+import torch
+
+from .serialization import load_submodel
+
+
+def set_seed(seed=42):
+    """Seed python / numpy / torch (CPU + every CUDA device) and ask for deterministic cuDNN
+    (reference utils.py:196-209)."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    os.environ['PYTHONHASHSEED'] = str(seed)
+
+
+def find_files_with_extension(root_folder, extension):
+    hits = []
+    for folder, _dirs, files in os.walk(root_folder):
+        for f in sorted(files):
+            if f.endswith('.' + extension.lstrip('.')):
+                hits.append(os.path.join(folder, f))
+    return sorted(hits)
+
+
+def model_fusion(cluster_id=0, base_dir=None):
+    """Merge the saved stage modules of one cluster into ``trained/trained_state_dict.pt``
+    (reference utils.py:232-255).  Stage state dicts already use the original parameter names; a
+    legacy ``L__self___`` prefix is stripped if present."""
+    base_dir = base_dir or os.environ.get('RAVNEST_HOME', '.')
+    folder = os.path.join(base_dir, 'node_data', 'cluster_{}'.format(cluster_id))
+    if not os.path.isdir(folder):
+        print('Submodels not found!')
+        return None
+    combined = {}
+    for path in find_files_with_extension(folder, 'pt'):
+        if os.path.basename(path) == 'submod.pt' and any(
+                f.startswith('submod_') and f.endswith('.pt') for f in os.listdir(os.path.dirname(path))):
+            continue                      # prefer the trained submod_<k>.pt over the initial stage
+        state = load_submodel(path).state_dict()
+        combined.update({k.replace('L__self___', ''): v.detach().to('cpu') for k, v in state.items()})
+    if not combined:
+        print('{} path has no submodels'.format(folder))
+        return None
+    out_dir = os.path.join(base_dir, 'trained')
+    os.makedirs(out_dir, exist_ok=True)
+    save_path = os.path.join(out_dir, 'trained_state_dict.pt')
+    torch.save(combined, save_path)
+    return save_path
+
+
+def reset_node_data(base_dir=None):
+    """``reset.py`` of the reference: drop every sub-folder of node_data/ (keeps node_configs.json)."""
+    base_dir = base_dir or os.environ.get('RAVNEST_HOME', '.')
+    root = os.path.join(base_dir, 'node_data')
+    if os.path.isdir(root):
+        for entry in os.listdir(root):
+            full = os.path.join(root, entry)
+            if os.path.isdir(full):
+                shutil.rmtree(full)
+
+
+def check_gpu_usage(device=None):
+    """Memory in use on ``device`` in MB.  The reference calls nvmlInit/Shutdown around every
+    forward/backward (utils.py:211-221); this reads the caching allocator's counter instead."""
+    if not torch.cuda.is_available():
+        return 0.0
+    return torch.cuda.memory_allocated(device) / 1e6
