@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Headline benchmark: BERT-base pre-training samples/sec (bf16) — or ResNet-50 images/sec — through
+the ravnest_b200 engine on N GPUs of one B200 box.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W   (N>1 launched under torchrun)
+prints ONE JSON line on rank 0.  ``--impl reference`` reports why the upstream package cannot run here;
+``--impl baseline`` runs the same schedule on stock cuBLAS/cuDNN/ATen ops + NCCL collectives + unfused
+torch optimizer (the baseline tier of BASELINE.md §3).
+
+Configs (BASELINE.json): BERT-base bf16, batch 8x512 per replica, LAMB, update_frequency 16
+(examples/bert/provider.py): N=1 solo, N=2 -> 2 stages x 1 replica, N=4 -> 2x2, N=8 -> 2x4.
+ResNet-50 (num_classes=200), batch 100x3x224x224 per replica, SGD-momentum: N=1 solo, 2 -> 2x1,
+4 -> 4x1, 8 -> 4x2.  Synthetic data of that shape, random-init weights.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'baseline', 'reference'])
+    ap.add_argument('--model', default='bert', choices=['bert', 'resnet50'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--update-frequency', type=int, default=None)
+    ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
+    return ap.parse_args()
+
+
+def reference_unavailable():
+    why = ("reference cannot be installed offline: setup.py pip-installs grpcio-tools==1.51.3 to compile protos and "
+           "ravnest/__init__ imports pippy (torchpippy==0.2.0) + torchinfo, none present in the image/wheelhouse; "
+           "it also has no NCCL/CUDA path (gRPC+pickle on CPU tensors)")
+    print(json.dumps({'impl': 'reference', 'unavailable': why}))
+
+
+class ClockSampler(threading.Thread):
+    """Sample SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                     nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap',
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: 'hw_power_brake'}
+            while not self._halt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as err:        # NVML missing: report it rather than fake clocks
+            self.reasons.add('nvml_unavailable:{}'.format(type(err).__name__))
+
+    def summary(self):
+        self._halt.set()
+        self.join(2)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def topology_for(model, n):
+    if model == 'bert':
+        return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}[n]
+    return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}[n]
+
+
+def build_model(args):
+    import torch
+    from ravnest_b200 import models
+    if args.model == 'bert':
+        cfg = models.BertConfig()
+        if args.layers:
+            cfg.num_hidden_layers = args.layers
+        model = models.BertForPreTraining(cfg)
+        B, S = 8, 512
+        example = {'input_ids': torch.randint(0, cfg.vocab_size, (2, S)), 'attention_mask': torch.ones(2, S, dtype=torch.long),
+                   'token_type_ids': torch.zeros(2, S, dtype=torch.long)}
+        return model, (), example, B
+    model = models.resnet50(num_classes=200)
+    return model, (torch.rand(2, 3, 224, 224),), {}, 100
+
+
+class SyntheticBert:
+    """Fixed pool of synthetic BERT batches (pinned host memory or device-resident)."""
+
+    def __init__(self, n, batch, seq, vocab, device=None, seed=0):
+        import torch
+        g = torch.Generator().manual_seed(seed)
+        self.items = []
+        for _ in range(n):
+            ids = torch.randint(0, vocab, (batch, seq), generator=g)
+            mask = torch.ones(batch, seq, dtype=torch.long)
+            tt = torch.zeros(batch, seq, dtype=torch.long)
+            labels = torch.full((batch, seq), -100, dtype=torch.long)
+            pick = torch.rand(batch, seq, generator=g) < 0.15
+            labels[pick] = ids[pick]
+            sop = torch.randint(0, 2, (batch,), generator=g)
+            item = {'input_ids': ids, 'attention_mask': mask, 'token_type_ids': tt, 'labels': labels, 'sentence_order_label': sop}
+            if device is not None:
+                item = {k: v.to(device) for k, v in item.items()}
+            elif torch.cuda.is_available():
+                item = {k: v.pin_memory() for k, v in item.items()}
+            self.items.append(item)
+
+    def __len__(self):
+        return len(self.items)
+
+    def __iter__(self):
+        while True:
+            for it in self.items:
+                yield it
+
+    def input_bytes(self):
+        it = self.items[0]
+        return sum(v.numel() * v.element_size() for v in it.values())
+
+
+class SyntheticImages:
+    def __init__(self, n, batch, classes, device=None, seed=0, dtype=None):
+        import torch
+        g = torch.Generator().manual_seed(seed)
+        self.items = []
+        for _ in range(n):
+            x = torch.randn(batch, 3, 224, 224, generator=g)
+            y = torch.randint(0, classes, (batch,), generator=g)
+            if device is not None:
+                x, y = x.to(device), y.to(device)
+            elif torch.cuda.is_available():
+                x, y = x.pin_memory(), y.pin_memory()
+            self.items.append((x, y))
+
+    def __len__(self):
+        return len(self.items)
+
+    def __iter__(self):
+        while True:
+            for it in self.items:
+                yield it
+
+    def input_bytes(self):
+        x, y = self.items[0]
+        return x.numel() * x.element_size() + y.numel() * y.element_size()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        reference_unavailable()
+        return 0
+    import torch
+    import torch.distributed as dist
+    import ravnest_b200 as rv
+    from ravnest_b200 import ops
+    from ravnest_b200.runtime.dist_transport import init_distributed
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world != args.gpus:
+        if args.gpus > 1 and 'RANK' not in os.environ:
+            # convenience: re-launch ourselves under torchrun
+            import subprocess
+            cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+                   '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 400)] + sys.argv
+            return subprocess.call(cmd)
+    if not torch.cuda.is_available():
+        print(json.dumps({'error': 'no CUDA device visible; bench.py needs a B200'}))
+        return 1
+    rank, world, dev = init_distributed()
+    gloo = dist.new_group(backend='gloo') if world > 1 else None
+    if args.impl == 'baseline':
+        ops.set_backend('torch')
+    rv.set_seed(1234 + 0)
+    torch.backends.cudnn.deterministic = False
+    torch.backends.cudnn.benchmark = True
+
+    stages, replicas = topology_for(args.model, world)
+    home = os.environ.get('RAVNEST_HOME') or os.path.join(tempfile.gettempdir(), 'rvn_bench_{}'.format(os.environ.get('MASTER_PORT', '0')))
+    os.environ['RAVNEST_HOME'] = home
+    model, ex_args, ex_kwargs, batch = build_model(args)
+    if rank == 0:
+        os.makedirs(home, exist_ok=True)
+        props = None
+        if args.model == 'bert' and stages == 2:
+            props = [0.42, 0.58]            # leaf owns the (untied) 23.4 M decoder matrix: balance FLOPs, not params
+        rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
+                      node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props)
+    if world > 1:
+        dist.barrier(group=gloo)
+    del model
+
+    cfg = rv.load_node_json_configs('node_{}'.format(rank), base_dir=home)
+    replica = cfg['rank']
+    fused = args.impl == 'native'
+    if args.model == 'bert':
+        upd = args.update_frequency or 16
+        pool_dev = SyntheticBert(4, batch, 512, 30522, device=dev, seed=replica)
+        pool_host = SyntheticBert(4, batch, 512, 30522, device=None, seed=replica)
+
+        def criterion(outputs, targets):
+            t = targets
+            if not t['labels'].is_cuda:
+                t = {k: v.to(dev, non_blocking=True) for k, v in t.items() if k in ('labels', 'sentence_order_label')}
+            return rv.models.bert_pretraining_loss(outputs, t['labels'], t['sentence_order_label']) / upd
+
+        node_kwargs = dict(optimizer=rv.Lamb, optimizer_params={'lr': 1.76e-3, 'eps': 1e-6, 'weight_decay': 0.01,
+                                                                'clamp_value': 10000.0, 'debias': True},
+                           update_frequency=upd, dtype=torch.bfloat16)
+        feed = lambda node, item: node.forward_compute(input_ids=item['input_ids'], attention_mask=item['attention_mask'],
+                                                       token_type_ids=item['token_type_ids'])
+        metric, unit = 'bert_base_pretraining_samples_per_sec', 'samples/s'
+    else:
+        upd = args.update_frequency or 1
+        pool_dev = SyntheticImages(2, batch, 200, device=dev, seed=replica)
+        pool_host = SyntheticImages(2, batch, 200, device=None, seed=replica)
+        loss_fct = torch.nn.CrossEntropyLoss()
+
+        def criterion(outputs, targets):
+            return loss_fct(outputs.float(), targets[1].to(dev, non_blocking=True))
+
+        node_kwargs = dict(optimizer=torch.optim.SGD, optimizer_params={'lr': 0.01, 'momentum': 0.9, 'weight_decay': 5e-4},
+                           update_frequency=upd, dtype=torch.bfloat16)
+        feed = lambda node, item: node.forward_compute(tensors=item[0])
+        metric, unit = 'resnet50_images_per_sec', 'images/s'
+
+    labels = {'dev': iter(pool_dev), 'host': iter(pool_host)}
+
+    class Labels:                   # leaf/solo label source switches together with the input source
+        mode = 'dev'
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            return next(labels[Labels.mode])
+
+        def __len__(self):
+            return 1 << 30
+
+    node = rv.Node(name='node_{}'.format(rank), criterion=criterion, labels=Labels(), device=dev, base_dir=home,
+                   reduce_factor=1 << 30, dp_mode='gradient', fused_optimizer=fused, loss_filename=None,
+                   recompute=False, **node_kwargs)
+    driver = node.node_type in ('root', 'solo')
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(group=gloo)
+        torch.cuda.synchronize(dev)
+
+    def run(steps, mode, readback):
+        Labels.mode = mode
+        node.compute_session.loss_readback = readback
+        src = iter(pool_dev if mode == 'dev' else pool_host)
+        if driver:
+            for _ in range(steps):
+                feed(node, next(src))
+            node.wait_for_backwards()
+        sync()
+
+    def timed(steps, mode, readback):
+        sync()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = node.compute_stream
+        start.record(stream)
+        t0 = time.time()
+        run(steps, mode, readback)
+        end.record(stream)
+        torch.cuda.synchronize(dev)
+        wall = time.time() - t0
+        ms = torch.tensor([start.elapsed_time(end), wall * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    run(max(3, args.warmup), 'dev', False)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    dev_ms, dev_wall = timed(args.steps, 'dev', False)
+    clocks = sampler.summary()
+    result = None
+    e2e = None
+    if not args.no_e2e:
+        run(3, 'host', True)
+        e2e_ms, e2e_wall = timed(args.steps, 'host', True)
+        e2e = {'value': replicas * batch * args.steps / (max(e2e_ms, e2e_wall) / 1e3), 'unit': unit,
+               'h2d_bytes_per_step': pool_host.input_bytes(), 'd2h_bytes_per_step': 4, 'ms_per_step': max(e2e_ms, e2e_wall) / args.steps}
+    launches = count_launches(node, feed, pool_dev, driver, sync, Labels) if rank == 0 or world > 1 else None
+    if rank == 0:
+        value = replicas * batch * args.steps / (dev_ms / 1e3)
+        result = {
+            'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic (random tokens/images of the benchmark shape; random-init weights)',
+            'impl': args.impl,
+            'config': {'model': 'bert-base-uncased BertForPreTraining (110.1M)' if args.model == 'bert' else 'resnet50(num_classes=200)',
+                       'global_batch': replicas * batch, 'per_replica_batch': batch, 'seq_len': 512 if args.model == 'bert' else None,
+                       'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': 'LAMB' if args.model == 'bert' else 'SGD-momentum',
+                       'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)',
+                       'l2': 'working set (weights+activations, >1 GB/step) exceeds the 126 MB L2; no explicit flush'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'wall_ms_per_step': dev_wall / args.steps,
+        }
+        if args.layers:
+            result['invalid'] = 'debug run with --layers'
+        print(json.dumps(result))
+    sync()
+    if driver:
+        node.stop()
+    node._stop.wait(20)
+    time.sleep(0.2)
+    if world > 1:
+        dist.barrier(group=gloo)
+        dist.destroy_process_group()
+    return 0
+
+
+def count_launches(node, feed, pool, driver, sync, Labels):
+    """Kernels whose name starts with ``rvn_`` (ours) launched by ONE step on this rank, via the
+    torch profiler — outside the timed region."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    Labels.mode = 'dev'
+    try:
+        sync()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            if driver:
+                feed(node, next(iter(pool)))
+                node.wait_for_backwards()
+            sync()
+        mine = total = 0
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                total += 1
+                if 'rvn_' in ev.name:
+                    mine += 1
+        return {'ours_per_step': mine, 'all_per_step': total}
+    except Exception as err:
+        return {'error': repr(err)}
+
+
+if __name__ == '__main__':
+    sys.exit(main())

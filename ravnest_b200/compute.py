@@ -86,6 +86,9 @@ class Compute:
         self.lr_scheduler = None
         self._fused = None
         self._average_grads = bool(average_grads_over_dp)
+        self.loss_readback = False          # copy every step's loss to pinned host memory (async D2H)
+        self._loss_host = None
+        self.loss_history: List[Any] = []
         if optimizer_cls is not None:
             self._build_optimizer(optimizer_cls, dict(optimizer_params or {}), fused_optimizer, average_grads_over_dp)
             if lr_scheduler is not None:
@@ -231,6 +234,12 @@ class Compute:
             in_grads = [a.grad if isinstance(a, torch.Tensor) and a.requires_grad else None for a in inputs]
             det = loss.detach()
             self.last_loss = det
+            if self.loss_readback and det.is_cuda:
+                if self._loss_host is None:
+                    self._loss_host = torch.empty(64, dtype=torch.float32, pin_memory=True)
+                    self._loss_slot = 0
+                self._loss_host[self._loss_slot % 64].copy_(det.float(), non_blocking=True)
+                self._loss_slot += 1
             self._loss_acc = det.clone() if self._loss_acc is None else self._loss_acc.add_(det)
             updated = self._after_backward(update)
             if updated:

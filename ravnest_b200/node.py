@@ -154,6 +154,9 @@ class Node:
         self._saved = threading.Event()
         self._stop = threading.Event()
         self.metrics = {'forward': 0, 'backward': 0, 'updates': 0, 'reduces': 0}
+        self.compute_stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
+        if self.compute_stream is not None:
+            self.compute_stream.wait_stream(torch.cuda.current_stream(self.device))   # init work is done
         self.start()
 
     # ------------------------------------------------------------------ lifecycle
@@ -175,17 +178,23 @@ class Node:
         forward; the leaf remaps FORWARD->FIND_LOSS and NO_GRAD_FORWARD->output_type."""
         if self.device.type == 'cuda':
             torch.cuda.set_device(self.device)
+            # dedicated compute stream: collectives / barriers issued by the user's main thread on the
+            # legacy default stream can never stall stage compute (and vice versa)
+            torch.cuda.set_stream(self.compute_stream)
         while not self._stop.is_set():
             item = self.mailbox.get(timeout=0.25)
             if item is None:
                 continue
             _lane, msg = item
+            if '_ready_event' in msg:
+                self.transport.adopt(msg, self.device)
             action = msg['action']
             if self.is_last and action == ActionTypes.FORWARD:
                 action = ActionTypes.FIND_LOSS
             elif self.is_last and action == ActionTypes.NO_GRAD_FORWARD and self.node_type != NodeTypes.SOLO:
                 action = msg.get('output_type') or ActionTypes.VAL_ACCURACY
             if action == ActionTypes.SHUTDOWN:
+                threading.Thread(target=self.stop, daemon=True).start()
                 break
             try:
                 getattr(self, action)(msg)
@@ -242,13 +251,15 @@ class Node:
         what the leaf does with the result: 'val_accuracy' | 'accuracy' | 'prediction'."""
         self._check()
         args = self._pack_inputs(tensors, kwargs)
-        if self.node_type == NodeTypes.SOLO:
+        ctx = torch.cuda.stream(self.compute_stream) if self.compute_stream is not None else _NullCtx()
+        with ctx:       # same stream as the scheduler: ordered after every queued optimizer update
+            if self.node_type == NodeTypes.SOLO:
+                out = self.compute_session.no_grad_forward(args)
+                return self._consume_inference(out, output_type)
+            self.status = NodeStatus.FORWARD
             out = self.compute_session.no_grad_forward(args)
-            return self._consume_inference(out, output_type)
-        self.status = NodeStatus.FORWARD
-        out = self.compute_session.no_grad_forward(args)
-        data = self.plan.root_payload(out, args, self.compression)
-        self.transport.send(FORWARD, make_message(ActionTypes.NO_GRAD_FORWARD, -1, data, output_type=output_type))
+            data = self.plan.root_payload(out, args, self.compression)
+            self.transport.send(FORWARD, make_message(ActionTypes.NO_GRAD_FORWARD, -1, data, output_type=output_type))
         self.status = NodeStatus.IDLE
         return None
 
@@ -467,6 +478,14 @@ class Node:
         aux = os.path.join(self.base_dir, '{}_aux'.format(self.name))
         if os.path.isdir(aux):
             shutil.rmtree(aux)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 class _TensorLabels:

@@ -1,0 +1,136 @@
+"""Hot-op dispatch: hand-written sm_100a kernels on CUDA, plain PyTorch reference elsewhere.
+
+``backend()`` is ``'native'`` by default: CUDA tensors go to the kernels in ``ops/csrc`` (loaded
+from the in-tree extension ``ravnest_b200/ops/_C*.so``) and a missing extension is a hard error —
+a GPU box must never fall back silently.  ``set_backend('torch')`` selects the stock
+cuBLAS/cuDNN/ATen path: that is the BASELINE TIER the product is measured against.
+
+Every op has ``reference_<op>`` (fp32-accurate PyTorch math) used by the CPU path and by the GPU
+numerics tests.
+"""
+import math
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+_BACKEND = os.environ.get('RAVNEST_OPS_BACKEND', 'native')
+
+
+def set_backend(name: str) -> None:
+    global _BACKEND
+    assert name in ('native', 'torch')
+    _BACKEND = name
+
+
+def backend() -> str:
+    return _BACKEND
+
+
+def _native(*tensors) -> bool:
+    return _BACKEND == 'native' and all(t is None or t.is_cuda for t in tensors)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference implementations
+# ----------------------------------------------------------------------------------------------
+def _act(y, activation):
+    if activation is None:
+        return y
+    if activation == 'gelu':
+        return F.gelu(y)
+    if activation == 'gelu_tanh':
+        return F.gelu(y, approximate='tanh')
+    if activation == 'relu':
+        return F.relu(y)
+    raise ValueError(activation)
+
+
+def reference_linear(x, weight, bias=None, activation=None):
+    return _act(F.linear(x, weight, bias), activation)
+
+
+def reference_layer_norm(x, weight, bias, eps=1e-5, residual=None):
+    if residual is not None:
+        x = x + residual
+    return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+def reference_embedding(idx, weight):
+    return F.embedding(idx, weight)
+
+
+def reference_attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
+    """qkv: [B, S, 3H] packed (q | k | v); returns [B, S, H]."""
+    B, S, H3 = qkv.shape
+    H = H3 // 3
+    D = H // heads
+    q, k, v = qkv.split(H, dim=-1)
+    q = q.view(B, S, heads, D).transpose(1, 2)
+    k = k.view(B, S, heads, D).transpose(1, 2)
+    v = v.view(B, S, heads, D).transpose(1, 2)
+    att = (q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(D))
+    if causal:
+        mask = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+        att = att.masked_fill(~mask, float('-inf'))
+    if key_padding_mask is not None:
+        att = att.masked_fill(~key_padding_mask.bool()[:, None, None, :], float('-inf'))
+    att = torch.softmax(att.float(), dim=-1).to(qkv.dtype)
+    if dropout_p > 0.0:
+        att = F.dropout(att, dropout_p, True)
+    y = att @ v
+    return y.transpose(1, 2).reshape(B, S, H)
+
+
+def reference_cross_entropy(logits, target, ignore_index=-100):
+    return F.cross_entropy(logits.float(), target, ignore_index=ignore_index)
+
+
+# ----------------------------------------------------------------------------------------------
+# public ops
+# ----------------------------------------------------------------------------------------------
+def linear(x, weight, bias=None, activation=None):
+    if _native(x, weight):
+        from . import native
+        return native.linear(x, weight, bias, activation)
+    return reference_linear(x, weight, bias, activation)
+
+
+def layer_norm(x, weight, bias, eps=1e-5, residual=None):
+    if _native(x, weight):
+        from . import native
+        return native.layer_norm(x, weight, bias, eps, residual)
+    return reference_layer_norm(x, weight, bias, eps, residual)
+
+
+def embedding(idx, weight):
+    return reference_embedding(idx, weight)
+
+
+def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
+    if _native(qkv):
+        from . import native
+        return native.attention_qkv(qkv, heads, key_padding_mask, causal, dropout_p)
+    return reference_attention_qkv(qkv, heads, key_padding_mask, causal, dropout_p)
+
+
+def cross_entropy(logits, target, ignore_index=-100):
+    if _native(logits):
+        from . import native
+        return native.cross_entropy(logits, target, ignore_index)
+    return reference_cross_entropy(logits, target, ignore_index)
+
+
+def native_ops_loaded():
+    """Names of native kernels that have actually been launched in this process."""
+    try:
+        from . import native
+        return dict(native.calls)
+    except Exception:
+        return {}
+
+
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
+           'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
+           'reference_cross_entropy']

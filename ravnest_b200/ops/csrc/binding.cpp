@@ -1,0 +1,276 @@
+// pybind11 glue between torch tensors and the extern "C" kernel launchers (compiled by nvcc without torch headers).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime.h>
+#include <torch/extension.h>
+
+#include <vector>
+
+extern "C" {
+int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
+                  const void* bias, int act, const void* dact_in, int ld_dact, void* preact_out, int ld_preact, int block_n,
+                  int num_sms, cudaStream_t stream);
+int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
+                          float* rstd, int rows, int H, float eps, cudaStream_t stream);
+int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
+                           float* dgamma, float* dbeta, int rows, int H, int num_sms, cudaStream_t stream);
+int rvn_ce_forward(const void* logits, int ld, const int64_t* target, float* lse, float* stats, float* loss, int rows, int V,
+                   int64_t ignore_index, cudaStream_t stream);
+int rvn_ce_backward(const void* logits, int ld, const int64_t* target, const float* lse, const float* stats, const float* gscale,
+                    void* dlogits, int ld_out, int rows, int V, int64_t ignore_index, cudaStream_t stream);
+int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, cudaStream_t stream);
+int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
+}
+
+struct PeerPtrs {
+  const void* grad[8];
+  uint32_t* signal[8];
+  int n;
+  int rank;
+};
+struct OptArgs {
+  float lr, beta1, beta2, eps, weight_decay, momentum, dampening;
+  float grad_scale;
+  float bias_c1, bias_c2;
+  float clamp_value;
+  int nesterov, first_step, decoupled_wd, lamb_adam_mode;
+};
+
+extern "C" {
+int rvn_fused_update(const PeerPtrs* pp, const OptArgs* a, int kind, float* master, float* m, float* v, void* w_out, int grad_is_bf16,
+                     int out_is_bf16, size_t n, uint32_t epoch, uint32_t* done_counter, int num_sms, cudaStream_t stream);
+int rvn_fused_lamb(const PeerPtrs* pp, const OptArgs* a, float* master, float* m, float* v, void* w_out, int grad_is_bf16,
+                   int out_is_bf16, const int* chunk_param, const long long* chunk_start, const long long* chunk_end, int n_chunks,
+                   float* norms, int n_params, uint32_t epoch, uint32_t* done_counter, cudaStream_t stream);
+int rvn_fused_param_average(const PeerPtrs* pp, float* master_out, void* w_out, int out_is_bf16, size_t n, uint32_t epoch,
+                            uint32_t* done_counter, int num_sms, cudaStream_t stream);
+}
+
+namespace {
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
+}
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+void check(int code, const char* what) {
+  TORCH_CHECK(code == 0, "ravnest_b200 kernel launch failed: ", what, " (code ", code, ")");
+}
+
+int ld_of(const torch::Tensor& t) {
+  TORCH_CHECK(t.dim() == 2 && t.stride(1) == 1, "expected a 2-D tensor with unit inner stride");
+  TORCH_CHECK(t.stride(0) % 8 == 0 || t.size(0) == 1, "row stride must be a multiple of 8 elements (16 B) for TMA");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0, "tensor base must be 16-byte aligned");
+  return static_cast<int>(t.stride(0));
+}
+
+// D[M,N] = epi(op(A) * op(B)^T).  A: [M,K] (a_mn=false) or [K,M] (a_mn=true); B: [N,K] (b_mn=false) or [K,N] (b_mn=true).
+// Returns {D} or {D, preact}.  D is allocated with a row stride rounded up to 8 elements; a narrowed view is returned.
+std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::Tensor& B, bool b_mn,
+                                const c10::optional<torch::Tensor>& bias, int64_t act,
+                                const c10::optional<torch::Tensor>& dact_in, bool store_preact, int64_t block_n) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16,
+              "gemm expects CUDA bf16 operands");
+  c10::cuda::CUDAGuard guard(A.device());
+  const int M = a_mn ? A.size(1) : A.size(0);
+  const int K = a_mn ? A.size(0) : A.size(1);
+  const int N = b_mn ? B.size(1) : B.size(0);
+  TORCH_CHECK((b_mn ? B.size(0) : B.size(1)) == K, "inner dimensions differ");
+  const int lda = ld_of(A), ldb = ld_of(B);
+  const int ldd = (N + 7) / 8 * 8;
+  auto D = torch::empty({M, ldd}, A.options());
+  torch::Tensor P;
+  const void* bias_ptr = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->is_contiguous() && bias->numel() == N, "bad bias");
+    TORCH_CHECK(N % 8 == 0 || true, "");
+    bias_ptr = bias->data_ptr();
+  }
+  const void* dact_ptr = nullptr;
+  int ld_dact = 0;
+  if (dact_in.has_value() && dact_in->defined()) {
+    TORCH_CHECK(dact_in->size(0) == M && dact_in->size(1) == N, "dact_in must be [M,N]");
+    ld_dact = ld_of(*dact_in);
+    dact_ptr = dact_in->data_ptr();
+  }
+  void* preact_ptr = nullptr;
+  if (store_preact) {
+    P = torch::empty({M, ldd}, A.options());
+    preact_ptr = P.data_ptr();
+  }
+  if (block_n <= 0) {
+    // tile-shape heuristic: 128x256 tiles halve smem traffic per FLOP; take them when they still fill the machine
+    const int64_t tiles256 = static_cast<int64_t>((M + 127) / 128) * ((N + 255) / 256);
+    block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
+  }
+  check(rvn_gemm_bf16(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
+                      dact_ptr, ld_dact, preact_ptr, ldd, static_cast<int>(block_n), sm_count(), cur_stream()),
+        "gemm_bf16");
+  std::vector<torch::Tensor> out;
+  out.push_back(ldd == N ? D : D.narrow(1, 0, N));
+  if (store_preact) out.push_back(ldd == N ? P : P.narrow(1, 0, N));
+  return out;
+}
+
+std::vector<torch::Tensor> layernorm_fwd(const torch::Tensor& x, const c10::optional<torch::Tensor>& res, const torch::Tensor& gamma,
+                                         const torch::Tensor& beta, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kBFloat16, "layernorm expects contiguous bf16");
+  const int H = x.size(-1);
+  const int rows = x.numel() / H;
+  auto y = torch::empty_like(x);
+  auto mean = torch::empty({rows}, x.options().dtype(torch::kFloat32));
+  auto rstd = torch::empty({rows}, x.options().dtype(torch::kFloat32));
+  torch::Tensor sum;
+  const void* res_ptr = nullptr;
+  void* sum_ptr = nullptr;
+  if (res.has_value() && res->defined()) {
+    TORCH_CHECK(res->is_contiguous() && res->sizes() == x.sizes(), "residual must match x");
+    sum = torch::empty_like(x);
+    res_ptr = res->data_ptr();
+    sum_ptr = sum.data_ptr();
+  }
+  check(rvn_layernorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), sum_ptr,
+                              mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, H, static_cast<float>(eps), cur_stream()),
+        "layernorm_fwd");
+  if (sum.defined()) return {y, mean, rstd, sum};
+  return {y, mean, rstd};
+}
+
+std::vector<torch::Tensor> layernorm_bwd(const torch::Tensor& dy, const torch::Tensor& x, const torch::Tensor& gamma,
+                                         const torch::Tensor& mean, const torch::Tensor& rstd) {
+  c10::cuda::CUDAGuard guard(x.device());
+  const int H = x.size(-1);
+  const int rows = x.numel() / H;
+  auto dx = torch::empty_like(x);
+  auto dgamma = torch::zeros({H}, x.options().dtype(torch::kFloat32));
+  auto dbeta = torch::zeros({H}, x.options().dtype(torch::kFloat32));
+  check(rvn_layernorm_backward(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                               dx.data_ptr(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), rows, H, sm_count(), cur_stream()),
+        "layernorm_bwd");
+  return {dx, dgamma, dbeta};
+}
+
+// returns {loss (scalar fp32), lse [rows], stats [2]}
+std::vector<torch::Tensor> ce_fwd(const torch::Tensor& logits, const torch::Tensor& target, int64_t ignore_index) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(logits.dim() == 2 && logits.stride(1) == 1 && logits.scalar_type() == torch::kBFloat16, "ce expects 2-D bf16 logits");
+  TORCH_CHECK(logits.stride(0) % 8 == 0 && reinterpret_cast<uintptr_t>(logits.data_ptr()) % 16 == 0, "logit rows must be 16 B aligned");
+  const int rows = logits.size(0), V = logits.size(1);
+  auto f32 = logits.options().dtype(torch::kFloat32);
+  auto lse = torch::empty({rows}, f32);
+  auto stats = torch::zeros({2}, f32);
+  auto loss = torch::empty({}, f32);
+  check(rvn_ce_forward(logits.data_ptr(), logits.stride(0), target.data_ptr<int64_t>(), lse.data_ptr<float>(), stats.data_ptr<float>(),
+                       loss.data_ptr<float>(), rows, V, ignore_index, cur_stream()),
+        "ce_fwd");
+  return {loss, lse, stats};
+}
+
+torch::Tensor ce_bwd(const torch::Tensor& logits, const torch::Tensor& target, const torch::Tensor& lse, const torch::Tensor& stats,
+                     const torch::Tensor& gscale, int64_t ignore_index) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int rows = logits.size(0), V = logits.size(1);
+  const int ld_out = (V + 7) / 8 * 8;
+  auto d = torch::empty({rows, ld_out}, logits.options());
+  check(rvn_ce_backward(logits.data_ptr(), logits.stride(0), target.data_ptr<int64_t>(), lse.data_ptr<float>(), stats.data_ptr<float>(),
+                        gscale.data_ptr<float>(), d.data_ptr(), ld_out, rows, V, ignore_index, cur_stream()),
+        "ce_bwd");
+  return ld_out == V ? d : d.narrow(1, 0, V);
+}
+
+torch::Tensor column_sum(const torch::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == torch::kBFloat16, "column_sum expects 2-D bf16");
+  auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
+  check(rvn_column_sum(x.data_ptr(), x.stride(0), out.data_ptr<float>(), x.size(0), x.size(1), cur_stream()), "column_sum");
+  return out;
+}
+
+torch::Tensor act_bwd(const torch::Tensor& dy, const torch::Tensor& z, int64_t act) {
+  c10::cuda::CUDAGuard guard(dy.device());
+  TORCH_CHECK(dy.is_contiguous() && z.is_contiguous() && dy.numel() == z.numel(), "act_bwd expects contiguous same-size tensors");
+  auto dz = torch::empty_like(dy);
+  check(rvn_activation_backward(dy.data_ptr(), z.data_ptr(), dz.data_ptr(), dy.numel(), static_cast<int>(act), sm_count(), cur_stream()),
+        "act_bwd");
+  return dz;
+}
+
+// ---------------------------------------------------------------------------------------------- fused optimizers
+PeerPtrs make_peers(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank) {
+  PeerPtrs pp{};
+  TORCH_CHECK(grad_ptrs.size() >= 1 && grad_ptrs.size() <= 8, "1..8 DP peers supported");
+  pp.n = static_cast<int>(grad_ptrs.size());
+  pp.rank = static_cast<int>(rank);
+  for (int i = 0; i < pp.n; ++i) {
+    pp.grad[i] = reinterpret_cast<const void*>(grad_ptrs[i]);
+    pp.signal[i] = i < static_cast<int>(signal_ptrs.size()) ? reinterpret_cast<uint32_t*>(signal_ptrs[i]) : nullptr;
+  }
+  return pp;
+}
+
+OptArgs make_args(const std::vector<double>& f, const std::vector<int64_t>& flags) {
+  OptArgs a{};
+  a.lr = f[0]; a.beta1 = f[1]; a.beta2 = f[2]; a.eps = f[3]; a.weight_decay = f[4]; a.momentum = f[5]; a.dampening = f[6];
+  a.grad_scale = f[7]; a.bias_c1 = f[8]; a.bias_c2 = f[9]; a.clamp_value = f[10];
+  a.nesterov = flags[0]; a.first_step = flags[1]; a.decoupled_wd = flags[2]; a.lamb_adam_mode = flags[3];
+  return a;
+}
+
+void fused_update(int64_t kind, const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank,
+                  const std::vector<double>& f, const std::vector<int64_t>& flags, torch::Tensor master, torch::Tensor m,
+                  torch::Tensor v, torch::Tensor w_out, bool grad_is_bf16, int64_t epoch, torch::Tensor done_counter) {
+  c10::cuda::CUDAGuard guard(master.device());
+  PeerPtrs pp = make_peers(grad_ptrs, signal_ptrs, rank);
+  OptArgs a = make_args(f, flags);
+  check(rvn_fused_update(&pp, &a, static_cast<int>(kind), master.data_ptr<float>(), m.defined() && m.numel() ? m.data_ptr<float>() : nullptr,
+                         v.defined() && v.numel() ? v.data_ptr<float>() : nullptr, w_out.data_ptr(), grad_is_bf16,
+                         w_out.scalar_type() == torch::kBFloat16, static_cast<size_t>(master.numel()), static_cast<uint32_t>(epoch),
+                         reinterpret_cast<uint32_t*>(done_counter.data_ptr()), sm_count(), cur_stream()),
+        "fused_update");
+}
+
+void fused_lamb(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank, const std::vector<double>& f,
+                const std::vector<int64_t>& flags, torch::Tensor master, torch::Tensor m, torch::Tensor v, torch::Tensor w_out,
+                bool grad_is_bf16, torch::Tensor chunk_param, torch::Tensor chunk_start, torch::Tensor chunk_end, torch::Tensor norms,
+                int64_t epoch, torch::Tensor done_counter) {
+  c10::cuda::CUDAGuard guard(master.device());
+  PeerPtrs pp = make_peers(grad_ptrs, signal_ptrs, rank);
+  OptArgs a = make_args(f, flags);
+  check(rvn_fused_lamb(&pp, &a, master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), w_out.data_ptr(), grad_is_bf16,
+                       w_out.scalar_type() == torch::kBFloat16, chunk_param.data_ptr<int>(),
+                       reinterpret_cast<const long long*>(chunk_start.data_ptr<int64_t>()),
+                       reinterpret_cast<const long long*>(chunk_end.data_ptr<int64_t>()), static_cast<int>(chunk_param.numel()),
+                       norms.data_ptr<float>(), static_cast<int>(norms.numel() / 2), static_cast<uint32_t>(epoch),
+                       reinterpret_cast<uint32_t*>(done_counter.data_ptr()), cur_stream()),
+        "fused_lamb");
+}
+
+void fused_param_average(const std::vector<int64_t>& src_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank, torch::Tensor master_out,
+                         torch::Tensor w_out, int64_t epoch, torch::Tensor done_counter) {
+  c10::cuda::CUDAGuard guard(master_out.device());
+  PeerPtrs pp = make_peers(src_ptrs, signal_ptrs, rank);
+  check(rvn_fused_param_average(&pp, master_out.data_ptr<float>(), w_out.data_ptr(), w_out.scalar_type() == torch::kBFloat16,
+                                static_cast<size_t>(master_out.numel()), static_cast<uint32_t>(epoch),
+                                reinterpret_cast<uint32_t*>(done_counter.data_ptr()), sm_count(), cur_stream()),
+        "fused_param_average");
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("gemm", &gemm, "bf16 tcgen05 GEMM with fused epilogue");
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("ce_fwd", &ce_fwd);
+  m.def("ce_bwd", &ce_bwd);
+  m.def("column_sum", &column_sum);
+  m.def("act_bwd", &act_bwd);
+  m.def("fused_update", &fused_update);
+  m.def("fused_lamb", &fused_lamb);
+  m.def("fused_param_average", &fused_param_average);
+}

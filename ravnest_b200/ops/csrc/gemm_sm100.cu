@@ -1,0 +1,398 @@
+// K3: bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, cta_group::1, UMMA 128 x BN x 16), operands staged in
+// shared memory by TMA (128B swizzle), fp32 accumulators in TMEM (double-buffered so the epilogue of tile i
+// overlaps the MMAs of tile i+1), persistent CTAs (one per SM), warp-specialised:
+//   warp 0 : TMA producer      warp 1 : MMA issuer (one elected lane)     warp 2 : TMEM allocator
+//   warps 4-7 : epilogue  (tcgen05.ld -> bias / activation / activation-gradient -> bf16 -> swizzled smem -> TMA store)
+//
+//   D[M,N] = epi( A * B ),  A is M x K, B is N x K ("K-major", row-major [rows, K]) or their transposes stored
+//   row-major [K, rows] ("MN-major") — so forward (x W^T), dgrad (dY W) and wgrad (dY^T x) all run on the same
+//   kernel without materialising a transpose.
+//
+// Reference call sites this replaces: every nn.Linear fwd/dgrad/wgrad of the BERT / GPT / CNN / fc layers
+//  which upstream go through cuBLAS via torch 2.2.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sm100_ptx.cuh"
+
+namespace rvn {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int SLAB_N = 64;           // epilogue staging slab: 128 rows x 64 cols bf16 = 16 KB
+constexpr int SLAB_BYTES = BLOCK_M * SLAB_N * 2;
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_TANH = 2, ACT_RELU = 3 };
+
+struct GemmParams {
+  int M, N, K;
+  const __nv_bfloat16* bias;      // [N] or nullptr
+  const __nv_bfloat16* dact_in;   // [M, ld_aux] pre-activation (dact mode: D = acc * act'(z)) or nullptr
+  int ld_aux;
+  int act;                        // Act
+  int store_preact;               // also write the pre-activation through map_aux
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int OPERAND_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = 2 * SLAB_BYTES;
+  static constexpr int BAR_OFFSET = OPERAND_BYTES + STAGING_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + slack for manual 1024 B alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float dgelu_tanh(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = tanhf(u);
+  const float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case ACT_GELU: return gelu_erf(x);
+    case ACT_GELU_TANH: return gelu_tanh(x);
+    case ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float apply_dact(float z, int act) {
+  switch (act) {
+    case ACT_GELU: return dgelu_erf(z);
+    case ACT_GELU_TANH: return dgelu_tanh(z);
+    case ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
+                      const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;                 // two accumulator stages (256 or 512 columns)
+  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + L::OPERAND_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_d);
+    if (p.store_preact) tma_prefetch_desc(&map_aux);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], EPI_THREADS / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
+        const int n0 = (tile / p.num_m_blocks) * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);                 // box {64 (K), 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)                             // box {64 (M), 64 K-rows} per atom column
+              tma_load_2d(sa + j * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + j * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);                 // box {64 (K), BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BLOCK_K * 128), &map_b, &full_bar[stage], n0 + j * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major : atoms are 8 rows x 128 B, SBO = 1024 B between 8-row groups, advance 32 B per UMMA_K
+            // MN-major: atoms are 8 K-rows x 128 B (64 MN elements), SBO = 1024 B along K, LBO = BLOCK_K*128 B along MN,
+            //           advance 2 atoms (2048 B) per UMMA_K
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
+          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue (128 threads, one row each)
+    const int ewarp = warp - 4;                 // TMEM lane quadrant == warp index % 4
+    const int row_in_tile = ewarp * 32 + lane_id();
+    const bool issuer = threadIdx.x == 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t slab_counter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
+      const int n0 = (tile / p.num_m_blocks) * BN;
+      const int grow = m0 + row_in_tile;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int slab = 0; slab < BN / SLAB_N; ++slab) {
+        const int col0 = n0 + slab * SLAB_N;
+        if (col0 >= p.N) break;                                   // whole slab out of range (N tail)
+        uint8_t* buf_main = staging + (p.store_preact ? 0 : (slab_counter & 1)) * SLAB_BYTES;
+        uint8_t* buf_aux = staging + SLAB_BYTES;
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (issuer) {
+          if (p.store_preact) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BN + slab * SLAB_N + half * 32;
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
+          const int c_base = col0 + half * 32;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (c_base + i < p.N) {      // N is a multiple of 8 (16 B rows), so 8-wide groups are all-in or all-out
+                const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(p.bias + c_base + i));
+                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 bf = __bfloat1622float2(b2[j]);
+                  f[i + 2 * j] += bf.x;
+                  f[i + 2 * j + 1] += bf.y;
+                }
+              }
+            }
+          }
+          if (p.store_preact) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const int chunk = half * 4 + (i >> 3);
+              uint4 o;
+              o.x = pack_bf16x2(f[i], f[i + 1]); o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+              o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+              *reinterpret_cast<uint4*>(buf_aux + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = o;
+            }
+          }
+          if (p.dact_in != nullptr) {
+            if (grow < p.M) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (c_base + i < p.N) {
+                  const uint4 z4 = __ldg(reinterpret_cast<const uint4*>(p.dact_in + static_cast<size_t>(grow) * p.ld_aux + c_base + i));
+                  const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&z4);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 zf = __bfloat1622float2(z2[j]);
+                    f[i + 2 * j] *= apply_dact(zf.x, p.act);
+                    f[i + 2 * j + 1] *= apply_dact(zf.y, p.act);
+                  }
+                }
+              }
+            }
+          } else if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], p.act);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const int chunk = half * 4 + (i >> 3);       // 16-byte chunk index inside the 128-byte slab row
+            uint4 o;
+            o.x = pack_bf16x2(f[i], f[i + 1]); o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+            o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+            *reinterpret_cast<uint4*>(buf_main + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = o;
+          }
+        }
+        if (slab == BN / SLAB_N - 1 || col0 + SLAB_N >= p.N) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, EPI_THREADS);
+        if (issuer) {
+          tma_store_2d(&map_d, buf_main, col0, m0);
+          if (p.store_preact) tma_store_2d(&map_aux, buf_aux, col0, m0);
+          tma_store_commit();
+        }
+        ++slab_counter;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (err != cudaSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2D bf16 tensor map: ``inner`` contiguous elements, ``outer`` rows with ``ld`` elements between rows.
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return -1;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, void* aux_out, int ld_auxout,
+                  GemmParams p, int num_sms, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  CUtensorMap ma, mb, md, mx;
+  int e = 0;
+  // A: K-major -> [M rows, K inner]; MN-major -> stored [K rows, M inner]
+  e |= A_MN ? make_map(&ma, A, p.M, p.K, lda, 64, BLOCK_K) : make_map(&ma, A, p.K, p.M, lda, BLOCK_K, BLOCK_M);
+  e |= B_MN ? make_map(&mb, B, p.N, p.K, ldb, 64, BLOCK_K) : make_map(&mb, B, p.K, p.N, ldb, BLOCK_K, BN);
+  e |= make_map(&md, D, p.N, p.M, ldd, SLAB_N, BLOCK_M);
+  e |= make_map(&mx, aux_out ? aux_out : D, p.N, p.M, aux_out ? ld_auxout : ldd, SLAB_N, BLOCK_M);
+  if (e != 0) return 1000 + e;
+  p.num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = (p.N + BN - 1) / BN;
+  p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  auto kern = rvn_gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (ce != cudaSuccess) return 2000 + static_cast<int>(ce);
+    configured = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma, mb, md, mx, p);
+  cudaError_t le = cudaGetLastError();
+  return le == cudaSuccess ? 0 : 3000 + static_cast<int>(le);
+}
+
+}  // namespace rvn
+
+// C entry point used by binding.cpp.  Layout flags: a_mn / b_mn = operand stored [K, rows] instead of [rows, K].
+extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
+                             int K, const void* bias, int act, const void* dact_in, int ld_dact, void* preact_out,
+                             int ld_preact, int block_n, int num_sms, cudaStream_t stream) {
+  rvn::GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.dact_in = static_cast<const __nv_bfloat16*>(dact_in);
+  p.ld_aux = ld_dact;
+  p.act = act;
+  p.store_preact = preact_out != nullptr ? 1 : 0;
+#define RVN_DISPATCH(BN_)                                                                                              \
+  if (!a_mn && !b_mn) return rvn::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream); \
+  if (!a_mn && b_mn) return rvn::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream);   \
+  if (a_mn && b_mn) return rvn::launch<BN_, true, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream);     \
+  return rvn::launch<BN_, true, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream);
+  if (block_n == 256) { RVN_DISPATCH(256) }
+  RVN_DISPATCH(128)
+#undef RVN_DISPATCH
+}

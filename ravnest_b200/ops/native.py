@@ -1,0 +1,163 @@
+"""CUDA path of the hot ops: autograd Functions over the sm_100a kernels in ``rvn_C``.
+
+Layout conventions of ``rvn_C.gemm(A, a_mn, B, b_mn, bias, act, dact_in, store_preact, block_n)``:
+``D[M,N] = epi(A' B'^T)`` with A' = A ([M,K]) or A^T when ``a_mn`` (A stored [K,M]); B' = B ([N,K]) or
+B^T when ``b_mn`` (B stored [K,N]).  So for ``y = x W^T``:
+    forward  y  = gemm(x,  False, W,  False)           (both K-major)
+    dgrad    dx = gemm(dy, False, W,  True)            (W read MN-major: no transpose materialised)
+    wgrad    dW = gemm(dy, True,  x,  True)            (both MN-major)
+"""
+import math
+from collections import Counter
+
+import torch
+import torch.nn.functional as F
+
+from . import _ext
+
+_ACT = {None: 0, 'gelu': 1, 'gelu_tanh': 2, 'relu': 3}
+calls = Counter()          # op name -> number of native launches (smoke() / bench report these)
+fallbacks = Counter()      # op name -> number of times constraints forced the torch path
+
+
+def C():
+    return _ext.load()
+
+
+def _tma_ok(t: torch.Tensor) -> bool:
+    return (t.dim() == 2 and t.dtype == torch.bfloat16 and t.stride(1) == 1 and t.stride(0) % 8 == 0
+            and t.data_ptr() % 16 == 0 and t.size(0) > 0 and t.size(1) > 0)
+
+
+def _as2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    if not _tma_ok(x2):
+        x2 = x2.contiguous()
+    return x2
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, activation):
+        x2 = _as2d(x)
+        act = _ACT[activation]
+        need_pre = act != 0 and (x.requires_grad or weight.requires_grad)
+        outs = C().gemm(x2, False, weight, False, bias, act, None, need_pre, 0)
+        calls['gemm_fwd'] += 1
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(x2, weight, outs[1] if need_pre else None)
+        return outs[0].reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, z = ctx.saved_tensors
+        N = weight.shape[0]
+        dy2 = dy.reshape(-1, N)
+        if ctx.act != 0:
+            dyc = dy2 if dy2.is_contiguous() else dy2.contiguous()
+            zc = z if z.is_contiguous() else z.contiguous()
+            dy2 = C().act_bwd(dyc, zc, ctx.act)
+            calls['act_bwd'] += 1
+        if not _tma_ok(dy2):
+            dy2 = dy2.contiguous()
+            if not _tma_ok(dy2):                 # e.g. N not a multiple of 8: pad the row stride
+                pad = torch.zeros(dy2.shape[0], (N + 7) // 8 * 8, dtype=dy2.dtype, device=dy2.device)
+                pad[:, :N] = dy2
+                dy2 = pad[:, :N]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = C().gemm(dy2, False, weight, True, None, 0, None, False, 0)[0].reshape(ctx.x_shape)
+            calls['gemm_dgrad'] += 1
+        if ctx.needs_input_grad[1]:
+            dw = C().gemm(dy2, True, x2, True, None, 0, None, False, 0)[0]
+            calls['gemm_wgrad'] += 1
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = C().column_sum(dy2).to(weight.dtype)
+            calls['colsum'] += 1
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, activation=None):
+    K = x.shape[-1]
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or K % 8 != 0 or not _tma_ok(weight) or x.numel() == 0:
+        fallbacks['linear'] += 1
+        from . import reference_linear
+        return reference_linear(x, weight, bias, activation)
+    if bias is not None and (bias.dtype != torch.bfloat16 or not bias.is_contiguous()):
+        bias = bias.to(torch.bfloat16).contiguous()
+    return _Linear.apply(x, weight, bias, activation)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, residual):
+        xc = x.contiguous()
+        rc = residual.contiguous() if residual is not None else None
+        outs = C().layernorm_fwd(xc, rc, weight, bias, eps)
+        calls['layernorm_fwd'] += 1
+        y, mean, rstd = outs[0], outs[1], outs[2]
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(outs[3] if residual is not None else xc, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, weight, mean, rstd = ctx.saved_tensors
+        dx, dg, db = C().layernorm_bwd(dy.contiguous(), s, weight, mean, rstd)
+        calls['layernorm_bwd'] += 1
+        return dx, dg.to(weight.dtype), db.to(weight.dtype), None, (dx if ctx.has_res else None)
+
+
+def layer_norm(x, weight, bias, eps=1e-5, residual=None):
+    H = x.shape[-1]
+    if x.dtype != torch.bfloat16 or H % 8 != 0 or H > 4096 or weight.dtype != torch.bfloat16:
+        fallbacks['layer_norm'] += 1
+        from . import reference_layer_norm
+        return reference_layer_norm(x, weight, bias, eps, residual)
+    if residual is not None and residual.shape != x.shape:
+        residual = residual.expand_as(x)
+    return _LayerNorm.apply(x, weight, bias, eps, residual)
+
+
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        loss, lse, stats = C().ce_fwd(logits, target, ignore_index)
+        calls['ce_fwd'] += 1
+        ctx.ignore_index = ignore_index
+        ctx.save_for_backward(logits, target, lse, stats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, lse, stats = ctx.saved_tensors
+        d = C().ce_bwd(logits, target, lse, stats, g.reshape(1).float().contiguous(), ctx.ignore_index)
+        calls['ce_bwd'] += 1
+        return d, None, None
+
+
+def cross_entropy(logits, target, ignore_index=-100):
+    ok = (logits.dim() == 2 and logits.dtype == torch.bfloat16 and logits.stride(1) == 1 and logits.stride(0) % 8 == 0
+          and logits.data_ptr() % 16 == 0 and logits.shape[1] >= 64)
+    if not ok:
+        fallbacks['cross_entropy'] += 1
+        return F.cross_entropy(logits.float(), target, ignore_index=ignore_index)
+    return _CrossEntropy.apply(logits, target.contiguous(), ignore_index)
+
+
+def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
+    """Interim: library SDPA until ops/csrc/fmha_sm100.cu lands (tracked in DESIGN.md)."""
+    B, S, H3 = qkv.shape
+    H = H3 // 3
+    D = H // heads
+    q, k, v = qkv.view(B, S, 3, heads, D).permute(2, 0, 3, 1, 4)
+    mask = None
+    if key_padding_mask is not None:
+        mask = key_padding_mask.bool()[:, None, None, :]
+        if causal:
+            mask = mask & torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
+    out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=dropout_p, is_causal=causal and mask is None)
+    fallbacks['attention'] += 1
+    return out.transpose(1, 2).reshape(B, S, H)

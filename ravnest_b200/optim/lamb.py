@@ -7,7 +7,7 @@ that constructor and update rule:
     m <- b1 m + (1-b1) g ;  v <- b2 v + (1-b2) g^2 ;  (optional bias correction)
     u <- m / (sqrt(v) + eps) + wd * w
     trust <- clamp(||w||, 0, clamp_value) / ||u||        (1 if either norm is 0, or adam=True)
-    w <- w - lr * trust * u
+    w <- w - lr * c * trust * u      with c = sqrt(1-b2^t)/(1-b1^t) if debias else 1
 
 It is the numerical reference for the fused CUDA LAMB in ``ravnest_b200/ops/csrc/fused_optim.cu``.
 """
@@ -58,8 +58,6 @@ class Lamb(Optimizer):
                 else:
                     c = 1.0
                 update = m / v.sqrt().add(group['eps'])
-                if c != 1.0:
-                    update.mul_(c)
                 if group['weight_decay'] != 0:
                     update.add_(p, alpha=group['weight_decay'])
                 w_norm = torch.linalg.vector_norm(p).clamp(0, group['clamp_value'])
@@ -68,5 +66,5 @@ class Lamb(Optimizer):
                     trust = torch.ones((), device=p.device)
                 else:
                     trust = torch.where((w_norm > 0) & (u_norm > 0), w_norm / u_norm, torch.ones_like(w_norm))
-                p.add_(update * trust, alpha=-group['lr'])
+                p.add_(update * trust, alpha=-group['lr'] * c)
         return loss

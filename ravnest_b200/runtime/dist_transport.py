@@ -1,0 +1,315 @@
+"""torch.distributed transport: the B200 data plane for pipeline payloads.
+
+Replaces the reference's ``GPU -> .to('cpu') -> pickle -> 2 MiB gRPC chunks -> unpickle -> Manager
+proxy -> .to(device)`` hop (``ravnest/communication.py:67-77,:108``; ``endpoints.py:36-69``;
+SURVEY.md §2.3) with:
+
+  * tensors: NCCL p2p (``isend``/``irecv``) straight between HBMs over NVLink/NVSwitch, on dedicated
+    send / recv CUDA streams coupled to the compute stream by events (no host sync on the hot path);
+  * headers: a tiny pickled dict (action, fpid, flags, tensor shapes/dtypes, non-tensor values) over a
+    gloo pair-group — the only thing the CPU ever touches;
+  * one communicator per (stage pair, direction): forward traffic s -> s+1 and backward traffic
+    s+1 -> s never share a communicator, so an in-flight activation send can never deadlock against
+    an in-flight gradient send (NCCL executes a communicator's ops in issue order);
+  * DP groups (one per stage across replicas) for the collectives in ``parallel/``.
+
+With the ``gloo`` default backend the same code runs on CPU (tests run it with world_size > 1).
+rank == node_id (``node_<id>``), one process per GPU.
+"""
+import os
+import pickle
+import queue
+import threading
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..strings import ActionTypes
+from .mailbox import BACKWARD, FORWARD
+
+_TAG = {FORWARD: 11, BACKWARD: 13}
+
+
+def init_distributed(backend: Optional[str] = None, device: Optional[torch.device] = None) -> Tuple[int, int, torch.device]:
+    """Join the job described by RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT."""
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29531')
+    use_cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == 'cuda')
+    if use_cuda:
+        dev = torch.device('cuda', local % torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+    else:
+        dev = torch.device('cpu')
+    if not dist.is_initialized():
+        if backend is None:
+            backend = 'cuda:nccl,cpu:gloo' if use_cuda else 'gloo'
+        kwargs = {'device_id': dev} if use_cuda else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, dev
+
+
+def _load_chains(base_dir: str) -> Dict[int, List[int]]:
+    import json
+    folder = os.path.join(base_dir, 'node_data', 'nodes')
+    chains: Dict[int, List[int]] = {}
+    for fname in sorted(os.listdir(folder)):
+        if fname.startswith('node_') and fname.endswith('.json'):
+            with open(os.path.join(folder, fname)) as fh:
+                cfg = json.load(fh)
+            ids = cfg.get('cluster_node_ids')
+            if ids:
+                chains[int(cfg['rank'])] = [int(i) for i in ids]
+    return chains
+
+
+class _Groups:
+    """Every rank builds the same groups in the same order (``new_group`` is collective)."""
+    _cache: Dict[str, '_Groups'] = {}
+
+    def __init__(self, chains: Dict[int, List[int]]):
+        self.pair: Dict[Tuple[int, int, str], Any] = {}       # (src, dst, lane) -> tensor group
+        self.header: Dict[Tuple[int, int, str], Any] = {}     # (src, dst, lane) -> gloo group
+        self.dp: Dict[int, Any] = {}                          # stage index -> group
+        self.dp_ranks: Dict[int, List[int]] = {}
+        need_gloo = dist.get_backend() != 'gloo'
+        for cid in sorted(chains):
+            chain = chains[cid]
+            for a, b in zip(chain[:-1], chain[1:]):
+                for lane, (src, dst) in ((FORWARD, (a, b)), (BACKWARD, (b, a))):
+                    g = dist.new_group(ranks=sorted([a, b]))
+                    self.pair[(src, dst, lane)] = g
+                    self.header[(src, dst, lane)] = dist.new_group(ranks=sorted([a, b]), backend='gloo') if need_gloo else g
+        lengths = {len(c) for c in chains.values()}
+        if len(chains) > 1 and len(lengths) == 1:
+            for s in range(lengths.pop()):
+                ranks = [chains[cid][s] for cid in sorted(chains)]
+                self.dp[s] = dist.new_group(ranks=ranks)
+                self.dp_ranks[s] = ranks
+
+    @classmethod
+    def get(cls, chains: Dict[int, List[int]]) -> '_Groups':
+        key = repr(sorted(chains.items()))
+        if key not in cls._cache:
+            cls._cache[key] = cls(chains)
+        return cls._cache[key]
+
+
+def _split_tensors(obj: Any, bag: List[torch.Tensor]) -> Any:
+    """Replace every tensor in a nested message by a placeholder; tensors go to ``bag``."""
+    if isinstance(obj, torch.Tensor):
+        bag.append(obj)
+        return ('__tensor__', len(bag) - 1, tuple(obj.shape), obj.dtype)
+    if isinstance(obj, dict):
+        return {k: _split_tensors(v, bag) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_split_tensors(v, bag) for v in obj]
+    if isinstance(obj, tuple) and not (len(obj) == 4 and obj and obj[0] == '__tensor__'):
+        return tuple(_split_tensors(v, bag) for v in obj)
+    return obj
+
+
+def _join_tensors(obj: Any, bag: List[torch.Tensor]) -> Any:
+    if isinstance(obj, tuple) and len(obj) == 4 and obj[0] == '__tensor__':
+        return bag[obj[1]]
+    if isinstance(obj, dict):
+        return {k: _join_tensors(v, bag) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_join_tensors(v, bag) for v in obj]
+    if isinstance(obj, tuple):
+        return tuple(_join_tensors(v, bag) for v in obj)
+    return obj
+
+
+def _tensor_specs(skeleton: Any, out: List[Tuple[Tuple[int, ...], torch.dtype]]) -> None:
+    if isinstance(skeleton, tuple) and len(skeleton) == 4 and skeleton[0] == '__tensor__':
+        while len(out) <= skeleton[1]:
+            out.append(None)
+        out[skeleton[1]] = (skeleton[2], skeleton[3])
+    elif isinstance(skeleton, dict):
+        for v in skeleton.values():
+            _tensor_specs(v, out)
+    elif isinstance(skeleton, (list, tuple)):
+        for v in skeleton:
+            _tensor_specs(v, out)
+
+
+class DistTransport:
+    kind = 'dist'
+
+    def __init__(self, node, chains: Optional[Dict[int, List[int]]] = None, **_unused):
+        self.node = node
+        self.rank = dist.get_rank()
+        self.device = node.device
+        self.mailbox = node.mailbox
+        self.cuda = self.device.type == 'cuda'
+        cfg = node.config
+        chains = chains or _load_chains(node.base_dir)
+        self.chain = chains[int(cfg['rank'])]
+        self.stage = self.chain.index(self.rank)
+        self.groups = _Groups.get(chains)
+        self.next_rank = self.chain[self.stage + 1] if self.stage + 1 < len(self.chain) else None
+        self.prev_rank = self.chain[self.stage - 1] if self.stage > 0 else None
+        self.dp_group = self.groups.dp.get(self.stage)
+        self.dp_ranks = self.groups.dp_ranks.get(self.stage)
+        self._queues = {FORWARD: queue.Queue(), BACKWARD: queue.Queue()}
+        self._threads: List[threading.Thread] = []
+        self._stop = threading.Event()
+        self._pending = 0
+        self._pending_cv = threading.Condition()
+        self._inflight: Dict[str, List[Any]] = {FORWARD: [], BACKWARD: []}
+        self.send_stream = {FORWARD: None, BACKWARD: None}
+        self.recv_stream = {FORWARD: None, BACKWARD: None}
+        self.bytes_out = 0
+        self.rings = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def start(self) -> None:
+        if self.cuda:
+            for lane in (FORWARD, BACKWARD):
+                self.send_stream[lane] = torch.cuda.Stream(self.device)
+                self.recv_stream[lane] = torch.cuda.Stream(self.device)
+        plans = []
+        if self.next_rank is not None:
+            plans.append((self._sender_loop, FORWARD, self.next_rank))
+            plans.append((self._receiver_loop, BACKWARD, self.next_rank))
+        if self.prev_rank is not None:
+            plans.append((self._sender_loop, BACKWARD, self.prev_rank))
+            plans.append((self._receiver_loop, FORWARD, self.prev_rank))
+        for fn, lane, peer in plans:
+            t = threading.Thread(target=fn, args=(lane, peer), daemon=True,
+                                 name='{}-{}-{}'.format(self.node.name, fn.__name__, lane))
+            t.start()
+            self._threads.append(t)
+
+    def stop(self) -> None:
+        if self._stop.is_set():
+            return
+        # tell both neighbours so their receiver threads leave their blocking recv
+        for lane, peer in ((FORWARD, self.next_rank), (BACKWARD, self.prev_rank)):
+            if peer is not None:
+                self.send(lane, {'action': ActionTypes.SHUTDOWN, 'forward_pass_id': -1, 'data': {}})
+        self.flush(timeout=10)
+        self._stop.set()
+        for q in self._queues.values():
+            q.put(None)
+
+    # ------------------------------------------------------------------ send side
+    def send(self, lane: str, message: Dict[str, Any]) -> None:
+        ev = None
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        with self._pending_cv:
+            self._pending += 1
+        self._queues[lane].put((message, ev))
+
+    def flush(self, timeout: Optional[float] = None) -> None:
+        with self._pending_cv:
+            self._pending_cv.wait_for(lambda: self._pending == 0, timeout=timeout)
+
+    def _sender_loop(self, lane: str, peer: int) -> None:
+        if self.cuda:
+            torch.cuda.set_device(self.device)
+        group = self.groups.pair[(self.rank, peer, lane)]
+        hgroup = self.groups.header[(self.rank, peer, lane)]
+        q = self._queues[lane]
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            message, ev = item
+            try:
+                bag: List[torch.Tensor] = []
+                skeleton = _split_tensors(message, bag)
+                blob = torch.frombuffer(bytearray(pickle.dumps(skeleton, protocol=pickle.HIGHEST_PROTOCOL)), dtype=torch.uint8)
+                dist.send(torch.tensor([blob.numel()], dtype=torch.int64), dst=peer, group=hgroup, tag=_TAG[lane])
+                dist.send(blob, dst=peer, group=hgroup, tag=_TAG[lane])
+                if bag:
+                    if self.cuda:
+                        stream = self.send_stream[lane]
+                        stream.wait_event(ev)
+                        with torch.cuda.stream(stream):
+                            works = []
+                            for t in bag:
+                                t = t if t.is_contiguous() else t.contiguous()
+                                if t.device != self.device:
+                                    t = t.to(self.device, non_blocking=True)
+                                works.append((dist.isend(t, dst=peer, group=group), t))
+                                self.bytes_out += t.numel() * t.element_size()
+                        keep = self._inflight[lane]
+                        keep.extend(works)
+                        self._inflight[lane] = [(w, t) for w, t in keep if not w.is_completed()][-64:]
+                    else:
+                        for t in bag:
+                            dist.send(t.contiguous(), dst=peer, group=group, tag=_TAG[lane] + 1)
+                            self.bytes_out += t.numel() * t.element_size()
+            finally:
+                with self._pending_cv:
+                    self._pending -= 1
+                    self._pending_cv.notify_all()
+
+    # ------------------------------------------------------------------ receive side
+    def _receiver_loop(self, lane: str, peer: int) -> None:
+        if self.cuda:
+            torch.cuda.set_device(self.device)
+        group = self.groups.pair[(peer, self.rank, lane)]
+        hgroup = self.groups.header[(peer, self.rank, lane)]
+        while not self._stop.is_set():
+            size = torch.zeros(1, dtype=torch.int64)
+            try:
+                dist.recv(size, src=peer, group=hgroup, tag=_TAG[lane])
+                blob = torch.empty(int(size.item()), dtype=torch.uint8)
+                dist.recv(blob, src=peer, group=hgroup, tag=_TAG[lane])
+            except RuntimeError:
+                if self._stop.is_set():
+                    return
+                raise
+            skeleton = pickle.loads(blob.numpy().tobytes())
+            specs: List[Tuple[Tuple[int, ...], torch.dtype]] = []
+            _tensor_specs(skeleton, specs)
+            bag: List[torch.Tensor] = []
+            ev = None
+            if specs:
+                if self.cuda:
+                    stream = self.recv_stream[lane]
+                    with torch.cuda.stream(stream):
+                        works = []
+                        for shape, dtype in specs:
+                            t = torch.empty(shape, dtype=dtype, device=self.device)
+                            works.append(dist.irecv(t, src=peer, group=group))
+                            bag.append(t)
+                        for w in works:
+                            w.wait()
+                        ev = torch.cuda.Event()
+                        ev.record(stream)
+                else:
+                    for shape, dtype in specs:
+                        t = torch.empty(shape, dtype=dtype)
+                        dist.recv(t, src=peer, group=group, tag=_TAG[lane] + 1)
+                        bag.append(t)
+            message = _join_tensors(skeleton, bag)
+            if message.get('action') == ActionTypes.SHUTDOWN:
+                # a neighbour is leaving: stop serving this lane; the scheduler decides about the node
+                if lane == FORWARD:
+                    self.mailbox.put(FORWARD, message, block=False)
+                return
+            if ev is not None:
+                message['_ready_event'] = ev
+                message['_tensors'] = bag
+            self.mailbox.put(lane, message)
+
+    # ------------------------------------------------------------------ helpers for the scheduler
+    @staticmethod
+    def adopt(message: Dict[str, Any], device: torch.device) -> None:
+        """Make the scheduler's stream wait for the payload and own its memory."""
+        ev = message.pop('_ready_event', None)
+        tensors = message.pop('_tensors', None)
+        if ev is not None:
+            stream = torch.cuda.current_stream(device)
+            stream.wait_event(ev)
+            for t in tensors or ():
+                t.record_stream(stream)

@@ -134,6 +134,17 @@ class ParamStore:
         for p, o, n, s in zip(self.master_params, self.offsets, self.numels, self.shapes):
             p.grad = flat[o:o + n].view(s)
 
+    def rebind_grad(self, new_flat: torch.Tensor) -> None:
+        """Move the gradient bucket into externally allocated (e.g. symmetric / peer-mapped) memory."""
+        assert new_flat.numel() == self.total and new_flat.dtype == self.grad.dtype
+        new_flat.copy_(self.grad)
+        self.grad = new_flat
+        self.grad_views = [self.grad[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+        for slot in self.slots:
+            for leaf, g in zip(slot.leaves, self.grad_views):
+                leaf.grad = g
+        self._master_grad = None
+
     def zero_grad(self) -> None:
         self.grad.zero_()
 

@@ -1,0 +1,226 @@
+"""Numerics of every hand-written CUDA kernel vs a plain PyTorch fp32 reference of the same op (GPU only).
+
+Run on a B200:  python -m pytest tests -m gpu -x -q      (or  python tests/test_kernels_gpu.py <test_name>)
+"""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+DEV = 'cuda'
+
+
+def _C():
+    from ravnest_b200.ops import _ext
+    return _ext.load()
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _rand(*shape, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).to(torch.bfloat16)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 256, 128), (4096, 768, 768), (4096, 2304, 768), (300, 200, 72),
+                                   (4096, 768, 3072), (1000, 30522, 768)])
+@pytest.mark.parametrize('block_n', [128, 256])
+def test_gemm_nt(M, N, K, block_n):
+    torch.manual_seed(0)
+    a, b = _rand(M, K), _rand(N, K, scale=0.05)
+    out = _C().gemm(a, False, b, False, None, 0, None, False, block_n)[0]
+    ref = a.float() @ b.float().t()
+    assert out.shape == (M, N)
+    assert _rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 128, 128), (4096, 768, 2304), (520, 264, 200)])
+def test_gemm_dgrad_layout(M, N, K):
+    """D[M,N] = A[M,K] @ B[K,N] with B read MN-major (dx = dy @ W)."""
+    torch.manual_seed(1)
+    a, b = _rand(M, K), _rand(K, N, scale=0.05)
+    out = _C().gemm(a, False, b, True, None, 0, None, False, 0)[0]
+    assert _rel_err(out, a.float() @ b.float()) < 1e-2
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 256), (768, 3072, 4096), (264, 200, 520)])
+def test_gemm_wgrad_layout(M, N, K):
+    """D[M,N] = A[K,M]^T @ B[K,N] with both operands MN-major (dW = dy^T @ x)."""
+    torch.manual_seed(2)
+    a, b = _rand(K, M, scale=0.1), _rand(K, N, scale=0.1)
+    out = _C().gemm(a, True, b, True, None, 0, None, False, 0)[0]
+    assert _rel_err(out, a.float().t() @ b.float()) < 1e-2
+
+
+@pytest.mark.parametrize('act,name', [(1, 'gelu'), (2, 'gelu_tanh'), (3, 'relu')])
+def test_gemm_epilogue(act, name):
+    torch.manual_seed(3)
+    M, N, K = 512, 384, 256
+    a, b, bias = _rand(M, K), _rand(N, K, scale=0.05), _rand(N)
+    y, z = _C().gemm(a, False, b, False, bias, act, None, True, 128)
+    zref = a.float() @ b.float().t() + bias.float()
+    yref = {'gelu': torch.nn.functional.gelu(zref), 'gelu_tanh': torch.nn.functional.gelu(zref, approximate='tanh'),
+            'relu': torch.relu(zref)}[name]
+    assert _rel_err(z, zref) < 1e-2
+    assert _rel_err(y, yref) < 1e-2
+    # dact mode: D = (A B^T) * act'(z)
+    g = _C().gemm(a, False, b, False, None, act, z.contiguous(), False, 128)[0]
+    zr = z.float().requires_grad_(True)
+    f = {'gelu': torch.nn.functional.gelu(zr), 'gelu_tanh': torch.nn.functional.gelu(zr, approximate='tanh'), 'relu': torch.relu(zr)}[name]
+    dact = torch.autograd.grad(f.sum(), zr)[0]
+    assert _rel_err(g, (a.float() @ b.float().t()) * dact) < 2e-2
+
+
+def test_linear_autograd_matches_torch():
+    from ravnest_b200 import ops
+    torch.manual_seed(4)
+    x = _rand(8, 512, 768).requires_grad_(True)
+    w = _rand(3072, 768, scale=0.03).requires_grad_(True)
+    b = _rand(3072, scale=0.1).requires_grad_(True)
+    y = ops.linear(x, w, b, 'gelu')
+    gy = _rand(8, 512, 3072)
+    y.backward(gy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = ops.reference_linear(xr, wr, br, 'gelu')
+    yr.backward(gy.float())
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 2e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
+    assert _rel_err(b.grad, br.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize('rows,H', [(4096, 768), (704, 48), (33, 1024), (16, 3072)])
+@pytest.mark.parametrize('with_res', [False, True])
+def test_layernorm(rows, H, with_res):
+    from ravnest_b200 import ops
+    torch.manual_seed(5)
+    x = _rand(rows, H).requires_grad_(True)
+    r = _rand(rows, H).requires_grad_(True) if with_res else None
+    g = (1 + 0.1 * torch.randn(H, device=DEV)).to(torch.bfloat16).requires_grad_(True)
+    b = _rand(H, scale=0.1).requires_grad_(True)
+    y = ops.layer_norm(x, g, b, 1e-12, r)
+    gy = _rand(rows, H)
+    y.backward(gy)
+    xr, gr, br = (t.detach().float().requires_grad_(True) for t in (x, g, b))
+    rr = r.detach().float().requires_grad_(True) if with_res else None
+    yr = ops.reference_layer_norm(xr, gr, br, 1e-12, rr)
+    yr.backward(gy.float())
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 2e-2
+    assert _rel_err(g.grad, gr.grad) < 3e-2
+    assert _rel_err(b.grad, br.grad) < 3e-2
+    if with_res:
+        assert _rel_err(r.grad, rr.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------- cross entropy
+@pytest.mark.parametrize('rows,V', [(4096, 30522), (64, 1000), (17, 200)])
+def test_cross_entropy(rows, V):
+    from ravnest_b200 import ops
+    torch.manual_seed(6)
+    Vp = (V + 7) // 8 * 8
+    buf = _rand(rows, Vp, scale=2.0)
+    logits = buf[:, :V].detach().requires_grad_(True)
+    target = torch.randint(0, V, (rows,), device=DEV)
+    target[torch.rand(rows, device=DEV) < 0.5] = -100
+    target[0] = 3
+    loss = ops.cross_entropy(logits, target, -100)
+    (loss * 0.5).backward()
+    lr = logits.detach().float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, target, ignore_index=-100)
+    (ref * 0.5).backward()
+    assert abs(float(loss) - float(ref)) < 2e-3 * max(1.0, abs(float(ref)))
+    assert _rel_err(logits.grad, lr.grad) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------------- fused optimizers
+class _FakeModule(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.randn(300, 77))
+        self.b = torch.nn.Parameter(torch.randn(1000))
+        self.c = torch.nn.Parameter(torch.randn(64, 64, 3))
+
+
+@pytest.mark.parametrize('kind', ['sgd', 'adam', 'adamw', 'lamb'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_fused_optimizer_matches_torch(kind, dtype):
+    import ravnest_b200 as rv
+    from ravnest_b200.optim import build_optimizer
+    from ravnest_b200.runtime.param_store import ParamStore
+    torch.manual_seed(7)
+    mod = _FakeModule().to(DEV)
+    ref = _FakeModule().to(DEV)
+    ref.load_state_dict(mod.state_dict())
+    cls, params = {'sgd': (torch.optim.SGD, dict(lr=0.05, momentum=0.9, weight_decay=5e-4)),
+                   'adam': (torch.optim.Adam, dict(lr=1e-2, weight_decay=1e-3)),
+                   'adamw': (torch.optim.AdamW, dict(lr=1e-2, weight_decay=1e-2)),
+                   'lamb': (rv.Lamb, dict(lr=1e-2, weight_decay=0.01, debias=True, clamp_value=10000.0))}[kind]
+    store = ParamStore(mod.to(dtype), DEV, n_slots=3, compute_dtype=dtype)
+    opt, fused = build_optimizer(cls, dict(params), store, fused=True)
+    assert fused is not None
+    ropt = cls(ref.parameters(), **params)
+    for step in range(4):
+        grads = [torch.randn_like(p) * 0.1 for p in ref.parameters()]
+        for p, g, view in zip(ref.parameters(), grads, store.grad_views):
+            gq = g.to(dtype)
+            view.copy_(gq)
+            p.grad = gq.float()
+        fused.step()
+        ropt.step()
+    torch.cuda.synchronize()
+    for p, view in zip(ref.parameters(), store.master_views):
+        assert _rel_err(view, p) < 2e-3, kind
+    # published compute-dtype weights follow the master copy
+    for leaf, view in zip(store.current.leaves, store.master_views):
+        assert _rel_err(leaf, view) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+    assert float(store.grad.abs().sum()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------- model level
+def test_bert_small_native_vs_torch_backend():
+    """One fwd+bwd of a small BERT with the native kernels vs the stock-torch backend (same weights)."""
+    from ravnest_b200 import models, ops
+    torch.manual_seed(8)
+    cfg = models.BertConfig(vocab_size=2048, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024,
+                            max_position_embeddings=128, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = models.BertForPreTraining(cfg).to(DEV, torch.bfloat16)
+    B, S = 4, 128
+    ids = torch.randint(0, cfg.vocab_size, (B, S), device=DEV)
+    mask = torch.ones(B, S, dtype=torch.long, device=DEV)
+    mask[:, 100:] = 0
+    tt = torch.zeros(B, S, dtype=torch.long, device=DEV)
+    labels = torch.where(torch.rand(B, S, device=DEV) < 0.2, ids, torch.full_like(ids, -100))
+    sop = torch.randint(0, 2, (B,), device=DEV)
+    results = {}
+    for backend in ('native', 'torch'):
+        ops.set_backend(backend)
+        model.zero_grad(set_to_none=True)
+        out = model(ids, mask, tt)
+        loss = models.bert_pretraining_loss(out, labels, sop)
+        loss.backward()
+        results[backend] = (float(loss), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None})
+    ops.set_backend('native')
+    assert abs(results['native'][0] - results['torch'][0]) < 3e-2 * abs(results['torch'][0])
+    worst = max(_rel_err(results['native'][1][n], g) for n, g in results['torch'][1].items() if g.norm() > 0)
+    assert worst < 0.15, worst
+    from ravnest_b200.ops import native
+    assert native.calls['gemm_fwd'] > 0 and native.calls['layernorm_fwd'] > 0
+
+
+def test_smoke_entry():
+    import __graft_entry__ as entry
+    entry.smoke()
+
+
+if __name__ == '__main__':
+    sys.exit(pytest.main([__file__, '-x', '-q'] + (['-k', sys.argv[1]] if len(sys.argv) > 1 else [])))
