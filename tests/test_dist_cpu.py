@@ -1,0 +1,40 @@
+"""torch.distributed transport on CPU (gloo, world_size 4): 2 stages x 2 replicas, async pipeline,
+periodic parameter averaging (reference semantics) and per-step gradient all-reduce (DP 'gradient' mode)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import ravnest_b200 as rv
+from ravnest_b200 import models
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _launch(workdir, port, extra):
+    rv.set_seed(42)
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(32, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
+                  node_configs=rv.default_gpu_configs(4), proportions=[0.5, 0.5], base_dir=str(workdir))
+    env = dict(os.environ, RAVNEST_HOME=str(workdir), OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '4', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(HERE, 'dist_worker.py')] + extra
+    proc = subprocess.run(cmd, cwd=str(workdir), env=env, capture_output=True, text=True, timeout=420)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    return [json.load(open(os.path.join(str(workdir), 'result.json.{}'.format(r)))) for r in range(4)]
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize('dp_mode,recompute', [('average', 1), ('gradient', 0)])
+def test_two_by_two_grid_over_gloo(workdir, free_ports, dp_mode, recompute):
+    res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '3', '--dp-mode', dp_mode, '--recompute', str(recompute)])
+    assert [r['node_type'] for r in res] == ['root', 'leaf', 'root', 'leaf']
+    assert all(r['n_backwards'] == 12 for r in res)                      # 3 epochs x 4 batches per replica
+    # replicas of the same stage end bit-identical (averaging / identical reduced gradients)
+    assert res[0]['checksum'] == pytest.approx(res[2]['checksum'], rel=1e-6)
+    if dp_mode == 'gradient':
+        assert res[1]['checksum'] == pytest.approx(res[3]['checksum'], rel=1e-6)
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_1.txt'))]
+    assert len(losses) == 12 and losses[-1] < losses[0]

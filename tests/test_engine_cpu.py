@@ -1,0 +1,242 @@
+"""Engine semantics on CPU: pipeline == unsplit model, weight stashing / recompute, version ring,
+3-node localhost training over the gRPC path, cross-cluster ring averaging, checkpoint/resume."""
+import copy
+import json
+import os
+import threading
+import time
+
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+import ravnest_b200 as rv
+from ravnest_b200 import models
+from ravnest_b200.communication import StagePlan
+from ravnest_b200.compute import Compute
+from ravnest_b200.operations import split_model
+from ravnest_b200.runtime.param_store import ParamStore
+
+
+class TinyMLP(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(12, 32)
+        self.act = torch.nn.Tanh()
+        self.b = torch.nn.Linear(32, 32)
+        self.drop = torch.nn.Dropout(0.2)
+        self.c = torch.nn.Linear(32, 4)
+
+    def forward(self, x):
+        return self.c(self.drop(self.act(self.b(self.act(self.a(x))))))
+
+
+def _stages(model, proportions, x, **kw):
+    r = split_model(model, proportions, (x,))
+    plans, engines = [], []
+    for i, st in enumerate(r.stages):
+        plans.append(StagePlan(st.name, st.input_template(), st.output_template(), r.model_inputs_template if i == 0 else None))
+        engines.append(Compute(copy.deepcopy(st.module), optimizer_cls=torch.optim.SGD, optimizer_params={'lr': 0.1},
+                               criterion=(lambda out, tgt: torch.nn.functional.mse_loss(out, tgt)) if st.is_last else None,
+                               cluster_length=len(r.stages), loss_filename=None, is_last=st.is_last, **kw))
+    return plans, engines
+
+
+def _pipeline_step(plans, engines, fpid, x, y):
+    """Synchronous walk of one mini-batch through the stage engines (what Node does across processes)."""
+    out = engines[0].forward(fpid, [x], input_grads=False)
+    data = plans[0].root_payload(out, [x])
+    for plan, eng in zip(plans[1:-1], engines[1:-1]):
+        args = plan.gather_args(data)
+        plan.add_outputs(data, eng.forward(fpid, args))
+    args = plans[-1].gather_args(data)
+    loss, in_grads = engines[-1].loss_step(args, y)
+    grads = plans[-1].add_input_grads({}, in_grads)
+    for plan, eng in zip(reversed(plans[:-1]), reversed(engines[:-1])):
+        in_grads = eng.backward(fpid, plan.take_output_grads(grads))
+        grads = plan.add_input_grads(grads, in_grads)
+    return float(loss)
+
+
+@pytest.mark.parametrize('recompute', [True, False])
+def test_pipeline_matches_unsplit_model_step_for_step(recompute):
+    torch.manual_seed(0)
+    model = TinyMLP()
+    model.drop.p = 0.0
+    ref = copy.deepcopy(model)
+    x, y = torch.randn(16, 12), torch.randn(16, 4)
+    plans, engines = _stages(model, [0.3, 0.3, 0.4], x, recompute=recompute)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for step in range(5):
+        loss = _pipeline_step(plans, engines, step, x, y)
+        ref_loss = torch.nn.functional.mse_loss(ref(x), y)
+        opt.zero_grad()
+        ref_loss.backward()
+        opt.step()
+        assert loss == pytest.approx(float(ref_loss), rel=1e-5, abs=1e-6)
+    merged = {}
+    for eng in engines:
+        merged.update(eng.state_dict())
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(merged[k], v, atol=1e-5), k
+
+
+def test_recompute_replays_dropout_and_matches_resident_activations():
+    """reference schedule (no-grad forward + recompute with stashed RNG) == keeping the graph resident."""
+    x, y = torch.randn(16, 12), torch.randn(16, 4)
+    results = []
+    for recompute in (True, False):
+        torch.manual_seed(3)
+        plans, engines = _stages(TinyMLP(), [0.5, 0.5], x, recompute=recompute)
+        torch.manual_seed(11)
+        losses = [_pipeline_step(plans, engines, i, x, y) for i in range(4)]
+        results.append((losses, engines[0].store.master.clone()))
+    assert results[0][0] == pytest.approx(results[1][0], rel=1e-6)
+    assert torch.allclose(results[0][1], results[1][1], atol=1e-6)
+
+
+def test_weight_stashing_uses_the_forward_version_for_backward():
+    """Async depth 2: backward of fpid 0 arrives after fpid 1 was forwarded and after an update —
+    it must differentiate through the weights fpid 0 saw (PipeDream stashing), for both modes."""
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(4, 4)
+    x0, x1 = torch.randn(3, 4), torch.randn(3, 4)
+    g = torch.ones(3, 4)
+    for recompute in (True, False):
+        eng = Compute(copy.deepcopy(lin), optimizer_cls=torch.optim.SGD, optimizer_params={'lr': 0.5}, cluster_length=2,
+                      recompute=recompute, loss_filename=None)
+        w0 = eng.store.master_views[0].clone()
+        eng.forward(0, [x0.clone().requires_grad_(True)])
+        eng.forward(1, [x1.clone().requires_grad_(True)])
+        gin0 = eng.backward(0, {0: g})[0]             # update happens here -> version 1
+        assert eng.current_version() == 1
+        gin1 = eng.backward(1, {0: g})[0]             # must still use version 0 weights
+        assert torch.allclose(gin0, g @ w0, atol=1e-6)
+        assert torch.allclose(gin1, g @ w0, atol=1e-6)
+        assert eng.current_version() == 2 and not eng.flights
+        assert all(s.refs == 0 for s in eng.store.slots)
+
+
+def test_param_store_ring_reuses_and_grows():
+    store = ParamStore(torch.nn.Linear(8, 8), 'cpu', n_slots=2)
+    s0 = store.acquire()
+    store.publish()
+    assert store.current is not s0 and s0.refs == 1 and store.version == 1
+    s1 = store.acquire()
+    store.publish()                                   # both slots pinned -> ring grows
+    assert len(store.slots) == 3
+    store.release(s0)
+    store.release(s1)
+    before = len(store.slots)
+    store.publish()
+    assert len(store.slots) == before and store.version == 3
+    assert store.offsets[1] % 64 == 0
+
+
+def test_lamb_matches_closed_form():
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(5, 3))
+    p.grad = torch.randn(5, 3)
+    w0, g = p.detach().clone(), p.grad.clone()
+    opt = rv.Lamb([p], lr=0.1, weight_decay=0.01, debias=True, clamp_value=10000.0)
+    opt.step()
+    m, v = 0.1 * g, 0.001 * g * g
+    u = m / (v.sqrt() + 1e-6) + 0.01 * w0
+    c = (1 - 0.999) ** 0.5 / (1 - 0.9)
+    expect = w0 - 0.1 * c * (w0.norm() / u.norm()) * u
+    assert torch.allclose(p.detach(), expect, atol=1e-6)
+
+
+def _digits(n=320):
+    g = torch.Generator().manual_seed(0)
+    y = torch.randint(0, 10, (n,), generator=g)
+    x = torch.randn(n, 1, 8, 8, generator=g) * 0.3
+    for i in range(n):
+        x[i, 0, y[i] % 8, :] += 2.0
+        x[i, 0, :, (y[i] * 3) % 8] += 1.0
+    return x, torch.nn.functional.one_hot(y, 10).float()
+
+
+def _loss_fn(preds, targets):
+    return torch.nn.functional.mse_loss(preds, targets[1])
+
+
+def _loaders(x, y):
+    g = torch.Generator().manual_seed(42)
+    data = list(zip(x, y))
+    return DataLoader(data, generator=g, shuffle=True, batch_size=32), DataLoader(data, shuffle=False, batch_size=32)
+
+
+def test_three_node_cnn_trains_over_grpc_and_fuses(workdir, free_ports):
+    """BASELINE.json config #1: examples/cnn, 3 nodes on localhost, plumbing only."""
+    rv.set_seed(42)
+    ports = free_ports(3)
+    os.makedirs('node_data')
+    json.dump({str(i): {'IP': '0.0.0.0:{}'.format(p), 'benchmarks': {'ram': 8, 'bandwidth': 10}} for i, p in enumerate(ports)},
+              open('node_data/node_configs.json', 'w'))
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(32, 1, 8, 8),))
+    x, y = _digits()
+    nodes = []
+    for i in range(3):
+        tl, vl = _loaders(x, y)
+        nodes.append((rv.Node(name='node_{}'.format(i), optimizer=torch.optim.Adam, optimizer_params={'lr': 3e-3}, criterion=_loss_fn,
+                              labels=tl, test_labels=vl, device=torch.device('cpu'), reset=(i == 0)), tl, vl))
+    assert [n.node_type for n, _, _ in nodes] == ['root', 'stem', 'leaf']
+    root, tl, vl = nodes[0]
+    trainer = rv.Trainer(node=root, train_loader=tl, val_loader=vl, epochs=12, inputs_dtype=torch.float32, save=True)
+    trainer.train()
+    trainer.evaluate()
+    leaf = nodes[2][0]
+    deadline = time.time() + 20
+    while not (leaf._saved.is_set() and os.path.exists('val_accuracies.txt')) and time.time() < deadline:
+        time.sleep(0.05)
+    time.sleep(0.3)
+    leaf.compute_session.flush_losses()
+    losses = [float(l) for l in open('losses.txt')]
+    assert len(losses) == 12 * 10                       # one line per optimizer update
+    assert sum(losses[-10:]) < 0.8 * sum(losses[:10])   # it learns
+    accs = [float(l) for l in open('val_accuracies.txt')]
+    assert len(accs) >= 2 and accs[-1] > 0.5
+    assert root.latest_backward_id == root.forward_pass_id == 120
+    path = rv.model_fusion(0)
+    fused = torch.load(path)
+    full = models.CNN_Net()
+    assert not full.load_state_dict(fused).missing_keys
+    # heartbeat + latest-weights service answer on the control plane
+    assert root.transport.ping(('127.0.0.1', ports[1]))
+    got = root.transport.fetch_latest_weights(('127.0.0.1', ports[1]), 'dense_1.weight', 'dense_1.bias')
+    assert set(got) == {'dense_1.weight', 'dense_1.bias'}
+    # checkpoint / resume round trip
+    ck = leaf.checkpoint('t')
+    before = leaf.compute_session.store.master.clone()
+    leaf.compute_session.store.master.add_(1.0)
+    assert leaf.restore('t') and torch.equal(leaf.compute_session.store.master, before) and os.path.exists(ck)
+    for n, _, _ in nodes:
+        n.stop()
+
+
+def test_two_cluster_ring_average_over_grpc(workdir, free_ports):
+    """2 clusters x 1 stage... use 2 stages x 2 clusters wired by hand: parameter averaging equals the mean."""
+    rv.set_seed(1)
+    ports = free_ports(4)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+    nodes = [rv.Node(name='node_{}'.format(i), optimizer=torch.optim.SGD, optimizer_params={'lr': 0.1}, criterion=_loss_fn,
+                     labels=[(None, torch.zeros(1, 10))], device=torch.device('cpu'), transport='grpc', reset=False,
+                     average_optim=False) for i in range(4)]
+    with torch.no_grad():
+        for i, n in enumerate(nodes):
+            n.compute_session.store.master.fill_(float(i + 1))
+    expect = {0: 2.0, 2: 2.0, 1: 3.0, 3: 3.0}          # stage-0 peers are nodes 0,2 ; stage-1 peers are 1,3
+    threads = [threading.Thread(target=n.comm_session.parallel_ring_reduce) for n in nodes]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    for i, n in enumerate(nodes):
+        real = torch.cat([v.reshape(-1) for v in n.compute_session.store.master_views])
+        assert torch.allclose(real, torch.full_like(real, expect[i])), i
+        assert n.compute_session.current_version() == 1
+    for n in nodes:
+        n.stop()

@@ -1,0 +1,126 @@
+"""Planner: GA determinism, split boundaries vs the reference policy, templates, JSON schema."""
+import json
+import os
+
+import pytest
+import torch
+
+import ravnest_b200 as rv
+from ravnest_b200 import models
+from ravnest_b200.operations import (PlannerNode, calculate_fitness, equal_proportions, genetic_algorithm, round_percentages,
+                                     split_model)
+
+
+def _n(m):
+    return sum(p.numel() for p in m.parameters())
+
+
+def test_param_counts_match_reference_models():
+    assert _n(models.CNN_Net()) == 16426
+    assert _n(models.resnet50(num_classes=200)) == 23917832
+    assert _n(models.Inception3()) == 21638954
+    assert _n(models.GPT()) == 85728
+    assert _n(models.BertForPreTraining()) == 110106428
+
+
+def test_equal_proportions_policy():
+    assert equal_proportions(3) == [0.3, 0.3, pytest.approx(0.4)]
+    assert equal_proportions(4) == [0.2, 0.2, 0.2, pytest.approx(0.4)]
+    assert equal_proportions(2) == [0.5, 0.5]
+    assert round_percentages([33.3, 33.3, 33.4]) == [33, 33, 34]
+
+
+def test_cnn_split_matches_reference_boundaries():
+    r = split_model(models.CNN_Net(), [0.3, 0.3, 0.4], (torch.rand(64, 1, 8, 8),))
+    assert [_n(s.module) for s in r.stages] == [4896, 8448, 3082]
+    assert r.stages[1].input_template() == {0: {'submod_0': 'placeholder:tensor'}}
+    assert r.stages[0].output_template() == {0: {'target': ['submod_1']}}
+    assert r.model_inputs_template == {0: {'target': ['submod_0']}}
+    assert 'dense_1.weight' in r.stages[1].module.state_dict()          # original parameter names survive
+    assert 'bn_3.weight' in r.stages[2].module.state_dict()
+
+
+def test_resnet50_split_matches_survey_table():
+    m = models.resnet50(num_classes=200).eval()
+    x = torch.rand(2, 3, 224, 224)
+    r = split_model(m, [0.2, 0.2, 0.2, 0.4], (x,))
+    assert [_n(s.module) for s in r.stages] == [4337216, 4731392, 3412992, 11436232]
+    # cuts land mid-bottleneck: multi-tensor boundaries, one tensor skips a stage
+    assert r.stages[1].input_template() == {0: {'submod_0': 0}, 1: {'submod_0': 1}}
+    assert r.stages[1].output_template() == {0: {'target': ['submod_2']}, 1: {'target': ['submod_3']}}
+    for s in r.stages:
+        s.module.eval()
+    assert torch.allclose(r.run_local(x), m(x), atol=1e-5)
+
+
+def test_inception_and_gpt_splits_run():
+    m = models.Inception3().eval()
+    x = torch.rand(2, 3, 32, 32)
+    r = split_model(m, [0.3, 0.3, 0.4], (x,))
+    assert [_n(s.module) for s in r.stages] == [6293536, 5992320, 9353098]
+    g = models.GPT().eval()
+    idx = torch.randint(0, 3, (4, 11))
+    r8 = split_model(g, [1 / 8] * 8, (idx,))
+    assert len(r8.stages) == 8 and sum(_n(s.module) for s in r8.stages) == 85728
+    for s in r8.stages:
+        s.module.eval()
+    assert torch.allclose(r8.run_local(idx), g(idx), atol=1e-5)
+
+
+def test_bert_kwargs_split_routes_mask_to_both_stages():
+    cfg = models.BertConfig(vocab_size=512, hidden_size=64, num_hidden_layers=4, num_attention_heads=4, intermediate_size=128,
+                            max_position_embeddings=32)
+    m = models.BertForPreTraining(cfg).eval()
+    kw = {'input_ids': torch.randint(0, 512, (2, 16)), 'attention_mask': torch.ones(2, 16, dtype=torch.long),
+          'token_type_ids': torch.zeros(2, 16, dtype=torch.long)}
+    r = split_model(m, [0.5, 0.5], (), kw)
+    assert r.model_input_names == ['input_ids', 'attention_mask', 'token_type_ids']
+    assert r.model_inputs_template[1]['target'] == ['submod_0', 'submod_1']        # attention mask relayed to the leaf
+    for s in r.stages:
+        s.module.eval()
+    a, b = r.run_local(kw['input_ids'], kw['attention_mask'], kw['token_type_ids'])
+    ra, rb = m(**kw)
+    assert torch.allclose(a, ra, atol=1e-5) and torch.allclose(b, rb, atol=1e-5)
+
+
+def test_genetic_algorithm_is_deterministic_and_feasible():
+    nodes = [PlannerNode(i, '10.0.0.{}:80'.format(i), {'ram': r * 1024, 'bandwidth': b})
+             for i, (r, b) in enumerate([(8, 10), (8, 10), (16, 100), (4, 10), (32, 100), (8, 50)])]
+    a = genetic_algorithm(nodes, 6000, seed=3)
+    b = genetic_algorithm(nodes, 6000, seed=3)
+    assert {k: [n.node_id for n in v] for k, v in a.items()} == {k: [n.node_id for n in v] for k, v in b.items()}
+    for members in a.values():
+        assert sum(n.benchmarks['ram'] for n in members) > 6000
+    sol = [0] * len(nodes)
+    assert calculate_fitness(sol, nodes, 6000) == 0
+
+
+def test_clusterize_writes_reference_layout(workdir):
+    os.makedirs('node_data')
+    cfg = {str(i): {'IP': '0.0.0.0:{}'.format(8080 + i), 'benchmarks': {'ram': 8, 'bandwidth': 10}} for i in range(3)}
+    json.dump(cfg, open('node_data/node_configs.json', 'w'))
+    rv.clusterize(model=models.CNN_Net(), example_args=(torch.rand(64, 1, 8, 8),))
+    base = 'node_data/cluster_0/0.0.0.0:8080'
+    assert sorted(os.listdir(base)) == ['model_inputs.pkl', 'plan.json', 'submod.pt', 'submod_0_input.pkl', 'submod_0_output.pkl']
+    meta = json.load(open('node_data/nodes/node_1.json'))
+    for key in ('node_id', 'local_host', 'local_port', 'template_path', 'rank', 'ring_size', 'cluster_length', 'param_addresses',
+                'ring_ids', 'forward_target_host', 'forward_target_port', 'backward_target_host', 'backward_target_port', 'node_type'):
+        assert key in meta
+    assert meta['node_type'] == 'stem' and meta['cluster_length'] == 3 and meta['ring_size'] == 1
+    assert meta['ring_ids'] == {'1': 'dense_1.weight'}
+    assert json.load(open('node_data/nodes/node_0.json'))['node_type'] == 'root'
+    assert json.load(open('node_data/nodes/node_2.json'))['node_type'] == 'leaf'
+    loaded = rv.load_node_json_configs('node_2')
+    assert loaded['submod_file'] == 'submod_2' and loaded['ring_ids'] == {2: 'bn_3.weight'}
+    rv.reset_node_data()
+    assert os.listdir('node_data') == ['node_configs.json']
+
+
+def test_grid_topology_plan(workdir):
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
+                  node_configs=rv.default_gpu_configs(4), proportions=[0.5, 0.5])
+    metas = [json.load(open('node_data/nodes/node_{}.json'.format(i))) for i in range(4)]
+    assert [m['node_type'] for m in metas] == ['root', 'leaf', 'root', 'leaf']
+    assert [m['rank'] for m in metas] == [0, 0, 1, 1] and all(m['ring_size'] == 2 for m in metas)
+    assert metas[0]['dp_peer_node_ids'] == [0, 2] and metas[1]['dp_peer_node_ids'] == [1, 3]
+    assert list(metas[0]['param_addresses'][0]) == ['127.0.0.1:8082']          # same stage of the next replica
