@@ -33,6 +33,8 @@ def parse():
     ap.add_argument('--model', default='bert', choices=['bert', 'resnet50'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--update-frequency', type=int, default=None)
+    ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
+    ap.add_argument('--no-graphs', action='store_true', help='disable CUDA-graph capture of the stage step')
     ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
     return ap.parse_args()
 
@@ -196,6 +198,9 @@ def main():
     torch.backends.cudnn.benchmark = True
 
     stages, replicas = topology_for(args.model, world)
+    if args.topology:
+        stages, replicas = (int(v) for v in args.topology.lower().split('x'))
+        assert stages * replicas == world
     home = os.environ.get('RAVNEST_HOME') or os.path.join(tempfile.gettempdir(), 'rvn_bench_{}'.format(os.environ.get('MASTER_PORT', '0')))
     os.environ['RAVNEST_HOME'] = home
     model, ex_args, ex_kwargs, batch = build_model(args)
@@ -260,7 +265,7 @@ def main():
 
     node = rv.Node(name='node_{}'.format(rank), criterion=criterion, labels=Labels(), device=dev, base_dir=home,
                    reduce_factor=1 << 30, dp_mode='gradient', fused_optimizer=fused, loss_filename=None,
-                   recompute=False, **node_kwargs)
+                   recompute=False, use_cuda_graphs=not args.no_graphs, **node_kwargs)
     driver = node.node_type in ('root', 'solo')
 
     def sync():
@@ -317,7 +322,7 @@ def main():
             'config': {'model': 'bert-base-uncased BertForPreTraining (110.1M)' if args.model == 'bert' else 'resnet50(num_classes=200)',
                        'global_batch': replicas * batch, 'per_replica_batch': batch, 'seq_len': 512 if args.model == 'bert' else None,
                        'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': 'LAMB' if args.model == 'bert' else 'SGD-momentum',
-                       'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)',
+                       'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)', 'cuda_graphs': not args.no_graphs,
                        'l2': 'working set (weights+activations, >1 GB/step) exceeds the 126 MB L2; no explicit flush'},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'wall_ms_per_step': dev_wall / args.steps,
         }
@@ -354,7 +359,8 @@ def count_launches(node, feed, pool, driver, sync, Labels):
                 total += 1
                 if 'rvn_' in ev.name:
                     mine += 1
-        return {'ours_per_step': mine, 'all_per_step': total}
+        from ravnest_b200.ops import native_ops_loaded
+        return {'ours_per_step': mine, 'all_per_step': total, 'native_calls_traced': native_ops_loaded()}
     except Exception as err:
         return {'error': repr(err)}
 

@@ -65,7 +65,7 @@ class Compute:
                  cluster_length: int = 1, recompute: bool = True, compute_dtype: Optional[torch.dtype] = None,
                  loss_filename: Optional[str] = 'losses.txt', is_last: bool = False, dp_group=None,
                  fused_optimizer: Optional[bool] = None, lr_scheduler=None, lr_scheduler_params: Optional[dict] = None,
-                 average_grads_over_dp: bool = False):
+                 average_grads_over_dp: bool = False, use_cuda_graphs: bool = False):
         self.device = torch.device(device)
         self.model = model
         self.criterion = criterion
@@ -86,6 +86,11 @@ class Compute:
         self.lr_scheduler = None
         self._fused = None
         self._average_grads = bool(average_grads_over_dp)
+        self.use_graphs = bool(use_cuda_graphs)
+        self.graph_warmup = 3
+        self._graph = None
+        self._graph_seen = 0
+        self._graph_failed = False
         self.loss_readback = False          # copy every step's loss to pinned host memory (async D2H)
         self._loss_host = None
         self.loss_history: List[Any] = []
@@ -222,17 +227,24 @@ class Compute:
     # ------------------------------------------------------------------ leaf / solo
     def loss_step(self, args: Sequence[Any], targets: Any, update: Optional[bool] = None, input_grads: bool = True):
         """Leaf (or solo) step: forward WITH grad, criterion, backward, maybe update
-        (reference compute.py:273-311).  Returns (loss tensor, input grads)."""
+        (reference compute.py:273-311).  Returns (loss tensor, input grads).
+
+        On CUDA the step is captured into a CUDA graph after ``graph_warmup`` eager steps (see
+        runtime/graphs.py); anything un-capturable in the user's criterion falls back to eager."""
         with self.lock:
             self.model.train()
             slot = self.store.current
-            inputs = self._prepare_inputs(args, need_grad=input_grads)
-            with torch.enable_grad():
-                out = self._call(slot, inputs)
-                loss = self.criterion(out, targets)
-            loss.backward()
-            in_grads = [a.grad if isinstance(a, torch.Tensor) and a.requires_grad else None for a in inputs]
-            det = loss.detach()
+            det = in_grads = None
+            if self.use_graphs and self.device.type == 'cuda':
+                det, in_grads = self._graphed_loss_step(args, targets, input_grads, slot)
+            if det is None:
+                inputs = self._prepare_inputs(args, need_grad=input_grads)
+                with torch.enable_grad():
+                    out = self._call(slot, inputs)
+                    loss = self.criterion(out, targets)
+                loss.backward()
+                in_grads = [a.grad if isinstance(a, torch.Tensor) and a.requires_grad else None for a in inputs]
+                det = loss.detach()
             self.last_loss = det
             if self.loss_readback and det.is_cuda:
                 if self._loss_host is None:
@@ -245,6 +257,26 @@ class Compute:
             if updated:
                 self._queue_loss_line()
             return det, in_grads
+
+    def _graphed_loss_step(self, args, targets, input_grads, slot):
+        from .runtime.graphs import GraphedLossStep
+        g = self._graph
+        if g is not None and g.matches(args, targets, slot):
+            return g.run(args, targets)
+        self._graph_seen += 1
+        if self._graph_seen <= self.graph_warmup or self._graph_failed:
+            return None, None
+        try:
+            inputs = self._prepare_inputs(args, need_grad=False)
+            self._graph = GraphedLossStep(self, inputs, targets, input_grads)
+            return self._graph.run(inputs, targets)
+        except Exception as err:          # un-capturable criterion / op: stay eager, say so once
+            self._graph_failed = True
+            self._graph = None
+            import warnings
+            warnings.warn('CUDA-graph capture of the loss step failed, running eagerly: {!r}'.format(err))
+            torch.cuda.synchronize(self.device)
+            return None, None
 
     def _queue_loss_line(self) -> None:
         """One line per optimizer update = loss summed over the accumulation window

@@ -133,7 +133,8 @@ class Node:
             loss_filename=self.loss_filename if self.is_last else None, is_last=self.is_last,
             dp_group=self.dp_group if self.dp_mode == 'gradient' else None,
             fused_optimizer=kwargs.get('fused_optimizer'), lr_scheduler=lr_scheduler,
-            lr_scheduler_params=lr_scheduler_params or {}, average_grads_over_dp=self.dp_mode == 'gradient')
+            lr_scheduler_params=lr_scheduler_params or {}, average_grads_over_dp=self.dp_mode == 'gradient',
+            use_cuda_graphs=kwargs.get('use_cuda_graphs', self.device.type == 'cuda'))
         self.optimizer = self.compute_session.optimizer
         self.lr_scheduler = self.compute_session.lr_scheduler
         self.comm_session = Communication(

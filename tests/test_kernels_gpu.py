@@ -211,8 +211,13 @@ def test_bert_small_native_vs_torch_backend():
         results[backend] = (float(loss), {n: p.grad.float().clone() for n, p in model.named_parameters() if p.grad is not None})
     ops.set_backend('native')
     assert abs(results['native'][0] - results['torch'][0]) < 3e-2 * abs(results['torch'][0])
-    worst = max(_rel_err(results['native'][1][n], g) for n, g in results['torch'][1].items() if g.norm() > 0)
-    assert worst < 0.15, worst
+    # some gradients are mathematically ~0 (e.g. key biases: softmax is shift invariant), so errors are
+    # measured against the typical gradient magnitude rather than each tensor's own norm
+    ref = results['torch'][1]
+    floor = 1e-2 * max(float(g.norm()) for g in ref.values())
+    errs = {n: float((results['native'][1][n] - g).norm()) / (float(g.norm()) + floor) for n, g in ref.items()}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 0.1, (worst, errs[worst])
     from ravnest_b200.ops import native
     assert native.calls['gemm_fwd'] > 0 and native.calls['layernorm_fwd'] > 0
 
