@@ -20,6 +20,10 @@ int rvn_ce_forward(const void* logits, int ld, const int64_t* target, float* lse
 int rvn_ce_backward(const void* logits, int ld, const int64_t* target, const float* lse, const float* stats, const float* gscale,
                     void* dlogits, int ld_out, int rows, int V, int64_t ignore_index, cudaStream_t stream);
 int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, cudaStream_t stream);
+int rvn_fmha_forward(const void* qkv, void* out, float* lse, const float* kbias, int B, int S, int heads, int causal, float scale,
+                     cudaStream_t stream);
+int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const float* lse, const float* kbias, float* delta, float* dq_accum,
+                      void* dqkv, int B, int S, int heads, int causal, float scale, int num_sms, cudaStream_t stream);
 int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
 }
 
@@ -200,6 +204,44 @@ torch::Tensor act_bwd(const torch::Tensor& dy, const torch::Tensor& z, int64_t a
   return dz;
 }
 
+// qkv: [B, S, 3H] bf16 contiguous (q | k | v, heads of 64); kbias: optional [B, S] fp32 additive key bias.  Returns {out [B,S,H], lse [B,heads,S]}
+std::vector<torch::Tensor> fmha_fwd(const torch::Tensor& qkv, int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal,
+                                    double scale) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.is_contiguous() && qkv.scalar_type() == torch::kBFloat16 && qkv.dim() == 3, "fmha expects contiguous bf16 [B,S,3H]");
+  const int B = qkv.size(0), S = qkv.size(1), H = qkv.size(2) / 3;
+  TORCH_CHECK(H == heads * 64, "fmha kernel is specialised for head_dim 64");
+  auto out = torch::empty({B, S, H}, qkv.options());
+  auto lse = torch::empty({B, heads, S}, qkv.options().dtype(torch::kFloat32));
+  const float* kb = nullptr;
+  if (kbias.has_value() && kbias->defined()) {
+    TORCH_CHECK(kbias->is_contiguous() && kbias->scalar_type() == torch::kFloat32 && kbias->numel() == static_cast<int64_t>(B) * S, "bad kbias");
+    kb = kbias->data_ptr<float>();
+  }
+  check(rvn_fmha_forward(qkv.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), kb, B, S, static_cast<int>(heads), causal,
+                         static_cast<float>(scale), cur_stream()),
+        "fmha_fwd");
+  return {out, lse};
+}
+
+torch::Tensor fmha_bwd(const torch::Tensor& qkv, const torch::Tensor& out, const torch::Tensor& d_out, const torch::Tensor& lse,
+                       int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal, double scale) {
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.is_contiguous() && out.is_contiguous() && d_out.is_contiguous(), "fmha_bwd expects contiguous tensors");
+  const int B = qkv.size(0), S = qkv.size(1), H = qkv.size(2) / 3;
+  auto dqkv = torch::empty_like(qkv);
+  auto f32 = qkv.options().dtype(torch::kFloat32);
+  auto dq_accum = torch::zeros({B, S, H}, f32);
+  auto delta = torch::empty({B, heads, S}, f32);
+  const float* kb = nullptr;
+  if (kbias.has_value() && kbias->defined()) kb = kbias->data_ptr<float>();
+  check(rvn_fmha_backward(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr<float>(), kb, delta.data_ptr<float>(),
+                          dq_accum.data_ptr<float>(), dqkv.data_ptr(), B, S, static_cast<int>(heads), causal, static_cast<float>(scale),
+                          sm_count(), cur_stream()),
+        "fmha_bwd");
+  return dqkv;
+}
+
 // ---------------------------------------------------------------------------------------------- fused optimizers
 PeerPtrs make_peers(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank) {
   PeerPtrs pp{};
@@ -270,6 +312,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_bwd", &ce_bwd);
   m.def("column_sum", &column_sum);
   m.def("act_bwd", &act_bwd);
+  m.def("fmha_fwd", &fmha_fwd);
+  m.def("fmha_bwd", &fmha_bwd);
   m.def("fused_update", &fused_update);
   m.def("fused_lamb", &fused_lamb);
   m.def("fused_param_average", &fused_param_average);

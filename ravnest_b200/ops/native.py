@@ -147,11 +147,36 @@ def cross_entropy(logits, target, ignore_index=-100):
     return _CrossEntropy.apply(logits, target.contiguous(), ignore_index)
 
 
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads, kbias, causal):
+        qc = qkv.contiguous()
+        scale = 1.0 / math.sqrt(qc.shape[-1] // 3 // heads)
+        out, lse = C().fmha_fwd(qc, heads, kbias, causal, scale)
+        calls['fmha_fwd'] += 1
+        ctx.heads, ctx.causal, ctx.scale = heads, causal, scale
+        ctx.save_for_backward(qc, out, lse, kbias)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qc, out, lse, kbias = ctx.saved_tensors
+        dqkv = C().fmha_bwd(qc, out, d_out.contiguous(), lse, ctx.heads, kbias, ctx.causal, ctx.scale)
+        calls['fmha_bwd'] += 1
+        return dqkv, None, None, None
+
+
 def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
-    """Interim: library SDPA until ops/csrc/fmha_sm100.cu lands (tracked in DESIGN.md)."""
+    """Fused attention over packed qkv [B, S, 3H] -> [B, S, H] (tcgen05 FMHA, ops/csrc/fmha_sm100.cu)."""
     B, S, H3 = qkv.shape
     H = H3 // 3
     D = H // heads
+    if D == 64 and qkv.dtype == torch.bfloat16 and dropout_p == 0.0:
+        kbias = None
+        if key_padding_mask is not None:
+            kbias = torch.zeros(B, S, dtype=torch.float32, device=qkv.device).masked_fill_(~key_padding_mask.bool(), float('-inf'))
+        return _Attention.apply(qkv, heads, kbias, causal)
+    # head dims other than 64 / attention dropout: library SDPA (tracked in DESIGN.md as not-yet-native)
     q, k, v = qkv.view(B, S, 3, heads, D).permute(2, 0, 3, 1, 4)
     mask = None
     if key_padding_mask is not None:

@@ -142,6 +142,33 @@ def test_cross_entropy(rows, V):
     assert _rel_err(logits.grad, lr.grad) < 2e-2
 
 
+# ----------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize('B,S,heads,causal,padded', [(2, 128, 2, False, False), (8, 512, 12, False, True), (2, 384, 4, True, False),
+                                                     (3, 200, 2, False, True), (2, 200, 2, True, True)])
+def test_fmha_forward_backward(B, S, heads, causal, padded):
+    from ravnest_b200 import ops
+    torch.manual_seed(9)
+    H = heads * 64
+    qkv = _rand(B, S, 3 * H, scale=0.8).requires_grad_(True)
+    mask = None
+    if padded:
+        mask = torch.ones(B, S, dtype=torch.long, device=DEV)
+        for b in range(B):
+            mask[b, S - 7 * (b + 1):] = 0
+    out = ops.attention_qkv(qkv, heads, mask, causal, 0.0)
+    g = _rand(B, S, H)
+    out.backward(g)
+    ref_in = qkv.detach().float().requires_grad_(True)
+    ref = ops.reference_attention_qkv(ref_in, heads, mask, causal, 0.0)
+    ref.backward(g.float())
+    assert _rel_err(out, ref) < 2e-2
+    assert _rel_err(qkv.grad[..., 2 * H:], ref_in.grad[..., 2 * H:]) < 3e-2      # dV
+    assert _rel_err(qkv.grad[..., H:2 * H], ref_in.grad[..., H:2 * H]) < 3e-2    # dK
+    assert _rel_err(qkv.grad[..., :H], ref_in.grad[..., :H]) < 3e-2              # dQ
+    from ravnest_b200.ops import native
+    assert native.calls['fmha_fwd'] > 0 and native.calls['fmha_bwd'] > 0
+
+
 # ----------------------------------------------------------------------------------------------- fused optimizers
 class _FakeModule(torch.nn.Module):
     def __init__(self):
