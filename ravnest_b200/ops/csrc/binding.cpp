@@ -21,9 +21,10 @@ int rvn_ce_backward(const void* logits, int ld, const int64_t* target, const flo
                     void* dlogits, int ld_out, int rows, int V, int64_t ignore_index, cudaStream_t stream);
 int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, cudaStream_t stream);
 int rvn_fmha_forward(const void* qkv, void* out, float* lse, const float* kbias, int B, int S, int heads, int causal, float scale,
-                     cudaStream_t stream);
+                     const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const float* lse, const float* kbias, float* delta, float* dq_accum,
-                      void* dqkv, int B, int S, int heads, int causal, float scale, int num_sms, cudaStream_t stream);
+                      void* dqkv, int B, int S, int heads, int causal, float scale, const long long* rng, float dropout_p, int num_sms,
+                      cudaStream_t stream);
 int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
 }
 
@@ -205,8 +206,14 @@ torch::Tensor act_bwd(const torch::Tensor& dy, const torch::Tensor& z, int64_t a
 }
 
 // qkv: [B, S, 3H] bf16 contiguous (q | k | v, heads of 64); kbias: optional [B, S] fp32 additive key bias.  Returns {out [B,S,H], lse [B,heads,S]}
+const long long* rng_ptr(const c10::optional<torch::Tensor>& rng) {
+  if (!rng.has_value() || !rng->defined()) return nullptr;
+  TORCH_CHECK(rng->scalar_type() == torch::kInt64 && rng->numel() >= 2 && rng->is_cuda(), "rng state must be a CUDA int64[2] tensor");
+  return reinterpret_cast<const long long*>(rng->data_ptr<int64_t>());
+}
+
 std::vector<torch::Tensor> fmha_fwd(const torch::Tensor& qkv, int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal,
-                                    double scale) {
+                                    double scale, const c10::optional<torch::Tensor>& rng, double dropout_p) {
   c10::cuda::CUDAGuard guard(qkv.device());
   TORCH_CHECK(qkv.is_contiguous() && qkv.scalar_type() == torch::kBFloat16 && qkv.dim() == 3, "fmha expects contiguous bf16 [B,S,3H]");
   const int B = qkv.size(0), S = qkv.size(1), H = qkv.size(2) / 3;
@@ -219,13 +226,14 @@ std::vector<torch::Tensor> fmha_fwd(const torch::Tensor& qkv, int64_t heads, con
     kb = kbias->data_ptr<float>();
   }
   check(rvn_fmha_forward(qkv.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), kb, B, S, static_cast<int>(heads), causal,
-                         static_cast<float>(scale), cur_stream()),
+                         static_cast<float>(scale), rng_ptr(rng), static_cast<float>(dropout_p), cur_stream()),
         "fmha_fwd");
   return {out, lse};
 }
 
 torch::Tensor fmha_bwd(const torch::Tensor& qkv, const torch::Tensor& out, const torch::Tensor& d_out, const torch::Tensor& lse,
-                       int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal, double scale) {
+                       int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal, double scale,
+                       const c10::optional<torch::Tensor>& rng, double dropout_p) {
   c10::cuda::CUDAGuard guard(qkv.device());
   TORCH_CHECK(qkv.is_contiguous() && out.is_contiguous() && d_out.is_contiguous(), "fmha_bwd expects contiguous tensors");
   const int B = qkv.size(0), S = qkv.size(1), H = qkv.size(2) / 3;
@@ -237,7 +245,7 @@ torch::Tensor fmha_bwd(const torch::Tensor& qkv, const torch::Tensor& out, const
   if (kbias.has_value() && kbias->defined()) kb = kbias->data_ptr<float>();
   check(rvn_fmha_backward(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr<float>(), kb, delta.data_ptr<float>(),
                           dq_accum.data_ptr<float>(), dqkv.data_ptr(), B, S, static_cast<int>(heads), causal, static_cast<float>(scale),
-                          sm_count(), cur_stream()),
+                          rng_ptr(rng), static_cast<float>(dropout_p), sm_count(), cur_stream()),
         "fmha_bwd");
   return dqkv;
 }

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
 #include "sm100_ptx.cuh"
 
 namespace rvn {
@@ -33,6 +34,8 @@ struct FmhaParams {
   int causal;
   __nv_bfloat16* out;                // [B*S, H]
   float* lse;                        // [B, heads, S] natural-log LSE of the scaled scores
+  const long long* rng;              // {seed, step} on the device (dropout) or nullptr
+  float dropout_p;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -153,6 +156,11 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
     for (int i = 0; i < FM_D; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
     const float* kb = p.kbias ? p.kbias + static_cast<size_t>(b) * p.S : nullptr;
+    const bool use_drop = p.rng != nullptr && p.dropout_p > 0.f;
+    DropoutRng drng;
+    if (use_drop) drng.init(p.rng, p.dropout_p);
+    // dropout groups: 4 consecutive keys of one (batch, head, query) row
+    const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 3) / 4);
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
       const int k0 = j * FM_BLOCK;
@@ -193,6 +201,14 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
           if (k >= p.S || (p.causal && k > q)) s = -INFINITY;
           pr[i] = fast_exp2(s - m_use);
           rsum += pr[i];
+        }
+        if (use_drop) {                                // the row sum stays un-dropped; P fed to the PV product is dropped
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float sc[4];
+            drng.scales4(drow + ((k0 + c * 32 + i) >> 2), sc);
+            pr[i] *= sc[0]; pr[i + 1] *= sc[1]; pr[i + 2] *= sc[2]; pr[i + 3] *= sc[3];
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -252,6 +268,8 @@ struct FmhaBwdParams {
   const float* delta;                // [B, heads, S]  rowsum(dO * O)
   float* dq_accum;                   // [B*S, H] fp32, zero-initialised (atomic accumulation over kv tiles)
   __nv_bfloat16* dqkv;               // [B*S, 3H]  (dK, dV written here; dQ cast in afterwards)
+  const long long* rng;
+  float dropout_p;
 };
 
 // delta[b,h,q] = sum_d dO[q, h*64+d] * O[q, h*64+d]; one thread per (row, head)
@@ -403,10 +421,14 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     uint8_t* ds_smem = smem + BwdSmem::DS_OFF;
     const float* kb = p.kbias ? p.kbias + static_cast<size_t>(b) * p.S : nullptr;
     const size_t stat_base = (static_cast<size_t>(b) * p.heads + h) * p.S;
+    const bool use_drop = p.rng != nullptr && p.dropout_p > 0.f;
+    DropoutRng drng;
+    if (use_drop) drng.init(p.rng, p.dropout_p);
     int it = 0;
     for (int i = i_first; i < n_q_tiles; ++i, ++it) {
       const uint32_t ph = it & 1;
       const int q = i * FM_BLOCK + r;
+      const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 3) / 4);
       const bool q_ok = q < p.S;
       const float lse2 = q_ok ? p.lse[stat_base + q] * LOG2E : INFINITY;
       const float dlt = q_ok ? p.delta[stat_base + q] : 0.f;
@@ -427,7 +449,23 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
           const bool masked = !q_ok || k >= p.S || (p.causal && k > q);
           const float pj = masked ? 0.f : fast_exp2(s - lse2);
           pr[j] = pj;
-          ds[j] = pj * (__uint_as_float(dv[j]) - dlt) * p.scale;
+          ds[j] = __uint_as_float(dv[j]);
+        }
+        if (use_drop) {                                // Z = P o M feeds dV; dP = dZ o M
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float sc[4];
+            drng.scales4(drow + ((k0 + c * 32 + j) >> 2), sc);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float pj = pr[j + t];
+              ds[j + t] = pj * (ds[j + t] * sc[t] - dlt) * p.scale;
+              pr[j + t] = pj * sc[t];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ds[j] = pr[j] * (ds[j] - dlt) * p.scale;
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -519,7 +557,7 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
 
 // qkv: [B*S, 3H] bf16 contiguous; out: [B*S, H]; lse: [B, heads, S]; kbias: [B, S] fp32 or nullptr
 extern "C" int rvn_fmha_forward(const void* qkv, void* out, float* lse, const float* kbias, int B, int S, int heads, int causal,
-                                float scale, cudaStream_t stream) {
+                                float scale, const long long* rng, float dropout_p, cudaStream_t stream) {
   using namespace rvn;
   const int H = heads * FM_D;
   CUtensorMap map;
@@ -531,6 +569,8 @@ extern "C" int rvn_fmha_forward(const void* qkv, void* out, float* lse, const fl
   p.causal = causal;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
+  p.rng = rng;
+  p.dropout_p = dropout_p;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(rvn_fmha_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL) != cudaSuccess) return 2000;
@@ -543,8 +583,8 @@ extern "C" int rvn_fmha_forward(const void* qkv, void* out, float* lse, const fl
 
 // qkv [B*S,3H], o / d_o [B*S,H] bf16; lse [B,heads,S]; dqkv [B*S,3H] (fully written); dq_accum [B*S,H] fp32 zeroed; delta scratch
 extern "C" int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const float* lse, const float* kbias, float* delta,
-                                 float* dq_accum, void* dqkv, int B, int S, int heads, int causal, float scale, int num_sms,
-                                 cudaStream_t stream) {
+                                 float* dq_accum, void* dqkv, int B, int S, int heads, int causal, float scale, const long long* rng,
+                                 float dropout_p, int num_sms, cudaStream_t stream) {
   using namespace rvn;
   const int H = heads * FM_D;
   CUtensorMap map_qkv, map_do;
@@ -563,6 +603,8 @@ extern "C" int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o
   p.delta = delta;
   p.dq_accum = dq_accum;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.rng = rng;
+  p.dropout_p = dropout_p;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(rvn_fmha_bwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL) != cudaSuccess) return 2000;
