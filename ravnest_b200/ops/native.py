@@ -147,23 +147,45 @@ def cross_entropy(logits, target, ignore_index=-100):
     return _CrossEntropy.apply(logits, target.contiguous(), ignore_index)
 
 
+_RNG = {}
+
+
+def rng_state(device) -> torch.Tensor:
+    """Device-resident {seed, step} used by every dropout-bearing kernel (Philox counter RNG).  ``step`` is bumped
+    by one tiny device op per consumer call, so CUDA-graph replays keep drawing fresh masks and a backward /
+    recompute replays its forward's mask from the snapshot it saved."""
+    key = (device.type, device.index)
+    if key not in _RNG:
+        seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        _RNG[key] = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+    return _RNG[key]
+
+
+def next_rng_snapshot(device) -> torch.Tensor:
+    state = rng_state(device)
+    snap = state.clone()
+    state[1:].add_(1)
+    return snap
+
+
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, heads, kbias, causal):
+    def forward(ctx, qkv, heads, kbias, causal, dropout_p):
         qc = qkv.contiguous()
         scale = 1.0 / math.sqrt(qc.shape[-1] // 3 // heads)
-        out, lse = C().fmha_fwd(qc, heads, kbias, causal, scale)
+        rng = next_rng_snapshot(qc.device) if dropout_p > 0.0 else None
+        out, lse = C().fmha_fwd(qc, heads, kbias, causal, scale, rng, dropout_p)
         calls['fmha_fwd'] += 1
-        ctx.heads, ctx.causal, ctx.scale = heads, causal, scale
-        ctx.save_for_backward(qc, out, lse, kbias)
+        ctx.heads, ctx.causal, ctx.scale, ctx.dropout_p = heads, causal, scale, dropout_p
+        ctx.save_for_backward(qc, out, lse, kbias, rng)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        qc, out, lse, kbias = ctx.saved_tensors
-        dqkv = C().fmha_bwd(qc, out, d_out.contiguous(), lse, ctx.heads, kbias, ctx.causal, ctx.scale)
+        qc, out, lse, kbias, rng = ctx.saved_tensors
+        dqkv = C().fmha_bwd(qc, out, d_out.contiguous(), lse, ctx.heads, kbias, ctx.causal, ctx.scale, rng, ctx.dropout_p)
         calls['fmha_bwd'] += 1
-        return dqkv, None, None, None
+        return dqkv, None, None, None, None
 
 
 def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
@@ -171,12 +193,12 @@ def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0
     B, S, H3 = qkv.shape
     H = H3 // 3
     D = H // heads
-    if D == 64 and qkv.dtype == torch.bfloat16 and dropout_p == 0.0:
+    if D == 64 and qkv.dtype == torch.bfloat16:
         kbias = None
         if key_padding_mask is not None:
             kbias = torch.zeros(B, S, dtype=torch.float32, device=qkv.device).masked_fill_(~key_padding_mask.bool(), float('-inf'))
-        return _Attention.apply(qkv, heads, kbias, causal)
-    # head dims other than 64 / attention dropout: library SDPA (tracked in DESIGN.md as not-yet-native)
+        return _Attention.apply(qkv, heads, kbias, causal, float(dropout_p))
+    # head dims other than 64: library SDPA (tracked in DESIGN.md as not-yet-native)
     q, k, v = qkv.view(B, S, 3, heads, D).permute(2, 0, 3, 1, 4)
     mask = None
     if key_padding_mask is not None:

@@ -169,6 +169,38 @@ def test_fmha_forward_backward(B, S, heads, causal, padded):
     assert native.calls['fmha_fwd'] > 0 and native.calls['fmha_bwd'] > 0
 
 
+def test_fmha_dropout_is_replayable_and_unbiased():
+    """Backward must regenerate exactly the forward's mask: with V = identity-like probes the dropped
+    probabilities can be read back, and grads must match a reference that uses the same mask."""
+    from ravnest_b200.ops import native
+    torch.manual_seed(10)
+    B, S, heads, p = 2, 128, 2, 0.25
+    H = heads * 64
+    qkv = _rand(B, S, 3 * H, scale=0.5)
+    qkv[..., 2 * H:] = 0
+    for h in range(heads):                              # V_h = [I_64 ; 0]: out[q, d] = dropped P[q, key d]
+        qkv[:, :64, 2 * H + h * 64:2 * H + (h + 1) * 64] = torch.eye(64, device=DEV, dtype=torch.bfloat16)
+    qkv = qkv.detach().requires_grad_(True)
+    out = native.attention_qkv(qkv, heads, None, False, p)
+    q, k = qkv[..., :H].float().view(B, S, heads, 64), qkv[..., H:2 * H].float().view(B, S, heads, 64)
+    probs = torch.softmax(torch.einsum('bqhd,bkhd->bhqk', q, k) / 8.0, dim=-1)[..., :64]       # [B,h,S,64]
+    got = out.float().view(B, S, heads, 64).permute(0, 2, 1, 3)
+    kept = got > 0
+    frac = float(kept.float().mean())
+    assert abs(frac - (1 - p)) < 0.03, frac
+    assert _rel_err(got[kept], (probs / (1 - p))[kept]) < 3e-2
+    # replay: same snapshot -> identical mask in backward; compare dV against the reference built from the observed mask
+    g = _rand(B, S, H)
+    out.backward(g)
+    mask = kept.float() / (1 - p)
+    z = (probs * mask)                                                                           # [B,h,S,64] dropped probs for keys 0..63
+    dv_ref = torch.einsum('bhqk,bqhd->bkhd', z, g.float().view(B, S, heads, 64))                 # keys 0..63 only
+    dv = qkv.grad[..., 2 * H:].float().view(B, S, heads, 64)[:, :64]
+    assert _rel_err(dv, dv_ref) < 5e-2
+    out2 = native.attention_qkv(qkv.detach(), heads, None, False, p)
+    assert not torch.equal(out2, out)                  # the step counter advanced: a fresh mask
+
+
 # ----------------------------------------------------------------------------------------------- fused optimizers
 class _FakeModule(torch.nn.Module):
     def __init__(self):
