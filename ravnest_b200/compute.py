@@ -48,9 +48,10 @@ def _flatten_outputs(out: Any) -> List[torch.Tensor]:
 
 class Flight:
     """Book-keeping for one in-flight forward pass."""
-    __slots__ = ('fpid', 'slot', 'inputs', 'outputs', 'rng', 'recomputed')
+    __slots__ = ('fpid', 'slot', 'inputs', 'outputs', 'rng', 'recomputed', 'graph')
 
-    def __init__(self, fpid, slot, inputs, outputs, rng):
+    def __init__(self, fpid, slot, inputs, outputs, rng, graph=None):
+        self.graph = graph
         self.fpid = fpid
         self.slot: Slot = slot
         self.inputs: List[torch.Tensor] = inputs
@@ -91,6 +92,8 @@ class Compute:
         self._graph = None
         self._graph_seen = 0
         self._graph_failed = False
+        self._stage_graphs = []
+        self._max_stage_graphs = cluster_length + 2
         self.loss_readback = False          # copy every step's loss to pinned host memory (async D2H)
         self._loss_host = None
         self.loss_history: List[Any] = []
@@ -162,11 +165,40 @@ class Compute:
                     out = self._call(slot, inputs)
                 self.flights[fpid] = Flight(fpid, slot, inputs, None, rng)
                 return out
+            if self.use_graphs and self.device.type == 'cuda':
+                gs = self._stage_graph_for(args, input_grads)
+                if gs is not None:
+                    out = gs.run_forward(args)
+                    self.flights[fpid] = Flight(fpid, slot, [], [], None, graph=gs)
+                    return out
             inputs = self._prepare_inputs(args, need_grad=input_grads)
             with torch.enable_grad():
                 out = self._call(slot, inputs)
             self.flights[fpid] = Flight(fpid, slot, inputs, _flatten_outputs(out), None)
             return _detach_tree(out)
+
+    def _stage_graph_for(self, args, input_grads):
+        """A free GraphedStage for this input signature (captured lazily after the eager warm-up)."""
+        from .runtime.graphs import GraphedStage, _signature
+        if self._graph_failed:
+            return None
+        sig = _signature(args, None)
+        for gs in self._stage_graphs:
+            if not gs.busy and gs.signature == sig:
+                return gs
+        self._graph_seen += 1
+        if self._graph_seen <= self.graph_warmup or len(self._stage_graphs) >= self._max_stage_graphs:
+            return None
+        try:
+            gs = GraphedStage(self, self._prepare_inputs(args, need_grad=False), input_grads)
+            self._stage_graphs.append(gs)
+            return gs
+        except Exception as err:
+            self._graph_failed = True
+            import warnings
+            warnings.warn('CUDA-graph capture of the stage failed, running eagerly: {!r}'.format(err))
+            torch.cuda.synchronize(self.device)
+            return None
 
     def recompute_forward(self, fpid: int, input_grads: bool = True) -> None:
         """Re-run fpid's forward WITH grad on its stashed weight version and RNG stream
@@ -195,6 +227,12 @@ class Compute:
         gradient for every stage input (``None`` for non-differentiable inputs)."""
         with self.lock:
             fl = self.flights[fpid]
+            if fl.graph is not None:
+                in_grads = fl.graph.run_backward(grads)
+                self.store.release(fl.slot)
+                del self.flights[fpid]
+                self._after_backward(update)
+                return in_grads
             if not fl.recomputed:
                 self.recompute_forward(fpid)
             outs, gs = [], []

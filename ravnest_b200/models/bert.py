@@ -58,9 +58,6 @@ class BertSelfOutput(nn.Module):
         self.LayerNorm = rnn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
         self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
 
-    def forward(self, hidden, residual):
-        return self.LayerNorm(self.dropout(self.dense(hidden)), residual)
-
 
 class BertAttention(nn.Module):
     def __init__(self, cfg):
@@ -68,17 +65,11 @@ class BertAttention(nn.Module):
         self.self = rnn.SelfAttention(cfg.hidden_size, cfg.num_attention_heads, cfg.attention_probs_dropout_prob)
         self.output = BertSelfOutput(cfg)
 
-    def forward(self, x, mask):
-        return self.output(self.self(x, mask), x)
-
 
 class BertIntermediate(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.dense = rnn.Linear(cfg.hidden_size, cfg.intermediate_size, activation='gelu')
-
-    def forward(self, x):
-        return self.dense(x)
 
 
 class BertOutput(nn.Module):
@@ -88,20 +79,31 @@ class BertOutput(nn.Module):
         self.LayerNorm = rnn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
         self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
 
-    def forward(self, hidden, residual):
-        return self.LayerNorm(self.dropout(self.dense(hidden)), residual)
-
 
 class BertLayer(nn.Module):
+    """One encoder block, a single FX leaf so the whole block runs as six fused kernels forward:
+    QKV GEMM(+bias) -> FMHA(+mask, +dropout) -> proj GEMM(+bias) -> LN(dropout(.)+residual) ->
+    FFN1 GEMM(+bias+GELU) / FFN2 GEMM(+bias) -> LN(dropout(.)+residual).
+    Sub-module / parameter names follow HF (attention.self / attention.output / intermediate / output)."""
+    _ravnest_leaf = True
+
     def __init__(self, cfg):
         super().__init__()
         self.attention = BertAttention(cfg)
         self.intermediate = BertIntermediate(cfg)
         self.output = BertOutput(cfg)
+        self.hidden_dropout = cfg.hidden_dropout_prob
 
     def forward(self, x, mask):
-        a = self.attention(x, mask)
-        return self.output(self.intermediate(a), a)
+        from .. import ops
+        p = self.hidden_dropout if self.training else 0.0
+        att, out = self.attention, self.output
+        ctx = att.self(x, mask)
+        a = att.output.dense(ctx)
+        a = ops.layer_norm(a, att.output.LayerNorm.weight, att.output.LayerNorm.bias, att.output.LayerNorm.eps, x, p)
+        inter = self.intermediate.dense
+        h = ops.mlp(a, inter.weight, inter.bias, out.dense.weight, out.dense.bias, inter.activation)
+        return ops.layer_norm(h, out.LayerNorm.weight, out.LayerNorm.bias, out.LayerNorm.eps, a, p)
 
 
 class BertEncoder(nn.Module):

@@ -62,7 +62,7 @@ class CausalSelfAttention(nn.Module):
 
     def __init__(self, cfg):
         super().__init__()
-        self.core = rnn.SelfAttention(cfg.n_embd, cfg.n_head, cfg.attn_pdrop, causal=True, fused_qkv=True)
+        self.core = rnn.SelfAttention(cfg.n_embd, cfg.n_head, cfg.attn_pdrop, causal=True, qkv_name='c_attn')
         self.c_attn = self.core.c_attn
         self.c_proj = rnn.Linear(cfg.n_embd, cfg.n_embd)
         self.resid_dropout = nn.Dropout(cfg.resid_pdrop)

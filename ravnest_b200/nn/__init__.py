@@ -50,36 +50,42 @@ class Dropout(nn.Dropout):
 
 
 class SelfAttention(nn.Module):
-    """Multi-head self-attention core: fused QKV projection -> FMHA -> output projection is left to
-    the caller.  Parameter layout matches HF BERT's ``attention.self`` when ``fused_qkv=False``
-    (``query``/``key``/``value`` Linear) and minGPT's ``c_attn`` when ``fused_qkv=True``."""
+    """Multi-head self-attention core: one fused QKV projection (a single [3H, H] parameter, so no per-step
+    ``cat`` of q/k/v weights) -> FMHA kernel.  The output projection is left to the caller.
 
-    def __init__(self, hidden, heads, dropout=0.0, causal=False, fused_qkv=False):
+    ``qkv_name`` is the attribute the fused Linear is registered under ('c_attn' for minGPT checkpoints,
+    'qkv' for BERT).  HF BERT checkpoints with separate ``query``/``key``/``value`` tensors are merged on load."""
+
+    def __init__(self, hidden, heads, dropout=0.0, causal=False, fused_qkv=True, qkv_name='qkv'):
         super().__init__()
         assert hidden % heads == 0
         self.hidden, self.heads, self.head_dim = hidden, heads, hidden // heads
         self.causal = causal
         self.dropout_p = dropout
-        self.fused_qkv = fused_qkv
-        if fused_qkv:
-            self.c_attn = Linear(hidden, 3 * hidden)
-        else:
-            self.query = Linear(hidden, hidden)
-            self.key = Linear(hidden, hidden)
-            self.value = Linear(hidden, hidden)
+        self.qkv_name = qkv_name
+        self.add_module(qkv_name, Linear(hidden, 3 * hidden))
+        self._register_load_state_dict_pre_hook(self._merge_hf_qkv)
+
+    def _merge_hf_qkv(self, state_dict, prefix, *_):
+        for kind in ('weight', 'bias'):
+            keys = [prefix + '{}.{}'.format(n, kind) for n in ('query', 'key', 'value')]
+            if all(k in state_dict for k in keys):
+                state_dict[prefix + '{}.{}'.format(self.qkv_name, kind)] = torch.cat([state_dict.pop(k) for k in keys], dim=0)
+
+    @property
+    def qkv_proj(self):
+        return getattr(self, self.qkv_name)
+
+    def split_qkv_state(self):
+        """HF-style {query,key,value}.{weight,bias} views of the fused parameter (export helper)."""
+        w, b = self.qkv_proj.weight, self.qkv_proj.bias
+        H = self.hidden
+        return {'{}.{}'.format(n, k): t[i * H:(i + 1) * H] for i, n in enumerate(('query', 'key', 'value')) for k, t in (('weight', w), ('bias', b))}
 
     def forward(self, x, key_padding_mask=None):
         """x: [B, S, H]; key_padding_mask: [B, S] with 1 = attend, 0 = padding (HF convention)."""
-        B, S, _ = x.shape
-        if self.fused_qkv:
-            qkv = self.c_attn(x)
-        else:
-            w = torch.cat([self.query.weight, self.key.weight, self.value.weight], dim=0)
-            b = torch.cat([self.query.bias, self.key.bias, self.value.bias], dim=0)
-            qkv = ops.linear(x, w, b, None)
-        out = ops.attention_qkv(qkv, self.heads, key_padding_mask, self.causal,
-                                self.dropout_p if self.training else 0.0)
-        return out
+        qkv = self.qkv_proj(x)
+        return ops.attention_qkv(qkv, self.heads, key_padding_mask, self.causal, self.dropout_p if self.training else 0.0)
 
 
 class GELU(nn.Module):

@@ -283,7 +283,7 @@ class Node:
             self._after_backward(fpid, epoch_change=targets[1])
             return
         out = self.compute_session.forward(fpid, args, input_grads=False)
-        inputs = self.compute_session.flights[fpid].inputs
+        inputs = self.compute_session.flights[fpid].inputs or args
         data = self.plan.root_payload(out, inputs, self.compression)
         self.transport.send(FORWARD, make_message(ActionTypes.FORWARD, fpid, data))
         self.metrics['forward'] += 1

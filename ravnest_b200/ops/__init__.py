@@ -51,7 +51,9 @@ def reference_linear(x, weight, bias=None, activation=None):
     return _act(F.linear(x, weight, bias), activation)
 
 
-def reference_layer_norm(x, weight, bias, eps=1e-5, residual=None):
+def reference_layer_norm(x, weight, bias, eps=1e-5, residual=None, dropout_p=0.0):
+    if dropout_p > 0.0:
+        x = F.dropout(x, dropout_p, True)
     if residual is not None:
         x = x + residual
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
@@ -97,11 +99,20 @@ def linear(x, weight, bias=None, activation=None):
     return reference_linear(x, weight, bias, activation)
 
 
-def layer_norm(x, weight, bias, eps=1e-5, residual=None):
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, dropout_p=0.0):
+    """``LN(dropout(x) + residual)``"""
     if _native(x, weight):
         from . import native
-        return native.layer_norm(x, weight, bias, eps, residual)
-    return reference_layer_norm(x, weight, bias, eps, residual)
+        return native.layer_norm(x, weight, bias, eps, residual, dropout_p)
+    return reference_layer_norm(x, weight, bias, eps, residual, dropout_p)
+
+
+def mlp(x, w1, b1, w2, b2, activation='gelu'):
+    """``act(x W1^T + b1) W2^T + b2``"""
+    if _native(x, w1):
+        from . import native
+        return native.mlp(x, w1, b1, w2, b2, activation)
+    return reference_linear(reference_linear(x, w1, b1, activation), w2, b2, None)
 
 
 def embedding(idx, weight):
@@ -131,6 +142,6 @@ def native_ops_loaded():
         return {}
 
 
-__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
            'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
            'reference_cross_entropy']

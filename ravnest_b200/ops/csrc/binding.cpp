@@ -9,17 +9,18 @@
 
 extern "C" {
 int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
-                  const void* bias, int act, const void* dact_in, int ld_dact, void* preact_out, int ld_preact, int block_n,
-                  int num_sms, cudaStream_t stream);
+                  const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out, int ld_preact,
+                  int block_n, int num_sms, cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
-                          float* rstd, int rows, int H, float eps, cudaStream_t stream);
-int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dx,
-                           float* dgamma, float* dbeta, int rows, int H, int num_sms, cudaStream_t stream);
+                          float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
+int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
+                           void* dx_drop, void* dgamma, void* dbeta, float* partial, int max_ctas, int rows, int H, const long long* rng,
+                           float dropout_p, cudaStream_t stream);
 int rvn_ce_forward(const void* logits, int ld, const int64_t* target, float* lse, float* stats, float* loss, int rows, int V,
                    int64_t ignore_index, cudaStream_t stream);
 int rvn_ce_backward(const void* logits, int ld, const int64_t* target, const float* lse, const float* stats, const float* gscale,
                     void* dlogits, int ld_out, int rows, int V, int64_t ignore_index, cudaStream_t stream);
-int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, cudaStream_t stream);
+int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, int num_sms, cudaStream_t stream);
 int rvn_fmha_forward(const void* qkv, void* out, float* lse, const float* kbias, int B, int S, int heads, int causal, float scale,
                      const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const float* lse, const float* kbias, float* delta, float* dq_accum,
@@ -77,7 +78,8 @@ int ld_of(const torch::Tensor& t) {
 // Returns {D} or {D, preact}.  D is allocated with a row stride rounded up to 8 elements; a narrowed view is returned.
 std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::Tensor& B, bool b_mn,
                                 const c10::optional<torch::Tensor>& bias, int64_t act,
-                                const c10::optional<torch::Tensor>& dact_in, bool store_preact, int64_t block_n) {
+                                const c10::optional<torch::Tensor>& dact_in, bool store_preact, int64_t block_n,
+                                int64_t aux_mode, const c10::optional<torch::Tensor>& out) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16,
               "gemm expects CUDA bf16 operands");
   c10::cuda::CUDAGuard guard(A.device());
@@ -86,8 +88,15 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   const int N = b_mn ? B.size(1) : B.size(0);
   TORCH_CHECK((b_mn ? B.size(0) : B.size(1)) == K, "inner dimensions differ");
   const int lda = ld_of(A), ldb = ld_of(B);
-  const int ldd = (N + 7) / 8 * 8;
-  auto D = torch::empty({M, ldd}, A.options());
+  int ldd = (N + 7) / 8 * 8;
+  torch::Tensor D;
+  if (out.has_value() && out->defined()) {           // write (or accumulate, aux_mode 2) straight into a caller-owned buffer
+    TORCH_CHECK(out->dim() == 2 && out->size(0) == M && out->size(1) == N && out->scalar_type() == torch::kBFloat16, "bad out tensor");
+    ldd = ld_of(*out);
+    D = *out;
+  } else {
+    D = torch::empty({M, ldd}, A.options());
+  }
   torch::Tensor P;
   const void* bias_ptr = nullptr;
   if (bias.has_value() && bias->defined()) {
@@ -104,7 +113,7 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   }
   void* preact_ptr = nullptr;
   if (store_preact) {
-    P = torch::empty({M, ldd}, A.options());
+    P = torch::empty({M, (N + 7) / 8 * 8}, A.options());
     preact_ptr = P.data_ptr();
   }
   if (block_n <= 0) {
@@ -113,16 +122,24 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
     block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
   }
   check(rvn_gemm_bf16(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
-                      dact_ptr, ld_dact, preact_ptr, ldd, static_cast<int>(block_n), sm_count(), cur_stream()),
+                      dact_ptr, ld_dact, static_cast<int>(aux_mode), preact_ptr, store_preact ? static_cast<int>(P.stride(0)) : ldd,
+                      static_cast<int>(block_n), sm_count(), cur_stream()),
         "gemm_bf16");
-  std::vector<torch::Tensor> out;
-  out.push_back(ldd == N ? D : D.narrow(1, 0, N));
-  if (store_preact) out.push_back(ldd == N ? P : P.narrow(1, 0, N));
-  return out;
+  std::vector<torch::Tensor> res;
+  res.push_back(D.size(1) == N ? D : D.narrow(1, 0, N));
+  if (store_preact) res.push_back(P.size(1) == N ? P : P.narrow(1, 0, N));
+  return res;
 }
 
+const long long* rng_ptr(const c10::optional<torch::Tensor>& rng) {
+  if (!rng.has_value() || !rng->defined()) return nullptr;
+  TORCH_CHECK(rng->scalar_type() == torch::kInt64 && rng->numel() >= 2 && rng->is_cuda(), "rng state must be a CUDA int64[2] tensor");
+  return reinterpret_cast<const long long*>(rng->data_ptr<int64_t>());
+}
+
+// y = LN(dropout(x) + res).  Returns {y, mean, rstd} (+ {sum} when a residual or dropout makes it differ from x)
 std::vector<torch::Tensor> layernorm_fwd(const torch::Tensor& x, const c10::optional<torch::Tensor>& res, const torch::Tensor& gamma,
-                                         const torch::Tensor& beta, double eps) {
+                                         const torch::Tensor& beta, double eps, const c10::optional<torch::Tensor>& rng, double dropout_p) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kBFloat16, "layernorm expects contiguous bf16");
   const int H = x.size(-1);
@@ -133,31 +150,43 @@ std::vector<torch::Tensor> layernorm_fwd(const torch::Tensor& x, const c10::opti
   torch::Tensor sum;
   const void* res_ptr = nullptr;
   void* sum_ptr = nullptr;
-  if (res.has_value() && res->defined()) {
+  const bool has_res = res.has_value() && res->defined();
+  const long long* rp = dropout_p > 0.0 ? rng_ptr(rng) : nullptr;
+  if (has_res) {
     TORCH_CHECK(res->is_contiguous() && res->sizes() == x.sizes(), "residual must match x");
-    sum = torch::empty_like(x);
     res_ptr = res->data_ptr();
+  }
+  if (has_res || rp != nullptr) {
+    sum = torch::empty_like(x);
     sum_ptr = sum.data_ptr();
   }
   check(rvn_layernorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), sum_ptr,
-                              mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, H, static_cast<float>(eps), cur_stream()),
+                              mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, H, static_cast<float>(eps), rp,
+                              static_cast<float>(dropout_p), cur_stream()),
         "layernorm_fwd");
   if (sum.defined()) return {y, mean, rstd, sum};
   return {y, mean, rstd};
 }
 
+// returns {dsum (grad of the normalised sum == grad of the residual), dx (== dsum, or dsum o mask with dropout), dgamma, dbeta}
 std::vector<torch::Tensor> layernorm_bwd(const torch::Tensor& dy, const torch::Tensor& x, const torch::Tensor& gamma,
-                                         const torch::Tensor& mean, const torch::Tensor& rstd) {
+                                         const torch::Tensor& mean, const torch::Tensor& rstd, const c10::optional<torch::Tensor>& rng,
+                                         double dropout_p) {
   c10::cuda::CUDAGuard guard(x.device());
   const int H = x.size(-1);
   const int rows = x.numel() / H;
-  auto dx = torch::empty_like(x);
-  auto dgamma = torch::zeros({H}, x.options().dtype(torch::kFloat32));
-  auto dbeta = torch::zeros({H}, x.options().dtype(torch::kFloat32));
+  auto dsum = torch::empty_like(x);
+  const long long* rp = dropout_p > 0.0 ? rng_ptr(rng) : nullptr;
+  torch::Tensor dx = rp != nullptr ? torch::empty_like(x) : dsum;
+  auto dgamma = torch::empty({H}, x.options());
+  auto dbeta = torch::empty({H}, x.options());
+  const int max_ctas = sm_count() * 2;
+  auto partial = torch::empty({static_cast<int64_t>(max_ctas) * 2 * H}, x.options().dtype(torch::kFloat32));
   check(rvn_layernorm_backward(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
-                               dx.data_ptr(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), rows, H, sm_count(), cur_stream()),
+                               dsum.data_ptr(), rp != nullptr ? dx.data_ptr() : nullptr, dgamma.data_ptr(), dbeta.data_ptr(),
+                               partial.data_ptr<float>(), max_ctas, rows, H, rp, static_cast<float>(dropout_p), cur_stream()),
         "layernorm_bwd");
-  return {dx, dgamma, dbeta};
+  return {dsum, dx, dgamma, dbeta};
 }
 
 // returns {loss (scalar fp32), lse [rows], stats [2]}
@@ -192,7 +221,7 @@ torch::Tensor column_sum(const torch::Tensor& x) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == torch::kBFloat16, "column_sum expects 2-D bf16");
   auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
-  check(rvn_column_sum(x.data_ptr(), x.stride(0), out.data_ptr<float>(), x.size(0), x.size(1), cur_stream()), "column_sum");
+  check(rvn_column_sum(x.data_ptr(), x.stride(0), out.data_ptr<float>(), x.size(0), x.size(1), sm_count(), cur_stream()), "column_sum");
   return out;
 }
 
@@ -206,12 +235,6 @@ torch::Tensor act_bwd(const torch::Tensor& dy, const torch::Tensor& z, int64_t a
 }
 
 // qkv: [B, S, 3H] bf16 contiguous (q | k | v, heads of 64); kbias: optional [B, S] fp32 additive key bias.  Returns {out [B,S,H], lse [B,heads,S]}
-const long long* rng_ptr(const c10::optional<torch::Tensor>& rng) {
-  if (!rng.has_value() || !rng->defined()) return nullptr;
-  TORCH_CHECK(rng->scalar_type() == torch::kInt64 && rng->numel() >= 2 && rng->is_cuda(), "rng state must be a CUDA int64[2] tensor");
-  return reinterpret_cast<const long long*>(rng->data_ptr<int64_t>());
-}
-
 std::vector<torch::Tensor> fmha_fwd(const torch::Tensor& qkv, int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal,
                                     double scale, const c10::optional<torch::Tensor>& rng, double dropout_p) {
   c10::cuda::CUDAGuard guard(qkv.device());
@@ -313,7 +336,9 @@ void fused_param_average(const std::vector<int64_t>& src_ptrs, const std::vector
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.def("gemm", &gemm, "bf16 tcgen05 GEMM with fused epilogue");
+  m.def("gemm", &gemm, "bf16 tcgen05 GEMM with fused epilogue", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
+        py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("aux_in") = py::none(), py::arg("store_preact") = false,
+        py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none());
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("ce_fwd", &ce_fwd);

@@ -32,8 +32,9 @@ enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_TANH = 2, ACT_RELU = 3 };
 struct GemmParams {
   int M, N, K;
   const __nv_bfloat16* bias;      // [N] or nullptr
-  const __nv_bfloat16* dact_in;   // [M, ld_aux] pre-activation (dact mode: D = acc * act'(z)) or nullptr
+  const __nv_bfloat16* dact_in;   // [M, ld_aux] auxiliary input tile or nullptr
   int ld_aux;
+  int aux_mode;                   // 1: D = acc * act'(aux)  (activation gradient)   2: D = acc + aux  (gradient accumulation)
   int act;                        // Act
   int store_preact;               // also write the pre-activation through map_aux
   int num_m_blocks, num_n_blocks, num_k_blocks;
@@ -269,8 +270,13 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float2 zf = __bfloat1622float2(z2[j]);
-                    f[i + 2 * j] *= apply_dact(zf.x, p.act);
-                    f[i + 2 * j + 1] *= apply_dact(zf.y, p.act);
+                    if (p.aux_mode == 2) {
+                      f[i + 2 * j] += zf.x;
+                      f[i + 2 * j + 1] += zf.y;
+                    } else {
+                      f[i + 2 * j] *= apply_dact(zf.x, p.act);
+                      f[i + 2 * j + 1] *= apply_dact(zf.y, p.act);
+                    }
                   }
                 }
               }
@@ -378,13 +384,14 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 
 // C entry point used by binding.cpp.  Layout flags: a_mn / b_mn = operand stored [K, rows] instead of [rows, K].
 extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
-                             int K, const void* bias, int act, const void* dact_in, int ld_dact, void* preact_out,
+                             int K, const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out,
                              int ld_preact, int block_n, int num_sms, cudaStream_t stream) {
   rvn::GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.dact_in = static_cast<const __nv_bfloat16*>(dact_in);
   p.ld_aux = ld_dact;
+  p.aux_mode = dact_in != nullptr ? aux_mode : 0;
   p.act = act;
   p.store_preact = preact_out != nullptr ? 1 : 0;
 #define RVN_DISPATCH(BN_)                                                                                              \

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "philox.cuh"
+
 namespace rvn {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -40,18 +42,22 @@ struct bf16x8 {
 };
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; each lane owns VPL 8-element vectors (H = 8 * 32 * VPL at most; tail lanes masked)
+// y = LN(dropout(x) + residual).  One warp per row; each lane owns VPL 8-element vectors.  The pre-norm sum s is
+// written (bf16) whenever it differs from x, because backward re-reads exactly what was normalised.
 template <int VPL>
 __global__ void __launch_bounds__(256) rvn_layernorm_fwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                          const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                                                          __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ sum_out,
                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int H,
-                                                         float eps) {
+                                                         float eps, const long long* __restrict__ rng, float dropout_p) {
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = H >> 3;
+  const bool use_drop = rng != nullptr && dropout_p > 0.f;
+  DropoutRng drng;
+  if (use_drop) drng.init(rng, dropout_p);
   float v[VPL][8];
   float s = 0.f;
 #pragma unroll
@@ -61,6 +67,16 @@ __global__ void __launch_bounds__(256) rvn_layernorm_fwd(const __nv_bfloat16* __
       bf16x8 a;
       a.load(x + static_cast<size_t>(row) * H + vec * 8);
       a.to_float(v[i]);
+      if (use_drop) {
+        const unsigned long long g = (static_cast<unsigned long long>(row) * H + vec * 8) >> 2;
+        float sc[4];
+        drng.scales4(g, sc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] *= sc[j];
+        drng.scales4(g + 1, sc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][4 + j] *= sc[j];
+      }
       if (res != nullptr) {
         bf16x8 r;
         float rf[8];
@@ -68,12 +84,12 @@ __global__ void __launch_bounds__(256) rvn_layernorm_fwd(const __nv_bfloat16* __
         r.to_float(rf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += rf[j];
-        if (sum_out != nullptr) {
-          bf16x8 o;
-          o.from_float(v[i]);
-          o.store(sum_out + static_cast<size_t>(row) * H + vec * 8);
-          o.to_float(v[i]);          // normalise exactly what backward will re-read
-        }
+      }
+      if (sum_out != nullptr) {
+        bf16x8 o;
+        o.from_float(v[i]);
+        o.store(sum_out + static_cast<size_t>(row) * H + vec * 8);
+        o.to_float(v[i]);            // normalise exactly what backward will re-read
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -114,18 +130,22 @@ __global__ void __launch_bounds__(256) rvn_layernorm_fwd(const __nv_bfloat16* __
   }
 }
 
-// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat ; dbeta += dy  (fp32 atomics per CTA)
+// dsum = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dx = dsum o dropout-mask (regenerated), dres = dsum.
+// Per-CTA partial dgamma / dbeta go to partial[cta][2][H]; rvn_layernorm_bwd_reduce sums them (no global atomics).
 template <int VPL>
 __global__ void __launch_bounds__(256) rvn_layernorm_bwd(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                          const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
-                                                         const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int H,
-                                                         int rows_per_block) {
+                                                         const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dsum_out,
+                                                         __nv_bfloat16* __restrict__ dx_drop_out, float* __restrict__ partial, int rows,
+                                                         int H, int rows_per_block, const long long* __restrict__ rng, float dropout_p) {
   extern __shared__ float red[];          // [2][H] partial dgamma / dbeta of this CTA
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const int nvec = H >> 3;
+  const bool use_drop = rng != nullptr && dropout_p > 0.f && dx_drop_out != nullptr;
+  DropoutRng drng;
+  if (use_drop) drng.init(rng, dropout_p);
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   float gf[VPL][8], dg[VPL][8], db[VPL][8];
@@ -177,7 +197,19 @@ __global__ void __launch_bounds__(256) rvn_layernorm_bwd(const __nv_bfloat16* __
         for (int j = 0; j < 8; ++j) of[j] = rstd * (gf[i][j] * dyf[i][j] - s1 - xh[i][j] * s2);
         bf16x8 o;
         o.from_float(of);
-        o.store(dx + static_cast<size_t>(row) * H + vec * 8);
+        o.store(dsum_out + static_cast<size_t>(row) * H + vec * 8);
+        if (use_drop) {
+          const unsigned long long g = (static_cast<unsigned long long>(row) * H + vec * 8) >> 2;
+          float sc[4];
+          drng.scales4(g, sc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) of[j] *= sc[j];
+          drng.scales4(g + 1, sc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) of[4 + j] *= sc[j];
+          o.from_float(of);
+          o.store(dx_drop_out + static_cast<size_t>(row) * H + vec * 8);
+        }
       }
     }
   }
@@ -193,10 +225,19 @@ __global__ void __launch_bounds__(256) rvn_layernorm_bwd(const __nv_bfloat16* __
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    atomicAdd(&dgamma[i], red[i]);
-    atomicAdd(&dbeta[i], red[H + i]);
-  }
+  float* mine = partial + static_cast<size_t>(blockIdx.x) * 2 * H;
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) mine[i] = red[i];
+}
+
+// dgamma[c] = sum_cta partial[cta][0][c], dbeta likewise; emitted directly in bf16
+__global__ void __launch_bounds__(128) rvn_layernorm_bwd_reduce(const float* __restrict__ partial, __nv_bfloat16* __restrict__ dgamma,
+                                                                __nv_bfloat16* __restrict__ dbeta, int n_cta, int H) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * H) return;
+  float s = 0.f;
+  for (int i = 0; i < n_cta; ++i) s += partial[static_cast<size_t>(i) * 2 * H + c];
+  if (c < H) dgamma[c] = __float2bfloat16(s);
+  else dbeta[c - H] = __float2bfloat16(s);
 }
 
 // ------------------------------------------------------------------------------------------------ cross entropy
@@ -300,20 +341,42 @@ __global__ void rvn_ce_finalize(const float* __restrict__ stats, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ column sum (bias grad)
-// out[c] = sum_r x[r, c]; x bf16 [rows, ld]; grid = (ceil(C/64), row_chunks); fp32 atomics into a zeroed buffer
+// out[c] += sum_r x[r, c]; x bf16 [rows, ld] (ld % 8 == 0).  256 threads = 32 column groups (8 columns, one 16 B load each)
+// x 8 row lanes; grid = (ceil(C/256), row_chunks); fp32 atomics into a zeroed buffer.
 __global__ void __launch_bounds__(256) rvn_colsum(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ out, int rows,
                                                   int C, int rows_per_block) {
-  __shared__ float sh[4][64];
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int rg = threadIdx.x >> 6;                      // 4 row groups
+  __shared__ float sh[8][256];
+  const int cg = threadIdx.x & 31;
+  const int rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
   const int row0 = blockIdx.y * rows_per_block;
   const int row1 = min(rows, row0 + rows_per_block);
-  float s = 0.f;
-  if (c < C)
-    for (int r = row0 + rg; r < row1; r += 4) s += __bfloat162float(x[static_cast<size_t>(r) * ld + c]);
-  sh[rg][threadIdx.x & 63] = s;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 + 8 <= C) {
+    for (int r = row0 + rl; r < row1; r += 8) {
+      bf16x8 a;
+      float f[8];
+      a.load(x + static_cast<size_t>(r) * ld + c0);
+      a.to_float(f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  } else if (c0 < C) {
+    for (int r = row0 + rl; r < row1; r += 8)
+      for (int j = 0; j < 8 && c0 + j < C; ++j) acc[j] += __bfloat162float(x[static_cast<size_t>(r) * ld + c0 + j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[rl][cg * 8 + j] = acc[j];
   __syncthreads();
-  if (rg == 0 && c < C) atomicAdd(&out[c], sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(&out[c], t);
+  }
 }
 
 }  // namespace rvn
@@ -328,29 +391,33 @@ __global__ void __launch_bounds__(256) rvn_colsum(const __nv_bfloat16* __restric
   else return -1;
 
 extern "C" int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out,
-                                     float* mean, float* rstd, int rows, int H, float eps, cudaStream_t stream) {
+                                     float* mean, float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p,
+                                     cudaStream_t stream) {
   if (H % 8 != 0) return -2;
   const int vpl = (H / 8 + 31) / 32;
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
   using T = const __nv_bfloat16*;
   RVN_LN_DISPATCH(rvn::rvn_layernorm_fwd, <<<grid, block, 0, stream>>>((T)x, (T)res, (T)gamma, (T)beta, (__nv_bfloat16*)y,
-                                                                        (__nv_bfloat16*)sum_out, mean, rstd, rows, H, eps))
+                                                                        (__nv_bfloat16*)sum_out, mean, rstd, rows, H, eps, rng, dropout_p))
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+// partial must hold max_ctas * 2 * H floats; returns the number of CTAs used through *n_cta_out
 extern "C" int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                                      void* dx, float* dgamma, float* dbeta, int rows, int H, int num_sms, cudaStream_t stream) {
+                                      void* dsum, void* dx_drop, void* dgamma, void* dbeta, float* partial, int max_ctas, int rows, int H,
+                                      const long long* rng, float dropout_p, cudaStream_t stream) {
   if (H % 8 != 0) return -2;
   const int vpl = (H / 8 + 31) / 32;
-  int blocks = num_sms * 2;
+  int blocks = max_ctas;
   int rpb = (rows + blocks - 1) / blocks;
   if (rpb < 8) rpb = 8;
   blocks = (rows + rpb - 1) / rpb;
   const size_t smem = 2 * H * sizeof(float);
   using T = const __nv_bfloat16*;
-  RVN_LN_DISPATCH(rvn::rvn_layernorm_bwd, <<<blocks, 256, smem, stream>>>((T)dy, (T)x, (T)gamma, mean, rstd, (__nv_bfloat16*)dx,
-                                                                         dgamma, dbeta, rows, H, rpb))
+  RVN_LN_DISPATCH(rvn::rvn_layernorm_bwd, <<<blocks, 256, smem, stream>>>((T)dy, (T)x, (T)gamma, mean, rstd, (__nv_bfloat16*)dsum,
+                                                                         (__nv_bfloat16*)dx_drop, partial, rows, H, rpb, rng, dropout_p))
+  rvn::rvn_layernorm_bwd_reduce<<<(2 * H + 127) / 128, 128, 0, stream>>>(partial, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, blocks, H);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -369,12 +436,13 @@ extern "C" int rvn_ce_backward(const void* logits, int ld, const int64_t* target
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-extern "C" int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, cudaStream_t stream) {
-  int chunks = rows / 256;
+extern "C" int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, int num_sms, cudaStream_t stream) {
+  const int col_blocks = (C + 255) / 256;
+  int chunks = (2 * num_sms + col_blocks - 1) / col_blocks;
+  if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
   if (chunks < 1) chunks = 1;
-  if (chunks > 64) chunks = 64;
   const int rpb = (rows + chunks - 1) / chunks;
-  dim3 grid((C + 63) / 64, (rows + rpb - 1) / rpb);
+  dim3 grid(col_blocks, (rows + rpb - 1) / rpb);
   rvn::rvn_colsum<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, out, rows, C, rpb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

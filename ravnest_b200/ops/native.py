@@ -36,6 +36,44 @@ def _as2d(x: torch.Tensor) -> torch.Tensor:
     return x2
 
 
+def _main_grad(weight):
+    """The flat-bucket gradient view of a ParamStore leaf (or None): wgrad accumulates into it in the GEMM epilogue
+    instead of materialising dW and paying a separate AccumulateGrad pass (Megatron-style gradient accumulation fusion)."""
+    g = weight.grad
+    if g is not None and g.dtype == torch.bfloat16 and g.dim() == 2 and _tma_ok(g) and ACCUMULATE_INTO_GRAD:
+        return g
+    return None
+
+
+ACCUMULATE_INTO_GRAD = True
+
+
+def _wgrad(dy2, x2, weight):
+    g = _main_grad(weight)
+    if g is not None:
+        C().gemm(dy2, True, x2, True, None, 0, g, False, 0, 2, g)       # g += dy^T x
+        calls['gemm_wgrad_acc'] += 1
+        return None
+    calls['gemm_wgrad'] += 1
+    return C().gemm(dy2, True, x2, True, None, 0, None, False, 0)[0]
+
+
+def _bias_grad(dy2, bias):
+    calls['colsum'] += 1
+    return C().column_sum(dy2).to(bias.dtype)
+
+
+def _pad_rows(dy2, N):
+    if _tma_ok(dy2):
+        return dy2
+    dy2 = dy2.contiguous()
+    if _tma_ok(dy2):
+        return dy2
+    pad = torch.zeros(dy2.shape[0], (N + 7) // 8 * 8, dtype=dy2.dtype, device=dy2.device)
+    pad[:, :N] = dy2
+    return pad[:, :N]
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, activation):
@@ -45,14 +83,13 @@ class _Linear(torch.autograd.Function):
         outs = C().gemm(x2, False, weight, False, bias, act, None, need_pre, 0)
         calls['gemm_fwd'] += 1
         ctx.act = act
-        ctx.has_bias = bias is not None
         ctx.x_shape = x.shape
-        ctx.save_for_backward(x2, weight, outs[1] if need_pre else None)
+        ctx.save_for_backward(x2, weight, bias, outs[1] if need_pre else None)
         return outs[0].reshape(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, weight, z = ctx.saved_tensors
+        x2, weight, bias, z = ctx.saved_tensors
         N = weight.shape[0]
         dy2 = dy.reshape(-1, N)
         if ctx.act != 0:
@@ -60,23 +97,58 @@ class _Linear(torch.autograd.Function):
             zc = z if z.is_contiguous() else z.contiguous()
             dy2 = C().act_bwd(dyc, zc, ctx.act)
             calls['act_bwd'] += 1
-        if not _tma_ok(dy2):
-            dy2 = dy2.contiguous()
-            if not _tma_ok(dy2):                 # e.g. N not a multiple of 8: pad the row stride
-                pad = torch.zeros(dy2.shape[0], (N + 7) // 8 * 8, dtype=dy2.dtype, device=dy2.device)
-                pad[:, :N] = dy2
-                dy2 = pad[:, :N]
+        dy2 = _pad_rows(dy2, N)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = C().gemm(dy2, False, weight, True, None, 0, None, False, 0)[0].reshape(ctx.x_shape)
             calls['gemm_dgrad'] += 1
         if ctx.needs_input_grad[1]:
-            dw = C().gemm(dy2, True, x2, True, None, 0, None, False, 0)[0]
-            calls['gemm_wgrad'] += 1
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = C().column_sum(dy2).to(weight.dtype)
-            calls['colsum'] += 1
+            dw = _wgrad(dy2, x2, weight)
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = _bias_grad(dy2, bias)
         return dx, dw, db, None
+
+
+class _MLP(torch.autograd.Function):
+    """y = act(x W1^T + b1) W2^T + b2 with the activation gradient fused into the dgrad GEMM epilogue
+    (dz = (dy W2) * act'(z) in one kernel: no separate activation-backward pass, dh never hits HBM twice)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, activation):
+        x2 = _as2d(x)
+        act = _ACT[activation]
+        h, z = C().gemm(x2, False, w1, False, b1, act, None, True, 0)
+        y = C().gemm(h, False, w2, False, b2, 0, None, False, 0)[0]
+        calls['gemm_fwd'] += 2
+        ctx.act = act
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(x2, w1, b1, w2, b2, h, z)
+        return y.reshape(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, b1, w2, b2, h, z = ctx.saved_tensors
+        dy2 = _pad_rows(dy.reshape(-1, w2.shape[0]), w2.shape[0])
+        dz = C().gemm(dy2, False, w2, True, None, ctx.act, z, False, 0, 1)[0]      # (dy W2) * act'(z)
+        calls['gemm_dgrad_dact'] += 1
+        dw2 = _wgrad(dy2, h, w2) if ctx.needs_input_grad[3] else None
+        db2 = _bias_grad(dy2, b2) if (b2 is not None and ctx.needs_input_grad[4]) else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = C().gemm(dz, False, w1, True, None, 0, None, False, 0)[0].reshape(ctx.x_shape)
+            calls['gemm_dgrad'] += 1
+        dw1 = _wgrad(dz, x2, w1) if ctx.needs_input_grad[1] else None
+        db1 = _bias_grad(dz, b1) if (b1 is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw1, db1, dw2, db2, None
+
+
+def mlp(x, w1, b1, w2, b2, activation='gelu'):
+    ok = (x.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0 and w1.shape[0] % 8 == 0 and w2.shape[0] % 8 == 0
+          and _tma_ok(w1) and _tma_ok(w2) and x.numel() > 0)
+    if not ok:
+        fallbacks['mlp'] += 1
+        return linear(linear(x, w1, b1, activation), w2, b2, None)
+    return _MLP.apply(x, w1, b1, w2, b2, activation)
 
 
 def linear(x, weight, bias=None, activation=None):
@@ -92,33 +164,36 @@ def linear(x, weight, bias=None, activation=None):
 
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, residual):
+    def forward(ctx, x, weight, bias, eps, residual, dropout_p):
         xc = x.contiguous()
         rc = residual.contiguous() if residual is not None else None
-        outs = C().layernorm_fwd(xc, rc, weight, bias, eps)
+        rng = next_rng_snapshot(xc.device) if dropout_p > 0.0 else None
+        outs = C().layernorm_fwd(xc, rc, weight, bias, eps, rng, dropout_p)
         calls['layernorm_fwd'] += 1
         y, mean, rstd = outs[0], outs[1], outs[2]
         ctx.has_res = residual is not None
-        ctx.save_for_backward(outs[3] if residual is not None else xc, weight, mean, rstd)
+        ctx.dropout_p = dropout_p
+        ctx.save_for_backward(outs[3] if len(outs) > 3 else xc, weight, mean, rstd, rng)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        s, weight, mean, rstd = ctx.saved_tensors
-        dx, dg, db = C().layernorm_bwd(dy.contiguous(), s, weight, mean, rstd)
+        s, weight, mean, rstd, rng = ctx.saved_tensors
+        dsum, dx, dg, db = C().layernorm_bwd(dy.contiguous(), s, weight, mean, rstd, rng, ctx.dropout_p)
         calls['layernorm_bwd'] += 1
-        return dx, dg.to(weight.dtype), db.to(weight.dtype), None, (dx if ctx.has_res else None)
+        return dx, dg, db, None, (dsum if ctx.has_res else None), None
 
 
-def layer_norm(x, weight, bias, eps=1e-5, residual=None):
+def layer_norm(x, weight, bias, eps=1e-5, residual=None, dropout_p=0.0):
+    """``LN(dropout(x) + residual)`` — dropout and the residual add are fused into the normalisation kernel."""
     H = x.shape[-1]
     if x.dtype != torch.bfloat16 or H % 8 != 0 or H > 4096 or weight.dtype != torch.bfloat16:
         fallbacks['layer_norm'] += 1
         from . import reference_layer_norm
-        return reference_layer_norm(x, weight, bias, eps, residual)
+        return reference_layer_norm(x, weight, bias, eps, residual, dropout_p)
     if residual is not None and residual.shape != x.shape:
         residual = residual.expand_as(x)
-    return _LayerNorm.apply(x, weight, bias, eps, residual)
+    return _LayerNorm.apply(x, weight, bias, eps, residual, float(dropout_p))
 
 
 class _CrossEntropy(torch.autograd.Function):

@@ -89,3 +89,86 @@ class GraphedLossStep:
         self.graph.replay()
         grads = [g.clone() if g is not None else None for g in self.static_in_grads]
         return self.static_loss.clone(), grads
+
+
+class GraphedStage:
+    """Forward and backward of a root/stem stage as two CUDA graphs sharing one memory pool.
+
+    One instance == one in-flight pass: it owns a private copy of the weights (that copy IS the stashed
+    version — PipeDream weight stashing becomes "don't refresh the copy until the pass has done its
+    backward"), static input/output buffers and the saved activations inside the graph pool.  A stage keeps
+    ``cluster_length + 1`` of them, so HBM holds every in-flight pass (resident-activation mode).
+    """
+
+    def __init__(self, compute, args: Sequence[Any], input_grads: bool):
+        self.compute = compute
+        dev = compute.device
+        store = compute.store
+        self.signature = _signature(args, None)
+        self.busy = False
+        self.weights_version = -1
+        # private weight copy + leaves that accumulate into the stage's flat gradient bucket
+        self.wbuf = torch.empty_like(store.current.flat)
+        self.params = {}
+        for name, o, n, s, g in zip(store.names, store.offsets, store.numels, store.shapes, store.grad_views):
+            leaf = self.wbuf[o:o + n].view(s).detach().requires_grad_(True)
+            leaf.grad = g
+            self.params[name] = leaf
+
+        def stage(t):
+            return torch.empty(t.shape, dtype=t.dtype, device=dev).copy_(t, non_blocking=True)
+
+        self.static_args = [stage(a) if isinstance(a, torch.Tensor) else a for a in args]
+        for a in self.static_args:
+            if isinstance(a, torch.Tensor) and a.is_floating_point() and input_grads:
+                a.requires_grad_(True)
+        self._arg_tensors = [a for a in self.static_args if isinstance(a, torch.Tensor)]
+        self.refresh_weights()
+        stream = torch.cuda.current_stream(dev)
+        cap = torch.cuda.Stream(dev)
+        cap.wait_stream(stream)
+        compute.model.train()
+        from torch.func import functional_call
+        self.fwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd_graph, stream=cap, capture_error_mode='thread_local'):
+            with torch.enable_grad():
+                out = functional_call(compute.model, self.params, tuple(self.static_args))
+        self.out_tree = out
+        self.static_outs = _tree_tensors(out, [])
+        self.grad_outs = [torch.zeros_like(o) if o.requires_grad else None for o in self.static_outs]
+        roots = [o for o in self.static_outs if o.requires_grad]
+        seeds = [g for g in self.grad_outs if g is not None]
+        self.bwd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.bwd_graph, stream=cap, pool=self.fwd_graph.pool(), capture_error_mode='thread_local'):
+            if roots:
+                torch.autograd.backward(roots, seeds)
+        stream.wait_stream(cap)
+        self.static_in_grads = [a.grad if isinstance(a, torch.Tensor) and a.requires_grad else None for a in self.static_args]
+
+    def refresh_weights(self) -> None:
+        store = self.compute.store
+        if self.weights_version != store.version:
+            self.wbuf.copy_(store.current.flat, non_blocking=True)
+            self.weights_version = store.version
+
+    def run_forward(self, args: Sequence[Any]):
+        self.busy = True
+        self.refresh_weights()
+        for dst, src in zip(self._arg_tensors, [a for a in args if isinstance(a, torch.Tensor)]):
+            dst.detach().copy_(src, non_blocking=True)
+        self.fwd_graph.replay()
+        return _tree_map(lambda t: t.detach().clone(), self.out_tree)
+
+    def run_backward(self, grads) -> List[Optional[torch.Tensor]]:
+        for idx, buf in enumerate(self.grad_outs):
+            if buf is None:
+                continue
+            g = grads.get(idx)
+            if g is None:
+                buf.zero_()
+            else:
+                buf.copy_(g, non_blocking=True)
+        self.bwd_graph.replay()
+        out = [g.clone() if g is not None else None for g in self.static_in_grads]
+        self.busy = False
+        return out

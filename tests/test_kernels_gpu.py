@@ -122,6 +122,56 @@ def test_layernorm(rows, H, with_res):
         assert _rel_err(r.grad, rr.grad) < 2e-2
 
 
+def test_layernorm_fused_dropout_replays_mask():
+    from ravnest_b200.ops import native
+    torch.manual_seed(11)
+    rows, H, p = 512, 768, 0.1
+    x = (_rand(rows, H) + 3.0).detach().requires_grad_(True)          # bounded away from 0 so dropped entries are identifiable
+    r = _rand(rows, H).requires_grad_(True)
+    g = torch.ones(H, device=DEV, dtype=torch.bfloat16).requires_grad_(True)
+    b = torch.zeros(H, device=DEV, dtype=torch.bfloat16).requires_grad_(True)
+    y = native.layer_norm(x, g, b, 1e-12, r, p)
+    gy = _rand(rows, H)
+    y.backward(gy)
+    # the mask is observable through dL/dx = dsum * mask/(1-p) and dL/dr = dsum
+    ratio = (x.grad.float() / r.grad.float().clamp_min(1e-30).where(r.grad.float().abs() > 1e-3, torch.ones_like(r.grad.float())))
+    sel = r.grad.float().abs() > 1e-2
+    kept = (x.grad.float().abs() > 0)[sel]
+    assert abs(float(kept.float().mean()) - (1 - p)) < 0.02
+    assert torch.allclose(ratio[sel][kept], torch.full_like(ratio[sel][kept], 1 / (1 - p)), rtol=3e-2)
+    # forward used the same mask: recompute the reference with the observed mask
+    mask = (x.grad.float().abs() > 0).float() / (1 - p)
+    mask = torch.where(sel, mask, torch.ones_like(mask) )            # unknown where dsum ~ 0; exclude those rows below
+    ref = torch.nn.functional.layer_norm(x.detach().float() * mask + r.detach().float(), (H,), eps=1e-12)
+    good_rows = sel.all(dim=1)
+    if good_rows.any():
+        assert _rel_err(y[good_rows], ref[good_rows]) < 2e-2
+
+
+def test_mlp_fused_matches_reference_and_accumulates_into_grad():
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(12)
+    x = _rand(4, 256, 768).requires_grad_(True)
+    w1, b1 = _rand(3072, 768, scale=0.03).requires_grad_(True), _rand(3072, scale=0.1).requires_grad_(True)
+    w2, b2 = _rand(768, 3072, scale=0.03).requires_grad_(True), _rand(768, scale=0.1).requires_grad_(True)
+    gy = _rand(4, 256, 768)
+    y = ops.mlp(x, w1, b1, w2, b2, 'gelu')
+    y.backward(gy)
+    ref_in = [t.detach().float().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = ops.reference_linear(ops.reference_linear(ref_in[0], ref_in[1], ref_in[2], 'gelu'), ref_in[3], ref_in[4])
+    yr.backward(gy.float())
+    assert _rel_err(y, yr) < 1e-2
+    for mine, ref in zip((x, w1, b1, w2, b2), ref_in):
+        assert _rel_err(mine.grad, ref.grad) < 2.5e-2
+    # second backward: wgrad accumulates in the GEMM epilogue straight into .grad (returns None to autograd)
+    before = native.calls['gemm_wgrad_acc']
+    y2 = ops.mlp(x, w1, b1, w2, b2, 'gelu')
+    y2.backward(gy)
+    assert native.calls['gemm_wgrad_acc'] == before + 2
+    assert _rel_err(w1.grad, 2 * ref_in[1].grad) < 2.5e-2 and _rel_err(w2.grad, 2 * ref_in[3].grad) < 2.5e-2
+
+
 # ----------------------------------------------------------------------------------------------- cross entropy
 @pytest.mark.parametrize('rows,V', [(4096, 30522), (64, 1000), (17, 200)])
 def test_cross_entropy(rows, V):
