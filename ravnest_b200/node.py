@@ -155,6 +155,12 @@ class Node:
         self._saved = threading.Event()
         self._stop = threading.Event()
         self.metrics = {'forward': 0, 'backward': 0, 'updates': 0, 'reduces': 0}
+        from .utils.tracing import StageTracer
+        from .runtime.watchdog import FaultInjector
+        self.tracer = StageTracer(name, self.device, enabled=kwargs.get('trace', True),
+                                  path=os.path.join(self.base_dir, '{}_metrics.jsonl'.format(name)) if kwargs.get('metrics_file') else None)
+        self.faults = FaultInjector(kwargs.get('fault_spec'))
+        self.heartbeat = None
         self.compute_stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
         if self.compute_stream is not None:
             self.compute_stream.wait_stream(torch.cuda.current_stream(self.device))   # init work is done
@@ -166,7 +172,19 @@ class Node:
         self._worker = threading.Thread(target=self._scheduler_loop, name='{}-sched'.format(self.name), daemon=True)
         self._worker.start()
 
+    def start_heartbeat(self, period: float = 1.0, on_failure=None):
+        """Ping pipeline neighbours over the gRPC control plane (reference defines Ping but never uses it)."""
+        from .runtime.watchdog import Heartbeat
+        cfg = self.config
+        peers = [(cfg[k + '_target_host'], cfg[k + '_target_port']) for k in ('forward', 'backward') if cfg.get(k + '_target_host') is not None]
+        self.heartbeat = Heartbeat(self.transport, peers, period=period, on_failure=on_failure)
+        self.heartbeat.start()
+        return self.heartbeat
+
     def stop(self) -> None:
+        if self.heartbeat is not None:
+            self.heartbeat.stop()
+        self.tracer.dump()
         self._stop.set()
         self.mailbox.close()
         try:
@@ -183,13 +201,17 @@ class Node:
             # legacy default stream can never stall stage compute (and vice versa)
             torch.cuda.set_stream(self.compute_stream)
         while not self._stop.is_set():
+            t_wait = time.time()
             item = self.mailbox.get(timeout=0.25)
+            self.tracer.idle(time.time() - t_wait)
             if item is None:
                 continue
             _lane, msg = item
             if '_ready_event' in msg:
-                self.transport.adopt(msg, self.device)
+                self.transport.adopt(msg, self.device, self.tracer)
             action = msg['action']
+            if self.faults.rules and self.faults.check(action, msg.get('forward_pass_id', -1)) == 'drop':
+                continue
             if self.is_last and action == ActionTypes.FORWARD:
                 action = ActionTypes.FIND_LOSS
             elif self.is_last and action == ActionTypes.NO_GRAD_FORWARD and self.node_type != NodeTypes.SOLO:
@@ -198,7 +220,8 @@ class Node:
                 threading.Thread(target=self.stop, daemon=True).start()
                 break
             try:
-                getattr(self, action)(msg)
+                with self.tracer.phase(action, msg.get('forward_pass_id', -1)):
+                    getattr(self, action)(msg)
             except BaseException as err:      # surface on the caller thread instead of dying silently
                 with self._cv:
                     self._errors.append(err)

@@ -14,7 +14,7 @@ int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int 
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
-                           void* dx_drop, void* dgamma, void* dbeta, float* partial, int max_ctas, int rows, int H, const long long* rng,
+                           void* dx_drop, void* dgamma, void* dbeta, float* acc, int num_sms, int rows, int H, const long long* rng,
                            float dropout_p, cudaStream_t stream);
 int rvn_ce_forward(const void* logits, int ld, const int64_t* target, float* lse, float* stats, float* loss, int rows, int V,
                    int64_t ignore_index, cudaStream_t stream);
@@ -180,11 +180,10 @@ std::vector<torch::Tensor> layernorm_bwd(const torch::Tensor& dy, const torch::T
   torch::Tensor dx = rp != nullptr ? torch::empty_like(x) : dsum;
   auto dgamma = torch::empty({H}, x.options());
   auto dbeta = torch::empty({H}, x.options());
-  const int max_ctas = sm_count() * 2;
-  auto partial = torch::empty({static_cast<int64_t>(max_ctas) * 2 * H}, x.options().dtype(torch::kFloat32));
+  auto acc = torch::empty({2 * static_cast<int64_t>(H)}, x.options().dtype(torch::kFloat32));
   check(rvn_layernorm_backward(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
                                dsum.data_ptr(), rp != nullptr ? dx.data_ptr() : nullptr, dgamma.data_ptr(), dbeta.data_ptr(),
-                               partial.data_ptr<float>(), max_ctas, rows, H, rp, static_cast<float>(dropout_p), cur_stream()),
+                               acc.data_ptr<float>(), sm_count(), rows, H, rp, static_cast<float>(dropout_p), cur_stream()),
         "layernorm_bwd");
   return {dsum, dx, dgamma, dbeta};
 }

@@ -51,10 +51,20 @@ struct FwdSmem {
   static constexpr int V_OFF = 2 * FM_TILE_BYTES;
   static constexpr int P_OFF = 3 * FM_TILE_BYTES;
   static constexpr int BAR_OFF = 5 * FM_TILE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int XCHG_OFF = BAR_OFF + 128;
+  static constexpr int TOTAL = XCHG_OFF + 2048 + 1024;
 };
 
-__global__ void __launch_bounds__(160, 2)
+constexpr int FM_SOFTMAX_THREADS = 256;      // 8 warps: thread = (query row, key half); warp w -> TMEM lanes 32*(w%4), half w/4
+constexpr int FM_THREADS = FM_SOFTMAX_THREADS + 32;
+
+// masked, scaled score in the log2 domain
+__device__ __forceinline__ float fm_score(uint32_t raw, float scale_log2, float kbias_log2, bool masked) {
+  const float s = fmaf(__uint_as_float(raw), scale_log2, kbias_log2);
+  return masked ? -INFINITY : s;
+}
+
+__global__ void __launch_bounds__(FM_THREADS, 2)
 rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -66,6 +76,8 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_o = bars + 5;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* xchg = reinterpret_cast<float*>(smem + FwdSmem::XCHG_OFF);      // [2][128] per-half row maxima / sums
+  float* kb_s = xchg + 256;                                               // [2][128] additive key bias (log2 domain) of tile j / j+1
 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * FM_BLOCK;
@@ -78,17 +90,17 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
     n_tiles = n_tiles < last ? n_tiles : last;
   }
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == FM_SOFTMAX_THREADS) {
     tma_prefetch_desc(&map_qkv);
     mbar_init(bar_q, 1);
     mbar_init(bar_k, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, FM_SOFTMAX_THREADS);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -99,7 +111,7 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================================================== control: TMA + MMA issue
     if (elect_one()) {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, false, false);
@@ -146,117 +158,142 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
     }
     __syncwarp();
   } else {
-    // ============================================================== softmax / accumulate (thread == query row)
-    const int r = threadIdx.x;                      // 0..127 == TMEM lane
+    // ============================================================== softmax / accumulate
+    const int half = warp >> 2;                     // which 64 keys of the tile / which 32 output dims
+    const int r = (warp & 3) * 32 + lane_id();      // query row in the tile == TMEM lane
     const int q = q0 + r;
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    uint8_t* p_smem = smem + FwdSmem::P_OFF;
-    float o[FM_D];
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint8_t* p_row = smem + FwdSmem::P_OFF + half * FM_TILE_BYTES + r * 128;
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < FM_D; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
     const float* kb = p.kbias ? p.kbias + static_cast<size_t>(b) * p.S : nullptr;
     const bool use_drop = p.rng != nullptr && p.dropout_p > 0.f;
     DropoutRng drng;
     if (use_drop) drng.init(p.rng, p.dropout_p);
-    // dropout groups: 4 consecutive keys of one (batch, head, query) row
-    const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 3) / 4);
+    // dropout groups: 8 consecutive keys of one (batch, head, query) row
+    const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 7) / 8);
+    // additive key bias of a tile, staged in smem once per tile: user padding bias (log2 domain) and -inf for keys >= S
+    auto stage_bias = [&](int tile) {
+      if (half == 0) {
+        const int k = tile * FM_BLOCK + r;
+        kb_s[(tile & 1) * 128 + r] = k >= p.S ? -INFINITY : (kb != nullptr ? kb[k] * LOG2E : 0.f);
+      }
+    };
+    stage_bias(0);
+    named_bar_sync(1, FM_SOFTMAX_THREADS);
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
-      const int k0 = j * FM_BLOCK;
+      const int kbase = j * FM_BLOCK + half * 64;    // first key handled by this thread
+      const bool biased = kb != nullptr || (j * FM_BLOCK + FM_BLOCK > p.S);
+      const bool diag = p.causal && (j * FM_BLOCK + FM_BLOCK - 1 > q0);
+      const bool edge = biased || diag;
+      const float* kbt = kb_s + (j & 1) * 128 + half * 64;
+      if (j + 1 < n_tiles) stage_bias(j + 1);        // ordered before its first read by this tile's exchange barrier
       mbar_wait(bar_s, ph);
       tcgen05_fence_after();
-      // ---- pass 1: row max of the masked, scaled scores (log2 domain)
+      // ---- pass 1: partial row max over this thread's 64 keys
       float tmax = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_sel + c * 32, v);
+        tmem_ld_32x32(tmem_s + lane_sel + half * 64 + c * 32, v);
         tmem_ld_wait();
+        if (!edge) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c * 32 + i;
-          float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (kb != nullptr && k < p.S) s += kb[k] * LOG2E;
-          if (k >= p.S || (p.causal && k > q)) s = -INFINITY;
-          tmax = fmaxf(tmax, s);
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]) * p.scale_log2);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int k = kbase + c * 32 + i;
+            tmax = fmaxf(tmax, fm_score(v[i], p.scale_log2, kbt[c * 32 + i], diag && k > q));
+          }
         }
       }
-      const float m_new = fmaxf(m, tmax);
+      xchg[half * 128 + r] = tmax;
+      named_bar_sync(1, FM_SOFTMAX_THREADS);
+      const float m_new = fmaxf(m, fmaxf(tmax, xchg[(half ^ 1) * 128 + r]));
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m - m_use);       // m == -inf -> 0
-      // ---- pass 2: probabilities -> bf16 -> swizzled smem; row sum
+      // ---- pass 2: probabilities -> bf16 -> swizzled smem; partial row sum
       float rsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_sel + c * 32, v);
+        tmem_ld_32x32(tmem_s + lane_sel + half * 64 + c * 32, v);
         tmem_ld_wait();
         float pr[32];
+        if (!edge) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c * 32 + i;
-          float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (kb != nullptr && k < p.S) s += kb[k] * LOG2E;
-          if (k >= p.S || (p.causal && k > q)) s = -INFINITY;
-          pr[i] = fast_exp2(s - m_use);
-          rsum += pr[i];
+          for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_use));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int k = kbase + c * 32 + i;
+            pr[i] = fast_exp2(fm_score(v[i], p.scale_log2, kbt[c * 32 + i], diag && k > q) - m_use);
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rsum += pr[i];
         if (use_drop) {                                // the row sum stays un-dropped; P fed to the PV product is dropped
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float sc[4];
-            drng.scales4(drow + ((k0 + c * 32 + i) >> 2), sc);
-            pr[i] *= sc[0]; pr[i + 1] *= sc[1]; pr[i + 2] *= sc[2]; pr[i + 3] *= sc[3];
+          for (int i = 0; i < 32; i += 8) {
+            float sc[8];
+            drng.scales8(drow + ((kbase + c * 32 + i) >> 3), sc);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) pr[i + t] *= sc[t];
           }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          const int chunk = c * 4 + (i >> 3);          // 16-byte chunk 0..15 of this row's 128 keys
+          const int chunk = c * 4 + (i >> 3);          // 16-byte chunk 0..7 of this half-row (64 keys = one 128 B swizzle row)
           uint4 w;
           w.x = pack_bf16x2(pr[i], pr[i + 1]); w.y = pack_bf16x2(pr[i + 2], pr[i + 3]);
           w.z = pack_bf16x2(pr[i + 4], pr[i + 5]); w.w = pack_bf16x2(pr[i + 6], pr[i + 7]);
-          *reinterpret_cast<uint4*>(p_smem + (chunk >> 3) * FM_TILE_BYTES + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) = w;
+          *reinterpret_cast<uint4*>(p_row + ((chunk ^ (r & 7)) << 4)) = w;
         }
       }
       l = l * alpha + rsum;
       m = m_new;
 #pragma unroll
-      for (int i = 0; i < FM_D; ++i) o[i] *= alpha;
+      for (int i = 0; i < 32; ++i) o[i] *= alpha;
       tcgen05_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(bar_p);
-      // ---- O += P V_j
+      // ---- O[:, half*32 .. +32] += (P V_j)
       mbar_wait(bar_o, ph);
       tcgen05_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_o + lane_sel + c * 32, v);
+        tmem_ld_32x32(tmem_o + lane_sel + half * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
       }
       tcgen05_fence_before();
     }
+    // combine the two halves' row sums
+    xchg[half * 128 + r] = l;
+    named_bar_sync(1, FM_SOFTMAX_THREADS);
+    l += xchg[(half ^ 1) * 128 + r];
     if (q < p.S) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q) * p.H + h * FM_D;
+      __nv_bfloat16* dst = p.out + static_cast<size_t>(row_base + q) * p.H + h * FM_D + half * 32;
 #pragma unroll
-      for (int i = 0; i < FM_D; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 w;
         w.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv); w.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
         w.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv); w.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
         *reinterpret_cast<uint4*>(dst + i) = w;
       }
-      p.lse[(static_cast<size_t>(b) * p.heads + h) * p.S + q] = l > 0.f ? (m + log2f(l)) * LN2 : INFINITY;
+      if (half == 0) p.lse[(static_cast<size_t>(b) * p.heads + h) * p.S + q] = l > 0.f ? (m + log2f(l)) * LN2 : INFINITY;
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
-
 
 // ================================================================================================ backward
 struct FmhaBwdParams {
@@ -321,10 +358,10 @@ struct BwdSmem {
   static constexpr int P_OFF = 4 * FM_TILE_BYTES;
   static constexpr int DS_OFF = 6 * FM_TILE_BYTES;
   static constexpr int BAR_OFF = 8 * FM_TILE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 128 + 512 + 1024;
 };
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(FM_THREADS, 1)
 rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const FmhaBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -344,17 +381,17 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   const int n_q_tiles = (p.S + FM_BLOCK - 1) / FM_BLOCK;
   const int i_first = p.causal ? blockIdx.x : 0;          // causal: only q tiles at or after this kv tile
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == FM_SOFTMAX_THREADS) {
     tma_prefetch_desc(&map_qkv);
     tma_prefetch_desc(&map_do);
     mbar_init(bar_kv, 1);
     mbar_init(bar_qd, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, FM_SOFTMAX_THREADS);
     mbar_init(bar_g, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -364,7 +401,7 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       constexpr uint32_t IDESC_QK = make_idesc_bf16(128, 128, false, false);   // S, dP : both K-major
       constexpr uint32_t IDESC_TT = make_idesc_bf16(128, 64, true, true);      // dV, dK: both MN-major
@@ -415,62 +452,75 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     }
     __syncwarp();
   } else {
-    const int r = threadIdx.x;
-    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
-    uint8_t* p_smem = smem + BwdSmem::P_OFF;
-    uint8_t* ds_smem = smem + BwdSmem::DS_OFF;
+    const int half = warp >> 2;                     // which 64 keys (P / dS) and which 32 dims (dQ, dK, dV) this thread owns
+    const int r = (warp & 3) * 32 + lane_id();
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int row_off = half * FM_TILE_BYTES + r * 128;
+    uint8_t* p_smem = smem + BwdSmem::P_OFF + row_off;
+    uint8_t* ds_smem = smem + BwdSmem::DS_OFF + row_off;
     const float* kb = p.kbias ? p.kbias + static_cast<size_t>(b) * p.S : nullptr;
     const size_t stat_base = (static_cast<size_t>(b) * p.heads + h) * p.S;
     const bool use_drop = p.rng != nullptr && p.dropout_p > 0.f;
     DropoutRng drng;
     if (use_drop) drng.init(p.rng, p.dropout_p);
+    const int kbase = k0 + half * 64;
+    float* kb_s = reinterpret_cast<float*>(smem + BwdSmem::BAR_OFF + 128);      // [128] key bias of this CTA's kv tile
+    if (half == 0) {
+      const int k = k0 + r;
+      kb_s[r] = k >= p.S ? -INFINITY : (kb != nullptr ? kb[k] * LOG2E : 0.f);
+    }
+    named_bar_sync(1, FM_SOFTMAX_THREADS);
+    const float* kbt = kb_s + half * 64;
+    const bool biased = kb != nullptr || (k0 + FM_BLOCK > p.S);
     int it = 0;
     for (int i = i_first; i < n_q_tiles; ++i, ++it) {
       const uint32_t ph = it & 1;
       const int q = i * FM_BLOCK + r;
-      const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 3) / 4);
       const bool q_ok = q < p.S;
       const float lse2 = q_ok ? p.lse[stat_base + q] * LOG2E : INFINITY;
       const float dlt = q_ok ? p.delta[stat_base + q] : 0.f;
+      const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 7) / 8);
+      const bool diag = p.causal && (k0 + FM_BLOCK - 1 > i * FM_BLOCK);
+      const bool edge = biased || diag || (i * FM_BLOCK + FM_BLOCK > p.S);
       mbar_wait(bar_s, ph);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tm_s + lane_sel + c * 32, sv);
-        tmem_ld_32x32(tm_dp + lane_sel + c * 32, dv);
+        tmem_ld_32x32(tm_s + lane_sel + half * 64 + c * 32, sv);
+        tmem_ld_32x32(tm_dp + lane_sel + half * 64 + c * 32, dv);
         tmem_ld_wait();
         float pr[32], ds[32];
+        if (!edge) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = k0 + c * 32 + j;
-          float s = __uint_as_float(sv[j]) * p.scale_log2;
-          if (kb != nullptr && k < p.S) s += kb[k] * LOG2E;
-          const bool masked = !q_ok || k >= p.S || (p.causal && k > q);
-          const float pj = masked ? 0.f : fast_exp2(s - lse2);
-          pr[j] = pj;
-          ds[j] = __uint_as_float(dv[j]);
+          for (int j = 0; j < 32; ++j) pr[j] = fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse2));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int k = kbase + c * 32 + j;
+            const bool masked = !q_ok || (diag && k > q);
+            pr[j] = masked ? 0.f : fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, kbt[c * 32 + j]) - lse2);
+          }
         }
         if (use_drop) {                                // Z = P o M feeds dV; dP = dZ o M
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float sc[4];
-            drng.scales4(drow + ((k0 + c * 32 + j) >> 2), sc);
+          for (int j = 0; j < 32; j += 8) {
+            float sc[8];
+            drng.scales8(drow + ((kbase + c * 32 + j) >> 3), sc);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
               const float pj = pr[j + t];
-              ds[j + t] = pj * (ds[j + t] * sc[t] - dlt) * p.scale;
+              ds[j + t] = pj * (__uint_as_float(dv[j + t]) * sc[t] - dlt) * p.scale;
               pr[j + t] = pj * sc[t];
             }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ds[j] = pr[j] * (ds[j] - dlt) * p.scale;
+          for (int j = 0; j < 32; ++j) ds[j] = pr[j] * (__uint_as_float(dv[j]) - dlt) * p.scale;
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          const int chunk = c * 4 + (j >> 3);
-          const int off = (chunk >> 3) * FM_TILE_BYTES + r * 128 + (((chunk & 7) ^ (r & 7)) << 4);
+          const int off = ((c * 4 + (j >> 3)) ^ (r & 7)) << 4;
           uint4 w;
           w.x = pack_bf16x2(pr[j], pr[j + 1]); w.y = pack_bf16x2(pr[j + 2], pr[j + 3]);
           w.z = pack_bf16x2(pr[j + 4], pr[j + 5]); w.w = pack_bf16x2(pr[j + 6], pr[j + 7]);
@@ -485,41 +535,37 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       mbar_arrive(bar_p);
       mbar_wait(bar_g, ph);
       tcgen05_fence_after();
-      // dQ_i += dS K_j  (this kv tile's contribution) -> fp32 atomics
-      float* dq_row = p.dq_accum + static_cast<size_t>(row_base + q) * p.H + h * FM_D;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      // dQ_i[:, half*32 .. +32] += dS K_j  (this kv tile's contribution) -> fp32 atomics
+      {
+        float* dq_row = p.dq_accum + static_cast<size_t>(row_base + q) * p.H + h * FM_D + half * 32;
         uint32_t v[32];
-        tmem_ld_32x32(tm_dq + lane_sel + c * 32, v);
+        tmem_ld_32x32(tm_dq + lane_sel + half * 32, v);
         tmem_ld_wait();
         if (q_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dq_row + c * 32 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) atomicAdd(dq_row + j, __uint_as_float(v[j]));
         }
       }
       tcgen05_fence_before();
     }
-    // dK_j, dV_j: thread == key row
+    // dK_j, dV_j: thread == (key row, 32-dim half)
     const int k = k0 + r;
     if (it > 0) {
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
-        __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(row_base + k) * 3 * p.H + (which == 0 ? p.H : 2 * p.H) + h * FM_D;
+        __nv_bfloat16* dst = p.dqkv + static_cast<size_t>(row_base + k) * 3 * p.H + (which == 0 ? p.H : 2 * p.H) + h * FM_D + half * 32;
+        uint32_t v[32];
+        tmem_ld_32x32((which == 0 ? tm_dk : tm_dv) + lane_sel + half * 32, v);
+        tmem_ld_wait();
+        if (k < p.S) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32((which == 0 ? tm_dk : tm_dv) + lane_sel + c * 32, v);
-          tmem_ld_wait();
-          if (k < p.S) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              w.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-              w.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              w.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-              w.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-              *reinterpret_cast<uint4*>(dst + c * 32 + j) = w;
-            }
+          for (int j = 0; j < 32; j += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            w.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            w.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+            w.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+            *reinterpret_cast<uint4*>(dst + j) = w;
           }
         }
       }
@@ -527,7 +573,7 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -577,7 +623,7 @@ extern "C" int rvn_fmha_forward(const void* qkv, void* out, float* lse, const fl
     configured = true;
   }
   dim3 grid((S + FM_BLOCK - 1) / FM_BLOCK, B * heads);
-  rvn_fmha_fwd_tcgen05<<<grid, 160, FwdSmem::TOTAL, stream>>>(map, p);
+  rvn_fmha_fwd_tcgen05<<<grid, FM_THREADS, FwdSmem::TOTAL, stream>>>(map, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 
@@ -611,7 +657,7 @@ extern "C" int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o
     configured = true;
   }
   dim3 grid((S + FM_BLOCK - 1) / FM_BLOCK, B * heads);
-  rvn_fmha_bwd_tcgen05<<<grid, 160, BwdSmem::TOTAL, stream>>>(map_qkv, map_do, p);
+  rvn_fmha_bwd_tcgen05<<<grid, FM_THREADS, BwdSmem::TOTAL, stream>>>(map_qkv, map_do, p);
   const size_t rows = static_cast<size_t>(B) * S;
   int blocks = num_sms * 4;
   rvn_fmha_bwd_cast_dq<<<blocks, 256, 0, stream>>>(dq_accum, static_cast<__nv_bfloat16*>(dqkv), rows, H);

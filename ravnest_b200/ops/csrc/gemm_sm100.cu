@@ -102,7 +102,8 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_bar = tmem_empty + 2;                     // TMA load of the auxiliary input slab (epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
@@ -111,7 +112,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     tma_prefetch_desc(&map_d);
-    if (p.store_preact) tma_prefetch_desc(&map_aux);
+    if (p.store_preact || p.dact_in != nullptr) tma_prefetch_desc(&map_aux);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
@@ -122,6 +123,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], EPI_THREADS / 32);
     }
+    mbar_init(aux_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -208,6 +210,9 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t slab_counter = 0;
+    uint32_t aux_phase = 0;
+    const bool has_aux_in = p.dact_in != nullptr;
+    const bool one_buffer = p.store_preact || has_aux_in;     // staging[1] is taken by the aux slab (in or out)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
       const int n0 = (tile / p.num_m_blocks) * BN;
@@ -218,13 +223,23 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (int slab = 0; slab < BN / SLAB_N; ++slab) {
         const int col0 = n0 + slab * SLAB_N;
         if (col0 >= p.N) break;                                   // whole slab out of range (N tail)
-        uint8_t* buf_main = staging + (p.store_preact ? 0 : (slab_counter & 1)) * SLAB_BYTES;
+        uint8_t* buf_main = staging + (one_buffer ? 0 : (slab_counter & 1)) * SLAB_BYTES;
         uint8_t* buf_aux = staging + SLAB_BYTES;
         // the TMA store that last read this staging buffer must have finished reading it
         if (issuer) {
-          if (p.store_preact) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (one_buffer) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         named_bar_sync(1, EPI_THREADS);
+        if (has_aux_in) {
+          // auxiliary input slab (pre-activation z, or the gradient tile being accumulated into) comes in through TMA:
+          // coalesced 128 B rows into swizzled smem instead of 32 scattered 16 B row reads per warp instruction
+          if (issuer) {
+            mbar_expect_tx(aux_bar, SLAB_BYTES);
+            tma_load_2d(buf_aux, &map_aux, aux_bar, col0, m0);
+          }
+          mbar_wait(aux_bar, aux_phase);
+          aux_phase ^= 1;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
@@ -260,24 +275,21 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
               *reinterpret_cast<uint4*>(buf_aux + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = o;
             }
           }
-          if (p.dact_in != nullptr) {
-            if (grow < p.M) {
+          if (has_aux_in) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (c_base + i < p.N) {
-                  const uint4 z4 = __ldg(reinterpret_cast<const uint4*>(p.dact_in + static_cast<size_t>(grow) * p.ld_aux + c_base + i));
-                  const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&z4);
+            for (int i = 0; i < 32; i += 8) {
+              const int chunk = half * 4 + (i >> 3);
+              const uint4 z4 = *reinterpret_cast<const uint4*>(buf_aux + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4));
+              const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&z4);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 zf = __bfloat1622float2(z2[j]);
-                    if (p.aux_mode == 2) {
-                      f[i + 2 * j] += zf.x;
-                      f[i + 2 * j + 1] += zf.y;
-                    } else {
-                      f[i + 2 * j] *= apply_dact(zf.x, p.act);
-                      f[i + 2 * j + 1] *= apply_dact(zf.y, p.act);
-                    }
-                  }
+              for (int j = 0; j < 4; ++j) {
+                const float2 zf = __bfloat1622float2(z2[j]);
+                if (p.aux_mode == 2) {
+                  f[i + 2 * j] += zf.x;
+                  f[i + 2 * j + 1] += zf.y;
+                } else {
+                  f[i + 2 * j] *= apply_dact(zf.x, p.act);
+                  f[i + 2 * j + 1] *= apply_dact(zf.y, p.act);
                 }
               }
             }
@@ -354,6 +366,11 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, void* aux_out, int ld_auxout,
                   GemmParams p, int num_sms, cudaStream_t stream) {
+  if (p.dact_in != nullptr) {            // aux INPUT tile (mutually exclusive with the pre-activation output)
+    aux_out = const_cast<__nv_bfloat16*>(p.dact_in);
+    ld_auxout = p.ld_aux;
+    p.store_preact = 0;
+  }
   using L = SmemLayout<BN>;
   CUtensorMap ma, mb, md, mx;
   int e = 0;

@@ -131,113 +131,124 @@ __global__ void __launch_bounds__(256) rvn_layernorm_fwd(const __nv_bfloat16* __
 }
 
 // dsum = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dx = dsum o dropout-mask (regenerated), dres = dsum.
-// Per-CTA partial dgamma / dbeta go to partial[cta][2][H]; rvn_layernorm_bwd_reduce sums them (no global atomics).
+// Pure streaming kernel: one warp per row, nothing shared between rows (parameter gradients are a separate column reduce).
 template <int VPL>
-__global__ void __launch_bounds__(256) rvn_layernorm_bwd(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                                                         const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
-                                                         const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dsum_out,
-                                                         __nv_bfloat16* __restrict__ dx_drop_out, float* __restrict__ partial, int rows,
-                                                         int H, int rows_per_block, const long long* __restrict__ rng, float dropout_p) {
-  extern __shared__ float red[];          // [2][H] partial dgamma / dbeta of this CTA
+__global__ void __launch_bounds__(256) rvn_layernorm_bwd_dx(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dsum_out,
+                                                            __nv_bfloat16* __restrict__ dx_drop_out, int rows, int H,
+                                                            const long long* __restrict__ rng, float dropout_p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
   const int nvec = H >> 3;
   const bool use_drop = rng != nullptr && dropout_p > 0.f && dx_drop_out != nullptr;
   DropoutRng drng;
   if (use_drop) drng.init(rng, dropout_p);
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float gf[VPL][8], dg[VPL][8], db[VPL][8];
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float gdy[VPL][8], xh[VPL][8];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int vec = lane + i * 32;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gf[i][j] = 0.f; }
     if (vec < nvec) {
-      bf16x8 g;
+      bf16x8 a, b, g;
+      float gf[8];
+      a.load(dy + static_cast<size_t>(row) * H + vec * 8);
+      b.load(x + static_cast<size_t>(row) * H + vec * 8);
       g.load(gamma + vec * 8);
-      g.to_float(gf[i]);
-    }
-  }
-  const int row0 = blockIdx.x * rows_per_block;
-  const int row1 = min(rows, row0 + rows_per_block);
-  for (int row = row0 + warp; row < row1; row += nwarps) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float dyf[VPL][8], xh[VPL][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int vec = lane + i * 32;
-      if (vec < nvec) {
-        bf16x8 a, b;
-        a.load(dy + static_cast<size_t>(row) * H + vec * 8);
-        b.load(x + static_cast<size_t>(row) * H + vec * 8);
-        a.to_float(dyf[i]);
-        b.to_float(xh[i]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xh[i][j] - mean) * rstd;
-          const float gdy = gf[i][j] * dyf[i][j];
-          s1 += gdy;
-          s2 += gdy * xh[i][j];
-          dg[i][j] += dyf[i][j] * xh[i][j];
-          db[i][j] += dyf[i][j];
-        }
-      }
-    }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int vec = lane + i * 32;
-      if (vec < nvec) {
-        float of[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) of[j] = rstd * (gf[i][j] * dyf[i][j] - s1 - xh[i][j] * s2);
-        bf16x8 o;
-        o.from_float(of);
-        o.store(dsum_out + static_cast<size_t>(row) * H + vec * 8);
-        if (use_drop) {
-          const unsigned long long g = (static_cast<unsigned long long>(row) * H + vec * 8) >> 2;
-          float sc[4];
-          drng.scales4(g, sc);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) of[j] *= sc[j];
-          drng.scales4(g + 1, sc);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) of[4 + j] *= sc[j];
-          o.from_float(of);
-          o.store(dx_drop_out + static_cast<size_t>(row) * H + vec * 8);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vec = lane + i * 32;
-    if (vec < nvec) {
+      a.to_float(gdy[i]);
+      b.to_float(xh[i]);
+      g.to_float(gf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[vec * 8 + j], dg[i][j]);
-        atomicAdd(&red[H + vec * 8 + j], db[i][j]);
+        xh[i][j] = (xh[i][j] - mean) * rstd;
+        gdy[i][j] *= gf[j];
+        s1 += gdy[i][j];
+        s2 += gdy[i][j] * xh[i][j];
       }
     }
   }
-  __syncthreads();
-  float* mine = partial + static_cast<size_t>(blockIdx.x) * 2 * H;
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) mine[i] = red[i];
+  s1 = warp_sum(s1) / H;
+  s2 = warp_sum(s2) / H;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + i * 32;
+    if (vec < nvec) {
+      float of[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) of[j] = rstd * (gdy[i][j] - s1 - xh[i][j] * s2);
+      bf16x8 o;
+      o.from_float(of);
+      o.store(dsum_out + static_cast<size_t>(row) * H + vec * 8);
+      if (use_drop) {
+        const unsigned long long g = (static_cast<unsigned long long>(row) * H + vec * 8) >> 2;
+        float sc[4];
+        drng.scales4(g, sc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) of[j] *= sc[j];
+        drng.scales4(g + 1, sc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) of[4 + j] *= sc[j];
+        o.from_float(of);
+        o.store(dx_drop_out + static_cast<size_t>(row) * H + vec * 8);
+      }
+    }
+  }
 }
 
-// dgamma[c] = sum_cta partial[cta][0][c], dbeta likewise; emitted directly in bf16
-__global__ void __launch_bounds__(128) rvn_layernorm_bwd_reduce(const float* __restrict__ partial, __nv_bfloat16* __restrict__ dgamma,
-                                                                __nv_bfloat16* __restrict__ dbeta, int n_cta, int H) {
+// acc[0][c] += sum_r dy[r,c] * xhat[r,c];  acc[1][c] += sum_r dy[r,c]   (column reduce; same tiling as rvn_colsum)
+__global__ void __launch_bounds__(256) rvn_layernorm_bwd_params(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                float* __restrict__ acc, int rows, int H, int rows_per_block) {
+  __shared__ float sh[2][8][256];
+  const int cg = threadIdx.x & 31;
+  const int rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
+  const int row0 = blockIdx.y * rows_per_block;
+  const int row1 = min(rows, row0 + rows_per_block);
+  float dg[8], db[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { dg[j] = 0.f; db[j] = 0.f; }
+  if (c0 < H) {
+    for (int r = row0 + rl; r < row1; r += 8) {
+      bf16x8 a, b;
+      float g[8], xv[8];
+      a.load(dy + static_cast<size_t>(r) * H + c0);
+      b.load(x + static_cast<size_t>(r) * H + c0);
+      a.to_float(g);
+      b.to_float(xv);
+      const float mean = mean_in[r], rstd = rstd_in[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dg[j] += g[j] * (xv[j] - mean) * rstd;
+        db[j] += g[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[0][rl][cg * 8 + j] = dg[j];
+    sh[1][rl][cg * 8 + j] = db[j];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < H) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += sh[0][i][threadIdx.x]; t1 += sh[1][i][threadIdx.x]; }
+    atomicAdd(&acc[c], t0);
+    atomicAdd(&acc[H + c], t1);
+  }
+}
+
+__global__ void __launch_bounds__(256) rvn_layernorm_bwd_finalize(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dgamma,
+                                                                  __nv_bfloat16* __restrict__ dbeta, int H) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
-  float s = 0.f;
-  for (int i = 0; i < n_cta; ++i) s += partial[static_cast<size_t>(i) * 2 * H + c];
-  if (c < H) dgamma[c] = __float2bfloat16(s);
-  else dbeta[c - H] = __float2bfloat16(s);
+  if (c < H) {
+    dgamma[c] = __float2bfloat16(acc[c]);
+    dbeta[c] = __float2bfloat16(acc[H + c]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ cross entropy
@@ -403,21 +414,26 @@ extern "C" int rvn_layernorm_forward(const void* x, const void* res, const void*
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// partial must hold max_ctas * 2 * H floats; returns the number of CTAs used through *n_cta_out
+// acc: 2*H fp32 scratch (zeroed here)
 extern "C" int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                                      void* dsum, void* dx_drop, void* dgamma, void* dbeta, float* partial, int max_ctas, int rows, int H,
+                                      void* dsum, void* dx_drop, void* dgamma, void* dbeta, float* acc, int num_sms, int rows, int H,
                                       const long long* rng, float dropout_p, cudaStream_t stream) {
   if (H % 8 != 0) return -2;
   const int vpl = (H / 8 + 31) / 32;
-  int blocks = max_ctas;
-  int rpb = (rows + blocks - 1) / blocks;
-  if (rpb < 8) rpb = 8;
-  blocks = (rows + rpb - 1) / rpb;
-  const size_t smem = 2 * H * sizeof(float);
   using T = const __nv_bfloat16*;
-  RVN_LN_DISPATCH(rvn::rvn_layernorm_bwd, <<<blocks, 256, smem, stream>>>((T)dy, (T)x, (T)gamma, mean, rstd, (__nv_bfloat16*)dsum,
-                                                                         (__nv_bfloat16*)dx_drop, partial, rows, H, rpb, rng, dropout_p))
-  rvn::rvn_layernorm_bwd_reduce<<<(2 * H + 127) / 128, 128, 0, stream>>>(partial, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, blocks, H);
+  const int wpb = 8;
+  dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+  RVN_LN_DISPATCH(rvn::rvn_layernorm_bwd_dx, <<<grid, block, 0, stream>>>((T)dy, (T)x, (T)gamma, mean, rstd, (__nv_bfloat16*)dsum,
+                                                                          (__nv_bfloat16*)dx_drop, rows, H, rng, dropout_p))
+  cudaMemsetAsync(acc, 0, sizeof(float) * 2 * H, stream);
+  const int col_blocks = (H + 255) / 256;
+  int chunks = (2 * num_sms + col_blocks - 1) / col_blocks;
+  if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
+  if (chunks < 1) chunks = 1;
+  const int rpb = (rows + chunks - 1) / chunks;
+  dim3 pgrid(col_blocks, (rows + rpb - 1) / rpb);
+  rvn::rvn_layernorm_bwd_params<<<pgrid, 256, 0, stream>>>((T)dy, (T)x, mean, rstd, acc, rows, H, rpb);
+  rvn::rvn_layernorm_bwd_finalize<<<(H + 255) / 256, 256, 0, stream>>>(acc, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, H);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -304,12 +304,16 @@ class DistTransport:
 
     # ------------------------------------------------------------------ helpers for the scheduler
     @staticmethod
-    def adopt(message: Dict[str, Any], device: torch.device) -> None:
-        """Make the scheduler's stream wait for the payload and own its memory."""
+    def adopt(message: Dict[str, Any], device: torch.device, tracer=None) -> None:
+        """Make the scheduler's stream wait for the payload and own its memory; the stall (if any) is
+        accounted as exposed communication."""
         ev = message.pop('_ready_event', None)
         tensors = message.pop('_tensors', None)
         if ev is not None:
             stream = torch.cuda.current_stream(device)
-            stream.wait_event(ev)
+            if tracer is not None:
+                tracer.exposed_wait(ev)
+            else:
+                stream.wait_event(ev)
             for t in tensors or ():
                 t.record_stream(stream)
