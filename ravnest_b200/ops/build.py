@@ -37,7 +37,7 @@ def build_all(verbose=False, force=False):
     from torch.utils import cpp_extension
     os.makedirs(BUILD_DIR, exist_ok=True)
     cpp_extension.load(name='rvn_C', sources=sources(), extra_cuda_cflags=CUDA_FLAGS, extra_cflags=['-O3', '-std=c++17'],
-                       extra_ldflags=['-lcuda'] if False else [], build_directory=BUILD_DIR, verbose=verbose, is_python_module=False)
+                       extra_ldflags=['-L/usr/lib/x86_64-linux-gnu', '-l:libstdc++.so.6', '-lm'], build_directory=BUILD_DIR, verbose=verbose, is_python_module=False)
     shutil.copyfile(os.path.join(BUILD_DIR, 'rvn_C.so'), TARGET)
     return TARGET
 

@@ -584,10 +584,16 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
                        uint32_t box_outer) {
   static EncodeTiledFn2 enc = nullptr;
   if (enc == nullptr) {
+    cudaFree(nullptr);             // binds the primary context to THIS thread (autograd worker threads may not have one yet)
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || ptr == nullptr) return -1;
     enc = reinterpret_cast<EncodeTiledFn2>(ptr);
+  }
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {               // driver call below needs a context current on this thread
+    cudaFree(nullptr);
+    ctx_bound = true;
   }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * 2};

@@ -37,6 +37,7 @@ struct GemmParams {
   int aux_mode;                   // 1: D = acc * act'(aux)  (activation gradient)   2: D = acc + aux  (gradient accumulation)
   int act;                        // Act
   int store_preact;               // also write the pre-activation through map_aux
+  int b_copy;                     // K2: B is read from a PEER's HBM; CTAs of the first M block also land every B tile locally
   int num_m_blocks, num_n_blocks, num_k_blocks;
 };
 
@@ -89,7 +90,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
-                      const GemmParams p) {
+                      const __grid_constant__ CUtensorMap map_bcopy, const GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BN;                 // two accumulator stages (256 or 512 columns)
@@ -193,6 +194,14 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
             umma_bf16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (!B_MN && p.b_copy && (tile % p.num_m_blocks) == 0) {
+            // K2 broadcast fusion: this B tile just arrived over NVLink from the stage leader; while the MMAs above
+            // consume it, write it through to the local weight buffer (TMA store undoes the swizzle) so every later
+            // step reads local HBM.  The store must have finished READING the stage before the stage is recycled.
+            tma_store_2d(&map_bcopy, smem + stage * L::STAGE_BYTES + L::A_BYTES, kb * BLOCK_K, (tile / p.num_m_blocks) * BN);
+            tma_store_commit();
+            tma_store_wait_read0();
           }
           umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
@@ -339,6 +348,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
+    cudaFree(nullptr);             // binds the primary context to THIS thread (autograd worker threads may not have one yet)
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
@@ -353,6 +363,13 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
                     uint32_t box_outer) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) return -1;
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  Threads that have only
+  // ever been handed work by the autograd engine may not have touched the runtime yet -> CUDA_ERROR_INVALID_CONTEXT.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -365,20 +382,22 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, void* aux_out, int ld_auxout,
-                  GemmParams p, int num_sms, cudaStream_t stream) {
+                  void* b_copy_dst, int ld_bcopy, GemmParams p, int num_sms, cudaStream_t stream) {
   if (p.dact_in != nullptr) {            // aux INPUT tile (mutually exclusive with the pre-activation output)
     aux_out = const_cast<__nv_bfloat16*>(p.dact_in);
     ld_auxout = p.ld_aux;
     p.store_preact = 0;
   }
   using L = SmemLayout<BN>;
-  CUtensorMap ma, mb, md, mx;
+  CUtensorMap ma, mb, md, mx, mc;
   int e = 0;
+  p.b_copy = (b_copy_dst != nullptr && !B_MN) ? 1 : 0;
   // A: K-major -> [M rows, K inner]; MN-major -> stored [K rows, M inner]
   e |= A_MN ? make_map(&ma, A, p.M, p.K, lda, 64, BLOCK_K) : make_map(&ma, A, p.K, p.M, lda, BLOCK_K, BLOCK_M);
   e |= B_MN ? make_map(&mb, B, p.N, p.K, ldb, 64, BLOCK_K) : make_map(&mb, B, p.K, p.N, ldb, BLOCK_K, BN);
   e |= make_map(&md, D, p.N, p.M, ldd, SLAB_N, BLOCK_M);
   e |= make_map(&mx, aux_out ? aux_out : D, p.N, p.M, aux_out ? ld_auxout : ldd, SLAB_N, BLOCK_M);
+  e |= make_map(&mc, p.b_copy ? b_copy_dst : B, p.K, p.N, p.b_copy ? ld_bcopy : ldb, BLOCK_K, BN);
   if (e != 0) return 1000 + e;
   p.num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = (p.N + BN - 1) / BN;
@@ -392,7 +411,7 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma, mb, md, mx, p);
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma, mb, md, mx, mc, p);
   cudaError_t le = cudaGetLastError();
   return le == cudaSuccess ? 0 : 3000 + static_cast<int>(le);
 }
@@ -402,7 +421,7 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 // C entry point used by binding.cpp.  Layout flags: a_mn / b_mn = operand stored [K, rows] instead of [rows, K].
 extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
                              int K, const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out,
-                             int ld_preact, int block_n, int num_sms, cudaStream_t stream) {
+                             int ld_preact, void* b_copy_dst, int ld_bcopy, int block_n, int num_sms, cudaStream_t stream) {
   rvn::GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -412,10 +431,10 @@ extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   p.act = act;
   p.store_preact = preact_out != nullptr ? 1 : 0;
 #define RVN_DISPATCH(BN_)                                                                                              \
-  if (!a_mn && !b_mn) return rvn::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream); \
-  if (!a_mn && b_mn) return rvn::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream);   \
-  if (a_mn && b_mn) return rvn::launch<BN_, true, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream);     \
-  return rvn::launch<BN_, true, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, p, num_sms, stream);
+  if (!a_mn && !b_mn) return rvn::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream); \
+  if (!a_mn && b_mn) return rvn::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);   \
+  if (a_mn && b_mn) return rvn::launch<BN_, true, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);     \
+  return rvn::launch<BN_, true, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);
   if (block_n == 256) { RVN_DISPATCH(256) }
   RVN_DISPATCH(128)
 #undef RVN_DISPATCH

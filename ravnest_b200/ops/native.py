@@ -36,6 +36,29 @@ def _as2d(x: torch.Tensor) -> torch.Tensor:
     return x2
 
 
+_PEER_WEIGHTS = {}          # data_ptr of a local weight leaf -> (leaf, peer view holding the fresh values)
+
+
+def arm_peer_weight(leaf, peer_view):
+    _PEER_WEIGHTS[leaf.data_ptr()] = (leaf, peer_view)
+
+
+def drain_peer_weights():
+    items = list(_PEER_WEIGHTS.values())
+    _PEER_WEIGHTS.clear()
+    return items
+
+
+def _forward_gemm(x2, weight, bias, act, need_pre):
+    """x2 W^T (+bias, act).  If ``weight`` is armed for a leader pull (K2), B is read from the leader's HBM over NVLink
+    and landed in ``weight`` by the same kernel."""
+    armed = _PEER_WEIGHTS.pop(weight.data_ptr(), None) if _PEER_WEIGHTS else None
+    if armed is not None:
+        calls['gemm_fwd_bcast'] += 1
+        return C().gemm(x2, False, armed[1], False, bias, act, None, need_pre, 0, 1, None, weight.detach())
+    return C().gemm(x2, False, weight, False, bias, act, None, need_pre, 0)
+
+
 def _main_grad(weight):
     """The flat-bucket gradient view of a ParamStore leaf (or None): wgrad accumulates into it in the GEMM epilogue
     instead of materialising dW and paying a separate AccumulateGrad pass (Megatron-style gradient accumulation fusion)."""
@@ -80,7 +103,7 @@ class _Linear(torch.autograd.Function):
         x2 = _as2d(x)
         act = _ACT[activation]
         need_pre = act != 0 and (x.requires_grad or weight.requires_grad)
-        outs = C().gemm(x2, False, weight, False, bias, act, None, need_pre, 0)
+        outs = _forward_gemm(x2, weight, bias, act, need_pre)
         calls['gemm_fwd'] += 1
         ctx.act = act
         ctx.x_shape = x.shape
@@ -117,8 +140,8 @@ class _MLP(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, activation):
         x2 = _as2d(x)
         act = _ACT[activation]
-        h, z = C().gemm(x2, False, w1, False, b1, act, None, True, 0)
-        y = C().gemm(h, False, w2, False, b2, 0, None, False, 0)[0]
+        h, z = _forward_gemm(x2, w1, b1, act, True)
+        y = _forward_gemm(h, w2, b2, 0, False)[0]
         calls['gemm_fwd'] += 2
         ctx.act = act
         ctx.x_shape = x.shape

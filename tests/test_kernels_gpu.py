@@ -345,5 +345,17 @@ def test_fused_allreduce_optimizer_two_gpus():
     assert proc.returncode == 0 and 'DIST_GPU_OK' in proc.stdout, proc.stdout[-1500:] + proc.stderr[-3000:]
 
 
+def test_broadcast_fused_gemm_two_gpus():
+    """K2 on real peers: first forward pulls weights from the leader inside the GEMM (needs >= 2 GPUs)."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29879', os.path.join(here, 'dist_gpu_bcast_worker.py')]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert proc.returncode == 0 and 'BCAST_GPU_OK' in proc.stdout, proc.stdout[-1500:] + proc.stderr[-3000:]
+
+
 if __name__ == '__main__':
     sys.exit(pytest.main([__file__, '-x', '-q'] + (['-k', sys.argv[1]] if len(sys.argv) > 1 else [])))

@@ -6,6 +6,9 @@ export NCCL_DEBUG=${NCCL_DEBUG:-WARN}
 echo "== dist_gpu_worker" > gpurun_out/multi_summary.txt
 timeout -k 10 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29871 tests/dist_gpu_worker.py > gpurun_out/multi_worker.log 2>&1
 echo "exit=$? $(grep DIST_GPU_OK gpurun_out/multi_worker.log)" >> gpurun_out/multi_summary.txt
+echo "== bcast worker (K2)" >> gpurun_out/multi_summary.txt
+timeout -k 10 280 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29873 tests/dist_gpu_bcast_worker.py > gpurun_out/multi_bcast.log 2>&1
+echo "exit=$? $(grep BCAST_GPU_OK gpurun_out/multi_bcast.log)" >> gpurun_out/multi_summary.txt
 run() {
   name=$1; shift
   timeout -k 10 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 300)) bench.py --gpus $N "$@" > gpurun_out/$name.log 2>&1
