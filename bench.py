@@ -208,7 +208,7 @@ def main():
         os.makedirs(home, exist_ok=True)
         props = None
         if args.model == 'bert' and stages == 2:
-            props = [0.42, 0.58]            # leaf owns the (untied) 23.4 M decoder matrix: balance FLOPs, not params
+            props = [0.67, 0.33]            # root: embeddings + 7 layers; leaf: 5 layers + the 30522-wide MLM head (balanced step time)
         rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
                       node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props)
     if world > 1:

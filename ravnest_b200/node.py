@@ -480,11 +480,38 @@ class Node:
     def _serve_latest_weights(self, first, last):
         return self.compute_session.latest_weights(first, last)
 
-    def update_with_latest_weights(self) -> None:
-        """(Re)join: adopt the newest parameters held by peers of the next cluster
-        (reference node.py:726-730)."""
+    def update_with_latest_weights(self, leader: int = 0) -> None:
+        """(Re)join: adopt the newest parameters of this stage (reference node.py:726-730).
+
+        gRPC transport: stream them from the peer(s) of the next cluster (``get_latest_weights`` RPC).
+        dist transport on CUDA: K2 — the DP-group leader publishes its weight bucket in symmetric memory and the
+        next forward's GEMMs read their weight tiles straight from the leader's HBM over NVLink, landing them
+        locally on the way (``parallel/broadcast.py``).  Collective: every replica of the stage must call it."""
+        if self.dp_group is not None and self.device.type == 'cuda' and self.compute_session.store.compute_dtype == torch.bfloat16:
+            from .parallel.broadcast import WeightBroadcaster
+            self.wait_for_backwards() if self.node_type in (NodeTypes.ROOT, NodeTypes.SOLO) else None
+            if getattr(self, '_broadcaster', None) is None:
+                self._broadcaster = WeightBroadcaster(self.compute_session.store, self.dp_group, leader)
+            with self.compute_session.lock:
+                self._broadcaster.publish()
+                self._broadcaster.arm()
+                self._pending_pull = True
+            return
+        if self.dp_group is not None:
+            with self.compute_session.lock:
+                torch.distributed.broadcast(self.compute_session.store.master, src=torch.distributed.get_global_rank(self.dp_group, leader),
+                                            group=self.dp_group)
+                self.compute_session.store.publish()
+            return
         weights = self.comm_session.get_latest_weights()
         self.compute_session.load_weights(weights)
+
+    def finish_weight_pull(self) -> None:
+        """Complete a K2 pull after the first forward has consumed (and landed) the GEMM weights."""
+        if getattr(self, '_pending_pull', False):
+            with self.compute_session.lock:
+                self._broadcaster.finish()
+            self._pending_pull = False
 
     def checkpoint(self, tag: str = 'latest') -> str:
         from .utils.checkpoint import save_checkpoint

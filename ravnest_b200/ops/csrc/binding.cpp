@@ -10,7 +10,8 @@
 extern "C" {
 int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
                   const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out, int ld_preact,
-                  void* b_copy_dst, int ld_bcopy, int block_n, int num_sms, cudaStream_t stream);
+                  void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int num_sms,
+                  cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
@@ -80,7 +81,8 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
                                 const c10::optional<torch::Tensor>& bias, int64_t act,
                                 const c10::optional<torch::Tensor>& dact_in, bool store_preact, int64_t block_n,
                                 int64_t aux_mode, const c10::optional<torch::Tensor>& out,
-                                const c10::optional<torch::Tensor>& b_copy_dst) {
+                                const c10::optional<torch::Tensor>& b_copy_dst, const c10::optional<torch::Tensor>& bcopy_flags,
+                                int64_t bcopy_epoch) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16,
               "gemm expects CUDA bf16 operands");
   c10::cuda::CUDAGuard guard(A.device());
@@ -128,10 +130,14 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
     TORCH_CHECK(!b_mn && b_copy_dst->sizes() == B.sizes() && b_copy_dst->scalar_type() == torch::kBFloat16, "bad b_copy_dst");
     ld_bcopy = ld_of(*b_copy_dst);
     bcopy_ptr = b_copy_dst->data_ptr();
+    TORCH_CHECK(bcopy_flags.has_value() && bcopy_flags->defined() && bcopy_flags->scalar_type() == torch::kInt32 &&
+                bcopy_flags->numel() >= static_cast<int64_t>((N + 127) / 128) * ((K + 63) / 64), "bcopy_flags too small");
   }
+  unsigned* flags_ptr = bcopy_ptr != nullptr ? reinterpret_cast<unsigned*>(bcopy_flags->data_ptr<int>()) : nullptr;
   check(rvn_gemm_bf16(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
                       dact_ptr, ld_dact, static_cast<int>(aux_mode), preact_ptr, store_preact ? static_cast<int>(P.stride(0)) : ldd,
-                      bcopy_ptr, ld_bcopy, static_cast<int>(block_n), sm_count(), cur_stream()),
+                      bcopy_ptr, ld_bcopy, flags_ptr, static_cast<unsigned>(bcopy_epoch), static_cast<int>(block_n), sm_count(),
+                      cur_stream()),
         "gemm_bf16");
   std::vector<torch::Tensor> res;
   res.push_back(D.size(1) == N ? D : D.narrow(1, 0, N));
@@ -345,7 +351,8 @@ void fused_param_average(const std::vector<int64_t>& src_ptrs, const std::vector
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "bf16 tcgen05 GEMM with fused epilogue", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("aux_in") = py::none(), py::arg("store_preact") = false,
-        py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none());
+        py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none(),
+        py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0);
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("ce_fwd", &ce_fwd);

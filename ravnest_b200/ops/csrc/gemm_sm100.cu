@@ -37,7 +37,9 @@ struct GemmParams {
   int aux_mode;                   // 1: D = acc * act'(aux)  (activation gradient)   2: D = acc + aux  (gradient accumulation)
   int act;                        // Act
   int store_preact;               // also write the pre-activation through map_aux
-  int b_copy;                     // K2: B is read from a PEER's HBM; CTAs of the first M block also land every B tile locally
+  int b_copy;                     // K2: B is read from a PEER's HBM by the first-M-block CTAs, which land every tile locally;
+  unsigned* bcopy_flags;          //     the other CTAs wait on flags[n_blk * num_k_blocks + kb] >= bcopy_epoch and read the LOCAL copy
+  unsigned bcopy_epoch;
   int num_m_blocks, num_n_blocks, num_k_blocks;
 };
 
@@ -118,7 +120,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.b_copy ? 2 : 1);          // K2: the landing warp also has to release each stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -158,7 +160,19 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
               tma_load_2d(sa + j * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + j * 64, k0);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);                 // box {64 (K), BN rows}
+            if (p.b_copy && (tile % p.num_m_blocks) != 0) {
+              // K2: this B tile is being pulled over NVLink by the CTA that owns (m_blk 0, this n_blk); wait until it has
+              // landed in local HBM, then read the local copy (peer memory is not L2-cached, so only ONE CTA crosses the link)
+              const unsigned* flag = p.bcopy_flags + (tile / p.num_m_blocks) * p.num_k_blocks + kb;
+              unsigned seen;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+              } while (seen < p.bcopy_epoch);
+              asm volatile("fence.proxy.async;" ::: "memory");
+              tma_load_2d(sb, &map_bcopy, &full_bar[stage], k0, n0);
+            } else {
+              tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);               // box {64 (K), BN rows}
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
@@ -195,14 +209,6 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
                                      : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
             umma_bf16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
           }
-          if (!B_MN && p.b_copy && (tile % p.num_m_blocks) == 0) {
-            // K2 broadcast fusion: this B tile just arrived over NVLink from the stage leader; while the MMAs above
-            // consume it, write it through to the local weight buffer (TMA store undoes the swizzle) so every later
-            // step reads local HBM.  The store must have finished READING the stage before the stage is recycled.
-            tma_store_2d(&map_bcopy, smem + stage * L::STAGE_BYTES + L::A_BYTES, kb * BLOCK_K, (tile / p.num_m_blocks) * BN);
-            tma_store_commit();
-            tma_store_wait_read0();
-          }
           umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
         }
@@ -210,6 +216,43 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == 3) {
+    // ================================================================ K2 landing warp (only when B comes from a peer)
+    // B tiles of the first M block arrived over NVLink from the stage leader.  While the tensor cores consume them this
+    // warp writes them through to the local weight buffer (TMA store undoes the swizzle) and publishes a per-tile flag;
+    // CTAs of the other M blocks wait for the flag and read the LOCAL copy, so each weight byte crosses the link once.
+    if (!B_MN && p.b_copy && elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const bool lands = (tile % p.num_m_blocks) == 0;
+        const int n_blk = tile / p.num_m_blocks;
+        unsigned* flags = p.bcopy_flags + n_blk * p.num_k_blocks;
+        int published = 0;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (lands) {
+            tma_store_2d(&map_bcopy, smem + stage * L::STAGE_BYTES + L::A_BYTES, kb * BLOCK_K, n_blk * BN);
+            tma_store_commit();
+            tma_store_wait_read0();                               // smem stage may be recycled
+          }
+          mbar_arrive(&empty_bar[stage]);
+          if (lands && kb >= 2) {                                 // stores complete in order: everything but the last 2 is in HBM
+            asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            for (; published <= kb - 2; ++published)
+              asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + published), "r"(p.bcopy_epoch) : "memory");
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (lands) {
+          tma_store_wait_all();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          for (; published < p.num_k_blocks; ++published)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + published), "r"(p.bcopy_epoch) : "memory");
+        }
+      }
     }
   } else if (warp >= 4) {
     // ================================================================ epilogue (128 threads, one row each)
@@ -222,10 +265,13 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t aux_phase = 0;
     const bool has_aux_in = p.dact_in != nullptr;
     const bool one_buffer = p.store_preact || has_aux_in;     // staging[1] is taken by the aux slab (in or out)
+    if (has_aux_in && issuer && static_cast<int>(blockIdx.x) < num_tiles) {   // aux tile of the very first slab: overlaps the mainloop
+      mbar_expect_tx(aux_bar, SLAB_BYTES);
+      tma_load_2d(staging + SLAB_BYTES, &map_aux, aux_bar, (blockIdx.x / p.num_m_blocks) * BN, (blockIdx.x % p.num_m_blocks) * BLOCK_M);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
       const int n0 = (tile / p.num_m_blocks) * BN;
-      const int grow = m0 + row_in_tile;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -239,16 +285,6 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (one_buffer) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         named_bar_sync(1, EPI_THREADS);
-        if (has_aux_in) {
-          // auxiliary input slab (pre-activation z, or the gradient tile being accumulated into) comes in through TMA:
-          // coalesced 128 B rows into swizzled smem instead of 32 scattered 16 B row reads per warp instruction
-          if (issuer) {
-            mbar_expect_tx(aux_bar, SLAB_BYTES);
-            tma_load_2d(buf_aux, &map_aux, aux_bar, col0, m0);
-          }
-          mbar_wait(aux_bar, aux_phase);
-          aux_phase ^= 1;
-        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
@@ -285,6 +321,12 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
           }
           if (has_aux_in) {
+            // auxiliary input slab (pre-activation z, or the gradient tile being accumulated into) arrives through TMA
+            // (coalesced 128 B rows into swizzled smem); its load was issued one slab ahead, so this wait is usually free
+            if (half == 0) {
+              mbar_wait(aux_bar, aux_phase);
+              aux_phase ^= 1;
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               const int chunk = half * 4 + (i >> 3);
@@ -327,6 +369,16 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
           tma_store_2d(&map_d, buf_main, col0, m0);
           if (p.store_preact) tma_store_2d(&map_aux, buf_aux, col0, m0);
           tma_store_commit();
+          if (has_aux_in) {
+            // every thread has consumed buf_aux (it passed the barrier above): prefetch the NEXT slab's aux tile now,
+            // either the next slab of this tile or the first slab of this CTA's next tile
+            int nt = tile, ns = slab + 1;
+            if (ns == BN / SLAB_N || n0 + ns * SLAB_N >= p.N) { nt = tile + gridDim.x; ns = 0; }
+            if (nt < num_tiles) {
+              mbar_expect_tx(aux_bar, SLAB_BYTES);
+              tma_load_2d(buf_aux, &map_aux, aux_bar, (nt / p.num_m_blocks) * BN + ns * SLAB_N, (nt % p.num_m_blocks) * BLOCK_M);
+            }
+          }
         }
         ++slab_counter;
       }
@@ -383,6 +435,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, void* aux_out, int ld_auxout,
                   void* b_copy_dst, int ld_bcopy, GemmParams p, int num_sms, cudaStream_t stream) {
+  if (p.bcopy_flags == nullptr) b_copy_dst = nullptr;
   if (p.dact_in != nullptr) {            // aux INPUT tile (mutually exclusive with the pre-activation output)
     aux_out = const_cast<__nv_bfloat16*>(p.dact_in);
     ld_auxout = p.ld_aux;
@@ -421,7 +474,8 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 // C entry point used by binding.cpp.  Layout flags: a_mn / b_mn = operand stored [K, rows] instead of [rows, K].
 extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
                              int K, const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out,
-                             int ld_preact, void* b_copy_dst, int ld_bcopy, int block_n, int num_sms, cudaStream_t stream) {
+                             int ld_preact, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n,
+                             int num_sms, cudaStream_t stream) {
   rvn::GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -430,6 +484,8 @@ extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   p.aux_mode = dact_in != nullptr ? aux_mode : 0;
   p.act = act;
   p.store_preact = preact_out != nullptr ? 1 : 0;
+  p.bcopy_flags = bcopy_flags;
+  p.bcopy_epoch = bcopy_epoch;
 #define RVN_DISPATCH(BN_)                                                                                              \
   if (!a_mn && !b_mn) return rvn::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream); \
   if (!a_mn && b_mn) return rvn::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);   \

@@ -49,13 +49,27 @@ def drain_peer_weights():
     return items
 
 
+_BCAST = {}
+
+
+def bcast_flags(device):
+    """Per-device landing flags of the broadcast-fused GEMM (one per weight tile) and a monotonically increasing
+    epoch, so the flags never need clearing between calls."""
+    key = (device.type, device.index)
+    if key not in _BCAST:
+        _BCAST[key] = [torch.zeros(1 << 16, dtype=torch.int32, device=device), 0]
+    _BCAST[key][1] += 1
+    return _BCAST[key][0], _BCAST[key][1]
+
+
 def _forward_gemm(x2, weight, bias, act, need_pre):
     """x2 W^T (+bias, act).  If ``weight`` is armed for a leader pull (K2), B is read from the leader's HBM over NVLink
     and landed in ``weight`` by the same kernel."""
     armed = _PEER_WEIGHTS.pop(weight.data_ptr(), None) if _PEER_WEIGHTS else None
     if armed is not None:
         calls['gemm_fwd_bcast'] += 1
-        return C().gemm(x2, False, armed[1], False, bias, act, None, need_pre, 0, 1, None, weight.detach())
+        flags, epoch = bcast_flags(weight.device)
+        return C().gemm(x2, False, armed[1], False, bias, act, None, need_pre, 0, 1, None, weight.detach(), flags, epoch)
     return C().gemm(x2, False, weight, False, bias, act, None, need_pre, 0)
 
 

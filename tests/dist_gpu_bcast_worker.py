@@ -57,7 +57,8 @@ def main():
     C = native.C()
 
     def fused():
-        return C.gemm(x, False, peer, False, None, 0, None, False, 0, 1, None, w_local.detach())
+        flags, epoch = native.bcast_flags(w_local.device)
+        return C.gemm(x, False, peer, False, None, 0, None, False, 0, 1, None, w_local.detach(), flags, epoch)
 
     def unfused():
         w_local.detach().copy_(peer)
