@@ -8,6 +8,8 @@ the 23 917 832 parameters of the Tiny-ImageNet config.  torchvision state dicts 
 import torch
 from torch import nn
 
+from .. import nn as rnn
+
 
 class Bottleneck(nn.Module):
     expansion = 4
@@ -15,16 +17,16 @@ class Bottleneck(nn.Module):
     def __init__(self, inplanes, planes, stride=1, downsample=False):
         super().__init__()
         out = planes * self.expansion
-        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.conv1 = rnn.Conv2d(inplanes, planes, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.conv2 = rnn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, out, 1, bias=False)
+        self.conv3 = rnn.Conv2d(planes, out, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(out)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = None
         if downsample:
-            self.downsample = nn.Sequential(nn.Conv2d(inplanes, out, 1, stride=stride, bias=False), nn.BatchNorm2d(out))
+            self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False), nn.BatchNorm2d(out))
 
     def forward(self, x):
         y = self.relu(self.bn1(self.conv1(x)))
@@ -38,7 +40,7 @@ class Bottleneck(nn.Module):
 class ResNet(nn.Module):
     def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, zero_init_residual=False):
         super().__init__()
-        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.conv1 = rnn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)

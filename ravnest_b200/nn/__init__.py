@@ -88,6 +88,16 @@ class SelfAttention(nn.Module):
         return ops.attention_qkv(qkv, self.heads, key_padding_mask, self.causal, self.dropout_p if self.training else 0.0)
 
 
+class Conv2d(nn.Conv2d):
+    """Drop-in ``nn.Conv2d`` (same parameters / state dict).  Pointwise convolutions of channels_last bf16 activations run
+    on the tcgen05 GEMM; everything else goes to cuDNN."""
+
+    def forward(self, x):
+        if isinstance(self.padding, str) or self.padding_mode != 'zeros':
+            return super().forward(x)
+        return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+
 class GELU(nn.Module):
     def __init__(self, approximate='none'):
         super().__init__()
@@ -97,4 +107,4 @@ class GELU(nn.Module):
         return F.gelu(x, approximate=self.approximate)
 
 
-__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'GELU']
+__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'Conv2d', 'GELU']

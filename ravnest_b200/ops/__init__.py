@@ -133,6 +133,16 @@ def cross_entropy(logits, target, ignore_index=-100):
     return reference_cross_entropy(logits, target, ignore_index)
 
 
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """2-D convolution.  On CUDA (bf16, channels_last) pointwise convolutions run on the tcgen05 GEMM — in NHWC a 1x1
+    convolution IS ``[N*H*W, Cin] x [Cout, Cin]^T`` with zero data movement; other shapes use cuDNN (K4 implicit-GEMM
+    kernel is the next step)."""
+    if _native(x, weight):
+        from . import native
+        return native.conv2d(x, weight, bias, stride, padding, dilation, groups)
+    return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+
 def native_ops_loaded():
     """Names of native kernels that have actually been launched in this process."""
     try:
@@ -142,6 +152,6 @@ def native_ops_loaded():
         return {}
 
 
-__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
            'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
            'reference_cross_entropy']

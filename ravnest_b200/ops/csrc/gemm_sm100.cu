@@ -37,8 +37,11 @@ struct GemmParams {
   int aux_mode;                   // 1: D = acc * act'(aux)  (activation gradient)   2: D = acc + aux  (gradient accumulation)
   int act;                        // Act
   int store_preact;               // also write the pre-activation through map_aux
-  int b_copy;                     // K2: B is read from a PEER's HBM by the first-M-block CTAs, which land every tile locally;
-  unsigned* bcopy_flags;          //     the other CTAs wait on flags[n_blk * num_k_blocks + kb] >= bcopy_epoch and read the LOCAL copy
+  int b_copy;                     // K2: B lives in a PEER's HBM.  The (otherwise idle) epilogue warps of all CTAs first pull it
+  const __nv_bfloat16* b_peer;    //     tile by tile over NVLink into the local buffer (every SM issues peer loads: one SM alone gets
+  __nv_bfloat16* b_local;         //     ~5 GB/s, the whole chip ~750 GB/s) and publish flags[n_blk * num_k_blocks + kb] = epoch;
+  int ld_bpeer, ld_blocal;        //     TMA producers wait on the flag of the tile they need and read the LOCAL copy.
+  unsigned* bcopy_flags;
   unsigned bcopy_epoch;
   int num_m_blocks, num_n_blocks, num_k_blocks;
 };
@@ -120,7 +123,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], p.b_copy ? 2 : 1);          // K2: the landing warp also has to release each stage
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -160,9 +163,9 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
               tma_load_2d(sa + j * (BLOCK_K * 128), &map_a, &full_bar[stage], m0 + j * 64, k0);
           }
           if constexpr (!B_MN) {
-            if (p.b_copy && (tile % p.num_m_blocks) != 0) {
-              // K2: this B tile is being pulled over NVLink by the CTA that owns (m_blk 0, this n_blk); wait until it has
-              // landed in local HBM, then read the local copy (peer memory is not L2-cached, so only ONE CTA crosses the link)
+            if (p.b_copy) {
+              // K2: wait until the epilogue warps of some CTA have pulled this B tile over NVLink into local HBM, then read
+              // the local copy (peer memory bypasses L2, so every weight byte must cross the link exactly once)
               const unsigned* flag = p.bcopy_flags + (tile / p.num_m_blocks) * p.num_k_blocks + kb;
               unsigned seen;
               do {
@@ -217,43 +220,6 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp == 3) {
-    // ================================================================ K2 landing warp (only when B comes from a peer)
-    // B tiles of the first M block arrived over NVLink from the stage leader.  While the tensor cores consume them this
-    // warp writes them through to the local weight buffer (TMA store undoes the swizzle) and publishes a per-tile flag;
-    // CTAs of the other M blocks wait for the flag and read the LOCAL copy, so each weight byte crosses the link once.
-    if (!B_MN && p.b_copy && elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const bool lands = (tile % p.num_m_blocks) == 0;
-        const int n_blk = tile / p.num_m_blocks;
-        unsigned* flags = p.bcopy_flags + n_blk * p.num_k_blocks;
-        int published = 0;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          if (lands) {
-            tma_store_2d(&map_bcopy, smem + stage * L::STAGE_BYTES + L::A_BYTES, kb * BLOCK_K, n_blk * BN);
-            tma_store_commit();
-            tma_store_wait_read0();                               // smem stage may be recycled
-          }
-          mbar_arrive(&empty_bar[stage]);
-          if (lands && kb >= 2) {                                 // stores complete in order: everything but the last 2 is in HBM
-            asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
-            asm volatile("fence.proxy.async;" ::: "memory");
-            for (; published <= kb - 2; ++published)
-              asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + published), "r"(p.bcopy_epoch) : "memory");
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (lands) {
-          tma_store_wait_all();
-          asm volatile("fence.proxy.async;" ::: "memory");
-          for (; published < p.num_k_blocks; ++published)
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + published), "r"(p.bcopy_epoch) : "memory");
-        }
-      }
-    }
   } else if (warp >= 4) {
     // ================================================================ epilogue (128 threads, one row each)
     const int ewarp = warp - 4;                 // TMEM lane quadrant == warp index % 4
@@ -263,6 +229,27 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t acc_phase = 0;
     uint32_t slab_counter = 0;
     uint32_t aux_phase = 0;
+    if (!B_MN && p.b_copy) {
+      // ---- K2 cooperative pull: B tile t = (n_blk, kb) is fetched from the leader by CTA (t mod grid); 16 B per load,
+      //      BN*8/128 independent loads per thread in flight, landed with plain stores, then a release flag
+      const int et = threadIdx.x - 128;
+      const int n_pull = p.num_n_blocks * p.num_k_blocks;
+      for (int t = blockIdx.x; t < n_pull; t += gridDim.x) {
+        const int r0 = (t / p.num_k_blocks) * BN;
+        const int c0 = (t % p.num_k_blocks) * BLOCK_K;
+#pragma unroll 4
+        for (int ch = et; ch < BN * 8; ch += EPI_THREADS) {
+          const int r = r0 + (ch >> 3), c = c0 + (ch & 7) * 8;
+          if (r < p.N && c < p.K) {
+            const uint4 v = *reinterpret_cast<const uint4*>(p.b_peer + static_cast<size_t>(r) * p.ld_bpeer + c);
+            *reinterpret_cast<uint4*>(p.b_local + static_cast<size_t>(r) * p.ld_blocal + c) = v;
+          }
+        }
+        __threadfence();
+        named_bar_sync(1, EPI_THREADS);
+        if (et == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.bcopy_flags + t), "r"(p.bcopy_epoch) : "memory");
+      }
+    }
     const bool has_aux_in = p.dact_in != nullptr;
     const bool one_buffer = p.store_preact || has_aux_in;     // staging[1] is taken by the aux slab (in or out)
     if (has_aux_in && issuer && static_cast<int>(blockIdx.x) < num_tiles) {   // aux tile of the very first slab: overlaps the mainloop
@@ -445,6 +432,10 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
   CUtensorMap ma, mb, md, mx, mc;
   int e = 0;
   p.b_copy = (b_copy_dst != nullptr && !B_MN) ? 1 : 0;
+  p.b_peer = static_cast<const __nv_bfloat16*>(B);
+  p.b_local = static_cast<__nv_bfloat16*>(b_copy_dst);
+  p.ld_bpeer = ldb;
+  p.ld_blocal = ld_bcopy;
   // A: K-major -> [M rows, K inner]; MN-major -> stored [K rows, M inner]
   e |= A_MN ? make_map(&ma, A, p.M, p.K, lda, 64, BLOCK_K) : make_map(&ma, A, p.K, p.M, lda, BLOCK_K, BLOCK_M);
   e |= B_MN ? make_map(&mb, B, p.N, p.K, ldb, 64, BLOCK_K) : make_map(&mb, B, p.K, p.N, ldb, BLOCK_K, BN);

@@ -320,3 +320,29 @@ def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0
     out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=dropout_p, is_causal=causal and mask is None)
     fallbacks['attention'] += 1
     return out.transpose(1, 2).reshape(B, S, H)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """Pointwise (1x1) convolutions on NHWC activations are GEMMs over the channel dimension: they reuse the tcgen05
+    GEMM (forward, dgrad with MN-major weights, wgrad with both operands MN-major) through ``linear``."""
+    kh, kw = weight.shape[2], weight.shape[3]
+    sh, sw = _pair(stride)
+    ph, pw = _pair(padding) if not isinstance(padding, str) else (0, 0)
+    ok = (kh == 1 and kw == 1 and groups == 1 and ph == 0 and pw == 0 and x.dim() == 4 and x.dtype == torch.bfloat16
+          and weight.dtype == torch.bfloat16 and weight.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0)
+    if not ok:
+        fallbacks['conv2d'] += 1
+        return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+    if sh != 1 or sw != 1:
+        x = x[:, :, ::sh, ::sw]
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    n, c, h, w = x.shape
+    x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)                  # zero-copy NHWC view
+    y2 = linear(x2, weight.reshape(weight.shape[0], c), bias, None)
+    calls['conv1x1_as_gemm'] += 1
+    return y2.view(n, h, w, weight.shape[0]).permute(0, 3, 1, 2)      # NCHW-shaped, channels_last-strided
