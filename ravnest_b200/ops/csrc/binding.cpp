@@ -27,6 +27,8 @@ int rvn_fmha_forward(const void* qkv, void* out, float* lse, const float* kbias,
 int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const float* lse, const float* kbias, float* delta, float* dq_accum,
                       void* dqkv, int B, int S, int heads, int causal, float scale, const long long* rng, float dropout_p, int num_sms,
                       cudaStream_t stream);
+int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho, int Wo,
+                     int Cout, int R, int S, int stride, int pad, int dil, int transposed, int num_sms, cudaStream_t stream);
 int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
 }
 
@@ -286,6 +288,35 @@ torch::Tensor fmha_bwd(const torch::Tensor& qkv, const torch::Tensor& out, const
   return dqkv;
 }
 
+// x: [N,H,W,Cin] bf16 contiguous (NHWC); w: [Cout,R,S,Cin] contiguous.  transposed=false: y = conv(x, w) -> [N,Ho,Wo,Cout].
+// transposed=true (dgrad, stride 1): x is dy [N,Ho,Wo,Cout], result is dx [N,H,W,Cin]; `out_hw` gives the result's H, W.
+torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c10::optional<torch::Tensor>& bias, int64_t stride,
+                        int64_t pad, int64_t dil, bool relu, bool transposed, int64_t out_h, int64_t out_w) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 &&
+              w.scalar_type() == torch::kBFloat16, "conv_nhwc expects contiguous bf16 NHWC activations and [Cout,R,S,Cin] weights");
+  const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
+  const int R = w.size(1), S = w.size(2);
+  const int k_ch = transposed ? w.size(0) : w.size(3);      // channels reduced over
+  const int n_ch = transposed ? w.size(3) : w.size(0);      // channels produced
+  TORCH_CHECK(C == k_ch && k_ch % 8 == 0 && n_ch % 8 == 0, "channel counts must match and be multiples of 8");
+  int Ho, Wo;
+  if (transposed) {
+    TORCH_CHECK(stride == 1, "native dgrad handles stride 1");
+    Ho = out_h; Wo = out_w;
+  } else {
+    Ho = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+    Wo = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  }
+  auto y = torch::empty({N, Ho, Wo, n_ch}, x.options());
+  const void* bias_ptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  const int eff_pad = transposed ? static_cast<int>(dil * (R - 1) - pad) : static_cast<int>(pad);
+  check(rvn_conv_forward(x.data_ptr(), w.data_ptr(), y.data_ptr(), bias_ptr, relu, N, H, W, k_ch, Ho, Wo, n_ch, R, S, static_cast<int>(stride),
+                         eff_pad, static_cast<int>(dil), transposed, sm_count(), cur_stream()),
+        "conv_forward");
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------------- fused optimizers
 PeerPtrs make_peers(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank) {
   PeerPtrs pp{};
@@ -359,6 +390,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_bwd", &ce_bwd);
   m.def("column_sum", &column_sum);
   m.def("act_bwd", &act_bwd);
+  m.def("conv_nhwc", &conv_nhwc);
   m.def("fmha_fwd", &fmha_fwd);
   m.def("fmha_bwd", &fmha_bwd);
   m.def("fused_update", &fused_update);

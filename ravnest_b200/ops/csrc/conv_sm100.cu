@@ -1,0 +1,407 @@
+// K4: NHWC bf16 convolution as an IMPLICIT GEMM on tcgen05 (no im2col buffer ever exists).
+//
+//   y[n, ho, wo, co] = sum_{r, s, ci} x[n, ho*stride + r*dil - pad, wo*stride + s*dil - pad, ci] * w[co, r, s, ci]
+//
+// GEMM view: M = output pixels, N = Cout, K = (r, s, ci).  A CTA tile is a TN x TH x TW patch of output pixels (<= 128
+// rows).  For filter tap (r, s) and a 64-channel slice, the A operand of that patch is the SAME patch of input pixels
+// shifted by the tap — one 4-D TMA box load {64 ch, TW, TH, TN} (element strides = conv stride) whose out-of-bounds
+// elements TMA zero-fills: padding costs nothing and there is no per-element address arithmetic anywhere.
+// B (weights, [Cout, R*S, Cin]) is a 3-D TMA box {64 ch, 1 tap, BN}.  The K loop walks taps x channel slices.
+// Everything downstream of the operand fetch is the GEMM pipeline of gemm_sm100.cu: smem ring -> tcgen05.mma (UMMA
+// 128 x BN x 16) -> double-buffered TMEM accumulators -> tcgen05.ld epilogue -> bf16 -> swizzled smem -> 4-D TMA store
+// of the output patch (clipped at the image borders by TMA).
+//
+// The same kernel computes dgrad of stride-1 convolutions (dx = conv(dy, flipped taps) with the weight read MN-major
+// through the [Cin, R*S, Cout] view), see rvn_conv_forward's `transposed` flag.
+// Reference call sites: every nn.Conv2d of ResNet-50 / Inception-V3 / CNN_Net, cuDNN upstream.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sm100_ptx.cuh"
+
+namespace rvn {
+
+constexpr int CV_BLOCK_M = 128;
+constexpr int CV_BLOCK_K = 64;
+constexpr int CV_THREADS = 256;
+constexpr int CV_EPI_THREADS = 128;
+constexpr int CV_SLAB_N = 64;
+constexpr int CV_SLAB_BYTES = CV_BLOCK_M * CV_SLAB_N * 2;
+
+struct ConvParams {
+  int N, H, W, Cin, Ho, Wo, Cout;
+  int R, S, stride, pad, dil;
+  int TW, TH, TN;                 // output patch of one CTA tile (TW*TH*TN <= 128)
+  int tiles_w, tiles_h, tiles_n;  // patches per dimension
+  int num_n_blocks;               // Cout / BN (rounded up)
+  int cin_blocks;                 // ceil(Cin / 64)
+  int flip;                       // 1: walk taps mirrored (dgrad)
+  const __nv_bfloat16* bias;      // [Cout] or nullptr
+  int relu;
+};
+
+// 4-D / 3-D TMA loads and the 4-D store
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int BN>
+struct ConvSmem {
+  static constexpr int A_BYTES = CV_BLOCK_M * CV_BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * CV_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int OPERAND_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = OPERAND_BYTES + 2 * CV_SLAB_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                               const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
+  using L = ConvSmem<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t IDESC = make_idesc_bf16(CV_BLOCK_M, BN, false, B_MN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + L::OPERAND_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_tiles = m_tiles * p.num_n_blocks;
+  const int num_k_blocks = p.R * p.S * p.cin_blocks;
+  const int rows = p.TW * p.TH * p.TN;                    // valid rows of an A tile / output patch
+  const uint32_t a_bytes = static_cast<uint32_t>(rows) * 128u;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_y);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], CV_EPI_THREADS / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 4 && rows < CV_BLOCK_M) {
+    // rows beyond the patch are never loaded by TMA: zero them once so the MMA never multiplies stale NaN patterns
+    for (int s = 0; s < STAGES; ++s) {
+      uint4* dst = reinterpret_cast<uint4*>(smem + s * L::STAGE_BYTES + rows * 128);
+      for (int i = threadIdx.x - 128; i < (CV_BLOCK_M - rows) * 8; i += CV_EPI_THREADS) dst[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int& wo0, int& ho0, int& n0, int& co0) {
+    const int mt = tile % m_tiles;
+    co0 = (tile / m_tiles) * BN;
+    wo0 = (mt % p.tiles_w) * p.TW;
+    ho0 = ((mt / p.tiles_w) % p.tiles_h) * p.TH;
+    n0 = (mt / (p.tiles_w * p.tiles_h)) * p.TN;
+  };
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int wo0, ho0, n0, co0;
+        decode(tile, wo0, ho0, n0, co0);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          const int tap = kb / p.cin_blocks;
+          const int c0 = (kb % p.cin_blocks) * CV_BLOCK_K;
+          int r = tap / p.S, s = tap % p.S;
+          if (p.flip) { r = p.R - 1 - r; s = p.S - 1 - s; }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], a_bytes + L::B_BYTES);
+          // input patch of this tap: coordinates may be negative / beyond the image -> TMA zero fill == padding
+          tma_load_4d(sa, &map_x, &full_bar[stage], c0, wo0 * p.stride + s * p.dil - p.pad, ho0 * p.stride + r * p.dil - p.pad, n0);
+          if constexpr (!B_MN) {
+            tma_load_3d(sb, &map_w, &full_bar[stage], c0, tap, co0);                       // {64 ci, 1 tap, BN co}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)                                               // weight viewed [ci(K rows)][tap][co]
+              tma_load_3d(sb + j * (CV_BLOCK_K * 128), &map_w, &full_bar[stage], co0 + j * 64, tap, c0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < CV_BLOCK_K / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, CV_BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_bf16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue
+    const int ewarp = warp - 4;
+    const int row_in_tile = ewarp * 32 + lane_id();
+    const bool issuer = threadIdx.x == 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t slab_counter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int wo0, ho0, n0, co0;
+      decode(tile, wo0, ho0, n0, co0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int slab = 0; slab < BN / CV_SLAB_N; ++slab) {
+        const int col0 = co0 + slab * CV_SLAB_N;
+        if (col0 >= p.Cout) break;
+        uint8_t* buf = staging + (slab_counter & 1) * CV_SLAB_BYTES;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        named_bar_sync(1, CV_EPI_THREADS);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BN + slab * CV_SLAB_N + half * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const int c_base = col0 + half * 32;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (c_base + i < p.Cout) {
+                const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(p.bias + c_base + i));
+                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 bf = __bfloat1622float2(b2[j]);
+                  f[i + 2 * j] += bf.x;
+                  f[i + 2 * j + 1] += bf.y;
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const int chunk = half * 4 + (i >> 3);
+            uint4 o;
+            o.x = pack_bf16x2(f[i], f[i + 1]); o.y = pack_bf16x2(f[i + 2], f[i + 3]);
+            o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+            *reinterpret_cast<uint4*>(buf + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = o;
+          }
+        }
+        if (slab == BN / CV_SLAB_N - 1 || col0 + CV_SLAB_N >= p.Cout) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane_id() == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, CV_EPI_THREADS);
+        if (issuer) {
+          tma_store_4d(&map_y, buf, col0, wo0, ho0, n0);        // rows of the patch in (n, h, w) order; clipped at borders
+          tma_store_commit();
+        }
+        ++slab_counter;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn3 conv_encode() {
+  static EncodeTiledFn3 fn = nullptr;
+  if (fn == nullptr) {
+    cudaFree(nullptr);
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn3>(ptr);
+  }
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
+  return fn;
+}
+
+// generic bf16 tensor map: dims / strides given innermost-first (strides in ELEMENTS for dims 1..rank-1)
+static int make_map_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                       const uint32_t* box, const uint32_t* elem_strides) {
+  EncodeTiledFn3 enc = conv_encode();
+  if (enc == nullptr) return -1;
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = elem_strides[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_elems[i] * 2;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+// pick the output patch (TW, TH, TN), TW*TH*TN <= 128, that wastes the fewest MMA rows for this layer
+static void pick_patch(int Wo, int Ho, int N, int& TW, int& TH, int& TN) {
+  double best = -1.0;
+  for (int tw = 1; tw <= 128 && tw <= Wo + 0; ++tw) {
+    if (tw > 64) break;
+    for (int th = 1; tw * th <= 128 && th <= Ho; ++th) {
+      int tn = 128 / (tw * th);
+      if (tn > N) tn = N;
+      if (tn < 1) continue;
+      const double tiles = static_cast<double>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+      const double eff = static_cast<double>(Wo) * Ho * N / (tiles * 128.0);
+      if (eff > best + 1e-9) { best = eff; TW = tw; TH = th; TN = tn; }
+    }
+  }
+}
+
+template <int BN, bool B_MN>
+static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int num_sms, cudaStream_t stream) {
+  using L = ConvSmem<BN>;
+  CUtensorMap mx, mw, my;
+  pick_patch(p.Wo, p.Ho, p.N, p.TW, p.TH, p.TN);
+  p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
+  p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
+  p.tiles_n = (p.N + p.TN - 1) / p.TN;
+  p.num_n_blocks = (p.Cout + BN - 1) / BN;
+  p.cin_blocks = (p.Cin + CV_BLOCK_K - 1) / CV_BLOCK_K;
+  int e = 0;
+  {   // x: [N, H, W, Cin] -> dims (Cin, W, H, N); box walks `stride` elements per output pixel
+    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    const uint64_t st[3] = {(uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    const uint32_t box[4] = {64u, (uint32_t)((p.TW - 1) * p.stride + 1), (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TN};
+    const uint32_t es[4] = {1u, (uint32_t)p.stride, (uint32_t)p.stride, 1u};
+    e |= make_map_nd(&mx, x, 4, dims, st, box, es);
+  }
+  if (!B_MN) {   // w: [Cout, R*S, Cin] -> dims (Cin, RS, Cout), box {64, 1, BN}
+    const uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.R * p.S, (uint64_t)p.Cout};
+    const uint64_t st[2] = {(uint64_t)p.Cin, (uint64_t)p.R * p.S * p.Cin};
+    const uint32_t box[3] = {64u, 1u, (uint32_t)BN};
+    const uint32_t es[3] = {1u, 1u, 1u};
+    e |= make_map_nd(&mw, w, 3, dims, st, box, es);
+  } else {       // dgrad: weight stored [K_out = old Cout... see rvn_conv_forward]: dims (Cout_gemm, RS, Cin_gemm), box {64, 1, 64}
+    const uint64_t dims[3] = {(uint64_t)p.Cout, (uint64_t)p.R * p.S, (uint64_t)p.Cin};
+    const uint64_t st[2] = {(uint64_t)p.Cout, (uint64_t)p.R * p.S * p.Cout};
+    const uint32_t box[3] = {64u, 1u, 64u};
+    const uint32_t es[3] = {1u, 1u, 1u};
+    e |= make_map_nd(&mw, w, 3, dims, st, box, es);
+  }
+  {   // y: [N, Ho, Wo, Cout] -> dims (Cout, Wo, Ho, N), box {64, TW, TH, TN}
+    const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
+    const uint64_t st[3] = {(uint64_t)p.Cout, (uint64_t)p.Wo * p.Cout, (uint64_t)p.Ho * p.Wo * p.Cout};
+    const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    const uint32_t es[4] = {1u, 1u, 1u, 1u};
+    e |= make_map_nd(&my, y, 4, dims, st, box, es);
+  }
+  if (e != 0) return 1000 + e;
+  auto kern = rvn_conv_implicit_gemm_tcgen05<BN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return 2000;
+    configured = true;
+  }
+  const int tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.num_n_blocks;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, CV_THREADS, L::TOTAL, stream>>>(mx, mw, my, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3000;
+}
+
+}  // namespace rvn
+
+// x [N,H,W,Cin], w [Cout,R,S,Cin] (or, transposed=1, the SAME buffer consumed as a map from Cout_in -> Cin_out for dgrad:
+// then `Cin`/`Cout` below are the GEMM K / N channel counts, i.e. Cin = channels of the incoming gradient), y [N,Ho,Wo,Cout].
+extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho,
+                                int Wo, int Cout, int R, int S, int stride, int pad, int dil, int transposed, int num_sms,
+                                cudaStream_t stream) {
+  rvn::ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.flip = transposed;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.relu = relu;
+  const long long m_tiles = (static_cast<long long>(N) * Ho * Wo + 127) / 128;
+  const bool wide = Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= num_sms;
+  if (transposed) {
+    if (wide) return rvn::conv_launch<256, true>(x, w, y, p, num_sms, stream);
+    return rvn::conv_launch<128, true>(x, w, y, p, num_sms, stream);
+  }
+  if (wide) return rvn::conv_launch<256, false>(x, w, y, p, num_sms, stream);
+  return rvn::conv_launch<128, false>(x, w, y, p, num_sms, stream);
+}

@@ -149,6 +149,19 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
         const int n0 = (tile / p.num_m_blocks) * BN;
+        if (!B_MN && p.b_copy) {
+          // K2: wait until the epilogue warps (of up to num_k_blocks different CTAs, in parallel) have pulled this n-block of B
+          // over NVLink into local HBM; ONE proxy fence per tile, then every B load of the tile reads the local copy
+          // (peer memory bypasses L2, so each weight byte must cross the link exactly once)
+          const unsigned* flags = p.bcopy_flags + (tile / p.num_m_blocks) * p.num_k_blocks;
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            unsigned seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + kb) : "memory");
+            } while (seen < p.bcopy_epoch);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -164,15 +177,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
           }
           if constexpr (!B_MN) {
             if (p.b_copy) {
-              // K2: wait until the epilogue warps of some CTA have pulled this B tile over NVLink into local HBM, then read
-              // the local copy (peer memory bypasses L2, so every weight byte must cross the link exactly once)
-              const unsigned* flag = p.bcopy_flags + (tile / p.num_m_blocks) * p.num_k_blocks + kb;
-              unsigned seen;
-              do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-              } while (seen < p.bcopy_epoch);
-              asm volatile("fence.proxy.async;" ::: "memory");
-              tma_load_2d(sb, &map_bcopy, &full_bar[stage], k0, n0);
+              tma_load_2d(sb, &map_bcopy, &full_bar[stage], k0, n0);          // local copy (its landing was awaited per tile)
             } else {
               tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);               // box {64 (K), BN rows}
             }

@@ -326,23 +326,83 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
+class _ConvNHWC(torch.autograd.Function):
+    """Implicit-GEMM convolution (ops/csrc/conv_sm100.cu) on NHWC activations.  Forward and the stride-1 data gradient run
+    on the tcgen05 kernel; the weight gradient (and stride-2 data gradients) still go through cuDNN — tracked in DESIGN.md."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, w_ohwi, bias, stride, pad, dil, relu):
+        y = C().conv_nhwc(x_nhwc, w_ohwi, bias, stride, pad, dil, relu, False, 0, 0)
+        calls['conv_fwd'] += 1
+        ctx.cfg = (stride, pad, dil, relu)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x_nhwc, w_ohwi, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        stride, pad, dil, relu = ctx.cfg
+        dy = dy.contiguous()
+        if relu:
+            dy = dy * (y > 0)
+        dx = dw = db = None
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        native_dx = need_dx and stride == 1
+        if native_dx:
+            dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2])
+            calls['conv_dgrad'] += 1
+        if need_dw or (need_dx and not native_dx) or ctx.has_bias:
+            # library path on NCHW-shaped channels_last views (zero-copy)
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), [w.shape[0]] if ctx.has_bias else None,
+                [stride, stride], [pad, pad], [dil, dil], False, [0, 0], 1, [need_dx and not native_dx, need_dw, ctx.has_bias])
+            fallbacks['conv_wgrad'] += 1
+            if need_dx and not native_dx:
+                dx = gx.permute(0, 2, 3, 1).contiguous()
+            if need_dw:
+                dw = gw.permute(0, 2, 3, 1).contiguous()
+            db = gb
+        return dx, dw, db, None, None, None, None
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
-    """Pointwise (1x1) convolutions on NHWC activations are GEMMs over the channel dimension: they reuse the tcgen05
-    GEMM (forward, dgrad with MN-major weights, wgrad with both operands MN-major) through ``linear``."""
+    """NCHW-shaped, channels_last-strided tensors in and out (what torch modules exchange); inside, NHWC views feed either the
+    tcgen05 GEMM (pointwise convs: in NHWC a 1x1 conv IS ``[N*H*W, Cin] x [Cout, Cin]^T``) or the implicit-GEMM conv kernel."""
     kh, kw = weight.shape[2], weight.shape[3]
     sh, sw = _pair(stride)
-    ph, pw = _pair(padding) if not isinstance(padding, str) else (0, 0)
-    ok = (kh == 1 and kw == 1 and groups == 1 and ph == 0 and pw == 0 and x.dim() == 4 and x.dtype == torch.bfloat16
-          and weight.dtype == torch.bfloat16 and weight.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0)
-    if not ok:
+    dh, dw_ = _pair(dilation)
+    if isinstance(padding, str):
         fallbacks['conv2d'] += 1
         return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
-    if sh != 1 or sw != 1:
-        x = x[:, :, ::sh, ::sw]
-    if not x.is_contiguous(memory_format=torch.channels_last):
-        x = x.contiguous(memory_format=torch.channels_last)
-    n, c, h, w = x.shape
-    x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)                  # zero-copy NHWC view
-    y2 = linear(x2, weight.reshape(weight.shape[0], c), bias, None)
-    calls['conv1x1_as_gemm'] += 1
-    return y2.view(n, h, w, weight.shape[0]).permute(0, 3, 1, 2)      # NCHW-shaped, channels_last-strided
+    ph, pw = _pair(padding)
+    cin, cout = weight.shape[1], weight.shape[0]
+    base_ok = (groups == 1 and x.dim() == 4 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+               and cin % 8 == 0 and cout % 8 == 0)
+    if base_ok and kh == 1 and kw == 1 and ph == 0 and pw == 0:
+        if sh != 1 or sw != 1:
+            x = x[:, :, ::sh, ::sw]
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        n, c, h, w = x.shape
+        x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)                  # zero-copy NHWC view
+        y2 = linear(x2, weight.reshape(cout, c), bias, None)
+        calls['conv1x1_as_gemm'] += 1
+        return y2.view(n, h, w, cout).permute(0, 3, 1, 2)                 # NCHW-shaped, channels_last-strided
+    if base_ok and sh == sw and ph == pw and dh == dw_ and kh == kw and sh in (1, 2) and IMPLICIT_GEMM_CONV:
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        w_ohwi = weight.permute(0, 2, 3, 1)
+        if not w_ohwi.is_contiguous():
+            w_ohwi = w_ohwi.contiguous()                                  # free when the module is channels_last
+        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), w_ohwi, bias, sh, ph, dh, False)
+        return y.permute(0, 3, 1, 2)
+    fallbacks['conv2d'] += 1
+    return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+
+IMPLICIT_GEMM_CONV = True

@@ -189,6 +189,29 @@ def test_cross_entropy(rows, V):
     assert _rel_err(logits.grad, lr.grad) < 2e-2
 
 
+# ----------------------------------------------------------------------------------------------- convolution
+@pytest.mark.parametrize('N,C,H,W,K,R,stride,pad', [(4, 64, 56, 56, 64, 3, 1, 1), (8, 128, 28, 28, 128, 3, 1, 1), (3, 256, 14, 14, 256, 3, 1, 1),
+                                                    (5, 512, 7, 7, 512, 3, 1, 1), (4, 128, 56, 56, 128, 3, 2, 1), (2, 48, 32, 32, 64, 5, 1, 2),
+                                                    (2, 64, 17, 17, 96, 3, 1, 0), (6, 64, 56, 56, 256, 1, 1, 0)])
+def test_conv2d_implicit_gemm(N, C, H, W, K, R, stride, pad):
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(13)
+    x = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = _rand(K, C, R, R, scale=0.05).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = ops.conv2d(x, w, None, stride, pad, 1, 1)
+    g = _rand(*y.shape).contiguous(memory_format=torch.channels_last)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, None, stride, pad)
+    yr.backward(g.float())
+    assert y.shape == yr.shape
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 2e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
+    assert native.calls['conv_fwd'] + native.calls['conv1x1_as_gemm'] > 0
+
+
 # ----------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize('B,S,heads,causal,padded', [(2, 128, 2, False, False), (8, 512, 12, False, True), (2, 384, 4, True, False),
                                                      (3, 200, 2, False, True), (2, 200, 2, True, True)])
