@@ -66,7 +66,7 @@ class Compute:
                  cluster_length: int = 1, recompute: bool = True, compute_dtype: Optional[torch.dtype] = None,
                  loss_filename: Optional[str] = 'losses.txt', is_last: bool = False, dp_group=None,
                  fused_optimizer: Optional[bool] = None, lr_scheduler=None, lr_scheduler_params: Optional[dict] = None,
-                 average_grads_over_dp: bool = False, use_cuda_graphs: bool = False):
+                 average_grads_over_dp: bool = False, use_cuda_graphs: bool = False, channels_last: bool = False):
         self.device = torch.device(device)
         self.model = model
         self.criterion = criterion
@@ -88,6 +88,7 @@ class Compute:
         self._fused = None
         self._average_grads = bool(average_grads_over_dp)
         self.use_graphs = bool(use_cuda_graphs)
+        self.channels_last = bool(channels_last)
         self.graph_warmup = 3
         self._graph = None
         self._graph_seen = 0
@@ -145,6 +146,8 @@ class Compute:
                     a = a.to(self.device, non_blocking=True)
                 if a.is_floating_point() and a.dtype != self.store.compute_dtype and a.dtype in (torch.float32, torch.float16, torch.bfloat16):
                     a = a.to(self.store.compute_dtype)
+                if self.channels_last and a.dim() == 4 and a.is_floating_point():
+                    a = a.contiguous(memory_format=torch.channels_last)
                 if need_grad and a.is_floating_point():
                     a.requires_grad_(True)
             prepared.append(a)

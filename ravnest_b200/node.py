@@ -73,6 +73,12 @@ class Node:
             model = load_submodel(os.path.join(self.template_path, 'submod.pt'))
         dtype = kwargs.get('dtype')
         model = model.to(device=self.device, dtype=dtype) if dtype is not None else model.to(self.device)
+        channels_last = kwargs.get('channels_last')
+        if channels_last is None:       # NHWC is the native layout of the conv kernels (and of cuDNN's tensor-core paths)
+            channels_last = self.device.type == 'cuda' and any(isinstance(m, torch.nn.Conv2d) for m in model.modules())
+        if channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        self.channels_last = bool(channels_last)
         self.model = model
         is_root = self.node_type in (NodeTypes.ROOT, NodeTypes.SOLO)
         in_t = load_pickle(os.path.join(self.template_path, '{}_input.pkl'.format(self.submod_file)))
@@ -134,7 +140,7 @@ class Node:
             dp_group=self.dp_group if self.dp_mode == 'gradient' else None,
             fused_optimizer=kwargs.get('fused_optimizer'), lr_scheduler=lr_scheduler,
             lr_scheduler_params=lr_scheduler_params or {}, average_grads_over_dp=self.dp_mode == 'gradient',
-            use_cuda_graphs=kwargs.get('use_cuda_graphs', self.device.type == 'cuda'))
+            use_cuda_graphs=kwargs.get('use_cuda_graphs', self.device.type == 'cuda'), channels_last=self.channels_last)
         self.optimizer = self.compute_session.optimizer
         self.lr_scheduler = self.compute_session.lr_scheduler
         self.comm_session = Communication(
