@@ -19,10 +19,10 @@ class BasicConv2d(nn.Module):
     def __init__(self, in_channels, out_channels, **kwargs):
         super().__init__()
         self.conv = rnn.Conv2d(in_channels, out_channels, bias=False, **kwargs)
-        self.bn = nn.BatchNorm2d(out_channels, eps=0.001)
+        self.bn = rnn.BatchNorm2d(out_channels, eps=0.001, relu=True)      # BN + ReLU in one kernel
 
     def forward(self, x):
-        return F.relu(self.bn(self.conv(x)), inplace=True)
+        return self.bn(self.conv(x))
 
 
 def _k(kernel, **kw):

@@ -12,37 +12,35 @@ from .. import nn as rnn
 
 
 class Bottleneck(nn.Module):
+    """conv1x1 -> BN+ReLU -> conv3x3 -> BN+ReLU -> conv1x1 -> BN + identity + ReLU; each "BN(+add)+ReLU" is ONE fused kernel
+    (rnn.BatchNorm2d).  Attribute / parameter names match torchvision so its checkpoints load."""
     expansion = 4
 
     def __init__(self, inplanes, planes, stride=1, downsample=False):
         super().__init__()
         out = planes * self.expansion
         self.conv1 = rnn.Conv2d(inplanes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = rnn.BatchNorm2d(planes, relu=True)
         self.conv2 = rnn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = rnn.BatchNorm2d(planes, relu=True)
         self.conv3 = rnn.Conv2d(planes, out, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(out)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn3 = rnn.BatchNorm2d(out, relu=True)           # relu(BN(conv3) + identity)
         self.downsample = None
         if downsample:
-            self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False), nn.BatchNorm2d(out))
+            self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False), rnn.BatchNorm2d(out))
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
-        y = self.bn3(self.conv3(y))
-        if self.downsample is not None:
-            x = self.downsample(x)
-        return self.relu(y + x)
+        y = self.bn1(self.conv1(x))
+        y = self.bn2(self.conv2(y))
+        identity = x if self.downsample is None else self.downsample(x)
+        return self.bn3(self.conv3(y), identity)
 
 
 class ResNet(nn.Module):
     def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, zero_init_residual=False):
         super().__init__()
         self.conv1 = rnn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
-        self.relu = nn.ReLU(inplace=True)
+        self.bn1 = rnn.BatchNorm2d(64, relu=True)
         self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
         inplanes = 64
         for i, (planes, blocks) in enumerate(zip((64, 128, 256, 512), layers)):
@@ -66,7 +64,7 @@ class ResNet(nn.Module):
                     nn.init.zeros_(m.bn3.weight)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(self.flatten(self.avgpool(x)))
 

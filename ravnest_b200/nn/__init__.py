@@ -98,6 +98,21 @@ class Conv2d(nn.Conv2d):
         return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
 
+class BatchNorm2d(nn.BatchNorm2d):
+    """``nn.BatchNorm2d`` (same parameters / buffers / state dict) with the ReLU and the residual add of the surrounding block
+    fused in: ``forward(x, residual=None)`` computes ``act(BN(x) + residual)``; ``relu=True`` selects the activation."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, relu=False, **kw):
+        super().__init__(num_features, eps=eps, momentum=momentum, **kw)
+        self.relu = relu
+
+    def forward(self, x, residual=None):
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        return ops.batch_norm_act(x, self.weight, self.bias, self.running_mean, self.running_var, residual, self.relu,
+                                  self.training or not self.track_running_stats, self.momentum if self.momentum is not None else 0.1, self.eps)
+
+
 class GELU(nn.Module):
     def __init__(self, approximate='none'):
         super().__init__()
@@ -107,4 +122,4 @@ class GELU(nn.Module):
         return F.gelu(x, approximate=self.approximate)
 
 
-__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'Conv2d', 'GELU']
+__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'Conv2d', 'BatchNorm2d', 'GELU']

@@ -143,6 +143,17 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 
+def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
+    """``relu(batch_norm(x) + residual)`` (the tail of every ResNet / Inception conv block) in one pass over the activation."""
+    if _native(x, weight) and x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        from . import native
+        return native.batch_norm_act(x, weight, bias, running_mean, running_var, residual, relu, training, momentum, eps)
+    y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
 def native_ops_loaded():
     """Names of native kernels that have actually been launched in this process."""
     try:
@@ -152,6 +163,6 @@ def native_ops_loaded():
         return {}
 
 
-__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
            'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
            'reference_cross_entropy']

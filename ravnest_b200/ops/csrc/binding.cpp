@@ -29,6 +29,13 @@ int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const flo
                       cudaStream_t stream);
 int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho, int Wo,
                      int Cout, int R, int S, int stride, int pad, int dil, int transposed, int num_sms, cudaStream_t stream);
+int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
+                   int stride, int pad, int dil, int num_sms, cudaStream_t stream);
+int rvn_batchnorm_forward(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps, float momentum, int relu,
+                          int training, int num_sms, cudaStream_t stream);
+int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* invstd,
+                           float* sums, void* dx, void* dres, long long M, int C, int relu, int num_sms, cudaStream_t stream);
 int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
 }
 
@@ -317,6 +324,64 @@ torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c1
   return y;
 }
 
+// dy [N,Ho,Wo,Cout], x [N,H,W,Cin] (NHWC bf16) -> dW [Cout,R,S,Cin] fp32
+torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t dil) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dy.scalar_type() == torch::kBFloat16 && x.scalar_type() == torch::kBFloat16,
+              "conv_wgrad_nhwc expects contiguous bf16 NHWC tensors");
+  const int N = x.size(0), H = x.size(1), W = x.size(2), Cin = x.size(3);
+  const int Ho = dy.size(1), Wo = dy.size(2), Cout = dy.size(3);
+  TORCH_CHECK(Cin % 8 == 0 && Cout % 8 == 0, "channel counts must be multiples of 8");
+  auto dw = torch::zeros({Cout, R, S, Cin}, x.options().dtype(torch::kFloat32));
+  check(rvn_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), N, H, W, Cin, Ho, Wo, Cout, static_cast<int>(R), static_cast<int>(S),
+                       static_cast<int>(stride), static_cast<int>(pad), static_cast<int>(dil), sm_count(), cur_stream()),
+        "conv_wgrad");
+  return dw;
+}
+
+// x: [..., C] bf16 contiguous (NHWC flattened); gamma/beta/mean/invstd fp32 [C].  training: batch statistics are computed (mean, invstd
+// returned); eval: the given mean / invstd are applied.  Returns {y, mean, invstd}
+std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::optional<torch::Tensor>& res, const torch::Tensor& gamma,
+                                         const torch::Tensor& beta, const c10::optional<torch::Tensor>& mean_in,
+                                         const c10::optional<torch::Tensor>& invstd_in, double eps, bool relu, bool training) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kBFloat16, "batchnorm expects contiguous bf16 NHWC input");
+  TORCH_CHECK(gamma.scalar_type() == torch::kFloat32 && beta.scalar_type() == torch::kFloat32, "gamma / beta must be fp32");
+  const int C = x.size(-1);
+  const long long M = x.numel() / C;
+  auto f32 = x.options().dtype(torch::kFloat32);
+  auto y = torch::empty_like(x);
+  torch::Tensor mean = training ? torch::empty({C}, f32) : mean_in.value();
+  torch::Tensor invstd = training ? torch::empty({C}, f32) : invstd_in.value();
+  auto sums = torch::empty({2 * static_cast<int64_t>(C)}, f32);
+  const void* res_ptr = (res.has_value() && res->defined()) ? res->data_ptr() : nullptr;
+  if (res_ptr) TORCH_CHECK(res->is_contiguous() && res->numel() == x.numel(), "residual must match x");
+  check(rvn_batchnorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr<float>(), beta.data_ptr<float>(), nullptr, nullptr, mean.data_ptr<float>(),
+                              invstd.data_ptr<float>(), sums.data_ptr<float>(), y.data_ptr(), M, C, static_cast<float>(eps), 0.f, relu,
+                              training, sm_count(), cur_stream()),
+        "batchnorm_fwd");
+  return {y, mean, invstd};
+}
+
+// returns {dx, dres (dz, defined only when want_dres), dgamma fp32, dbeta fp32}
+std::vector<torch::Tensor> batchnorm_bwd(const torch::Tensor& dy, const c10::optional<torch::Tensor>& y, const torch::Tensor& x,
+                                         const torch::Tensor& gamma, const torch::Tensor& mean, const torch::Tensor& invstd, bool relu,
+                                         bool want_dres) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous(), "batchnorm_bwd expects contiguous tensors");
+  const int C = x.size(-1);
+  const long long M = x.numel() / C;
+  auto sums = torch::empty({2 * static_cast<int64_t>(C)}, x.options().dtype(torch::kFloat32));
+  auto dx = torch::empty_like(x);
+  torch::Tensor dres;
+  if (want_dres) dres = torch::empty_like(x);
+  const void* y_ptr = relu ? y.value().data_ptr() : nullptr;
+  check(rvn_batchnorm_backward(dy.data_ptr(), y_ptr, x.data_ptr(), gamma.data_ptr<float>(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                               sums.data_ptr<float>(), dx.data_ptr(), want_dres ? dres.data_ptr() : nullptr, M, C, relu, sm_count(), cur_stream()),
+        "batchnorm_bwd");
+  return {dx, dres, sums.narrow(0, C, C), sums.narrow(0, 0, C)};
+}
+
 // ---------------------------------------------------------------------------------------------- fused optimizers
 PeerPtrs make_peers(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank) {
   PeerPtrs pp{};
@@ -391,6 +456,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("column_sum", &column_sum);
   m.def("act_bwd", &act_bwd);
   m.def("conv_nhwc", &conv_nhwc);
+  m.def("batchnorm_fwd", &batchnorm_fwd);
+  m.def("batchnorm_bwd", &batchnorm_bwd);
+  m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc);
   m.def("fmha_fwd", &fmha_fwd);
   m.def("fmha_bwd", &fmha_bwd);
   m.def("fused_update", &fused_update);

@@ -405,3 +405,213 @@ extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const voi
   if (wide) return rvn::conv_launch<256, false>(x, w, y, p, num_sms, stream);
   return rvn::conv_launch<128, false>(x, w, y, p, num_sms, stream);
 }
+
+// ================================================================================================ weight gradient
+//   dW[co, (r,s), ci] = sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*stride + r*dil - pad, wo*stride + s*dil - pad, ci]
+// GEMM with the PIXELS as the reduction dimension: A = dy patch (128 pixels x 128 co, MN-major), B = the tap-shifted x patch
+// (128 pixels x BN ci, MN-major) — both are the 4-D TMA patch loads of the forward kernel (zero fill = padding, and
+// zero-filled dy rows outside the image contribute nothing).  One CTA owns an output tile (co block, tap, ci block) and a
+// slice of the pixel patches (split-K: early layers have only a handful of output tiles); partial sums are added into
+// an fp32 [Cout, R*S, Cin] buffer with red.global.add.f32.
+namespace rvn {
+
+constexpr int WG_PIX = 128;                     // pixels per K block (power-of-two patch, zero-filled by TMA)
+constexpr int WG_A_BYTES = 2 * WG_PIX * 128;    // 128 co = two 64-wide MN atoms columns
+constexpr int WG_THREADS = 192;                 // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+
+struct WgradParams {
+  int N, H, W, Cin, Ho, Wo, Cout;
+  int R, S, stride, pad, dil;
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n;
+  int co_blocks, ci_blocks, splits, patches_per_split;
+  float* dw;                                    // [Cout, R*S, Cin] fp32, zero-initialised by the caller
+};
+
+template <int BN>
+struct WgradSmem {
+  static constexpr int B_BYTES = (BN / 64) * WG_PIX * 128;
+  static constexpr int STAGE_BYTES = WG_A_BYTES + B_BYTES;
+  static constexpr int STAGES = 3;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+rvn_conv_wgrad_tcgen05(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
+  using L = WgradSmem<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t IDESC = make_idesc_bf16(128, BN, true, true);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* done_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  // tile decode: blockIdx.x = ((split * co_blocks + co_blk) * RS + tap) * ci_blocks + ci_blk
+  int t = blockIdx.x;
+  const int ci_blk = t % p.ci_blocks; t /= p.ci_blocks;
+  const int tap = t % (p.R * p.S); t /= (p.R * p.S);
+  const int co_blk = t % p.co_blocks;
+  const int split = t / p.co_blocks;
+  const int n_patches = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int patch0 = split * p.patches_per_split;
+  const int patch1 = min(n_patches, patch0 + p.patches_per_split);
+  const int r = tap / p.S, s = tap % p.S;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = patch0; pt < patch1; ++pt) {
+        const int wo0 = (pt % p.tiles_w) * p.TW;
+        const int ho0 = ((pt / p.tiles_w) % p.tiles_h) * p.TH;
+        const int n0 = (pt / (p.tiles_w * p.tiles_h)) * p.TN;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + WG_A_BYTES;
+        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_4d(sa + j * (WG_PIX * 128), &map_dy, &full_bar[stage], co_blk * 128 + j * 64, wo0, ho0, n0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(sb + j * (WG_PIX * 128), &map_x, &full_bar[stage], ci_blk * BN + j * 64, wo0 * p.stride + s * p.dil - p.pad,
+                      ho0 * p.stride + r * p.dil - p.pad, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = patch0; pt < patch1; ++pt) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + WG_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_PIX / 16; ++k)
+          umma_bf16(tmem_d, make_smem_desc_sw128(a_addr + k * 2048, WG_PIX * 128, 1024),
+                    make_smem_desc_sw128(b_addr + k * 2048, WG_PIX * 128, 1024), IDESC, (pt != patch0 || k != 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (pt == patch1 - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (patch1 > patch0) {
+    // epilogue: thread == output-channel row; fp32 atomics into dW[co, tap, ci]
+    const int ewarp = (warp - 2) & 3;                     // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane_id();
+    (void)ewarp;
+    mbar_wait(done_bar, 0);
+    tcgen05_fence_after();
+    const int co = co_blk * 128 + row;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (co < p.Cout) {
+        float* dst = p.dw + (static_cast<size_t>(co) * p.R * p.S + tap) * p.Cin + ci_blk * BN + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ci_blk * BN + c * 32 + j < p.Cin) atomicAdd(dst + j, __uint_as_float(v[j]));
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+}
+
+// power-of-two patch with TW*TH*TN == 128 (zero-filled beyond the image) maximising useful pixels
+static void pick_patch_pow2(int Wo, int Ho, int N, int& TW, int& TH, int& TN) {
+  double best = -1.0;
+  for (int tw = 1; tw <= 128; tw *= 2)
+    for (int th = 1; tw * th <= 128; th *= 2) {
+      const int tn = 128 / (tw * th);
+      const double tiles = static_cast<double>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+      const double eff = static_cast<double>(Wo) * Ho * N / (tiles * 128.0);
+      if (eff > best + 1e-9) { best = eff; TW = tw; TH = th; TN = tn; }
+    }
+}
+
+template <int BN>
+static int wgrad_launch(const void* dy, const void* x, WgradParams p, int num_sms, cudaStream_t stream) {
+  using L = WgradSmem<BN>;
+  pick_patch_pow2(p.Wo, p.Ho, p.N, p.TW, p.TH, p.TN);
+  p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
+  p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
+  p.tiles_n = (p.N + p.TN - 1) / p.TN;
+  p.co_blocks = (p.Cout + 127) / 128;
+  p.ci_blocks = (p.Cin + BN - 1) / BN;
+  const int base_tiles = p.co_blocks * p.R * p.S * p.ci_blocks;
+  const int n_patches = p.tiles_w * p.tiles_h * p.tiles_n;
+  int splits = (2 * num_sms + base_tiles - 1) / base_tiles;
+  if (splits > n_patches) splits = n_patches;
+  if (splits < 1) splits = 1;
+  p.patches_per_split = (n_patches + splits - 1) / splits;
+  p.splits = (n_patches + p.patches_per_split - 1) / p.patches_per_split;
+  CUtensorMap mdy, mx;
+  int e = 0;
+  {
+    const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
+    const uint64_t st[3] = {(uint64_t)p.Cout, (uint64_t)p.Wo * p.Cout, (uint64_t)p.Ho * p.Wo * p.Cout};
+    const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    const uint32_t es[4] = {1u, 1u, 1u, 1u};
+    e |= make_map_nd(&mdy, dy, 4, dims, st, box, es);
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+    const uint64_t st[3] = {(uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    const uint32_t box[4] = {64u, (uint32_t)((p.TW - 1) * p.stride + 1), (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TN};
+    const uint32_t es[4] = {1u, (uint32_t)p.stride, (uint32_t)p.stride, 1u};
+    e |= make_map_nd(&mx, x, 4, dims, st, box, es);
+  }
+  if (e != 0) return 1000 + e;
+  auto kern = rvn_conv_wgrad_tcgen05<BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return 2000;
+    configured = true;
+  }
+  kern<<<base_tiles * p.splits, WG_THREADS, L::TOTAL, stream>>>(mdy, mx, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3000;
+}
+
+}  // namespace rvn
+
+// dy [N,Ho,Wo,Cout], x [N,H,W,Cin] bf16 NHWC; dw [Cout,R,S,Cin] fp32 zero-initialised (accumulated into)
+extern "C" int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R,
+                              int S, int stride, int pad, int dil, int num_sms, cudaStream_t stream) {
+  rvn::WgradParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
+  p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.dw = dw;
+  if (Cin > 64) return rvn::wgrad_launch<128>(dy, x, p, num_sms, stream);
+  return rvn::wgrad_launch<64>(dy, x, p, num_sms, stream);
+}

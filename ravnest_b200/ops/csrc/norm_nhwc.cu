@@ -1,0 +1,264 @@
+// K7: training-mode BatchNorm on NHWC bf16 activations, fused with the ReLU and the residual add that follow it in
+// ResNet / Inception blocks:      y = relu( (x - mean) * invstd * gamma + beta  (+ residual) )
+//
+// Measured motivation (profiles/resnet50_step_baseline_r1.txt): in the stock bf16 channels_last ResNet-50 step ATen's four
+// BatchNorm kernels take 12.4 ms of 24 ms while all convolutions together take ~3.5 ms.  These kernels are pure streams:
+// the activation is viewed as a flat array of 16-byte vectors and the launch is shaped so that every thread always lands on
+// the SAME 8-channel group (total thread count is a multiple of C/8) — per-channel parameters and partial sums live in
+// registers, loads are perfectly coalesced, no index arithmetic per element.
+//   forward : rvn_bn_stats (sum, sum of squares) -> rvn_bn_finalize (mean, invstd, running stats) -> rvn_bn_apply
+//   backward: rvn_bn_bwd_reduce (sum dz, sum dz*xhat with dz = dy * relu_mask) -> rvn_bn_bwd_apply (dx, dz for the skip branch)
+// Reference call sites: nn.BatchNorm2d in torchvision resnet50 / models.py BasicConv2d (models.py:383-392), F.relu, `out += identity`.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rvn {
+
+struct v8 {
+  uint4 raw;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void from_float(const float (&f)[8]) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+
+// sums[0..C) += sum_r x[r,c];  sums[C..2C) += sum_r x[r,c]^2      (total threads % (C/8) == 0)
+__global__ void __launch_bounds__(256) rvn_bn_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, size_t nvec, int C) {
+  extern __shared__ float sh[];                     // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(tid % (C / 8)) * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  size_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {      // two independent loads in flight
+    v8 a, b;
+    float fa[8], fb[8];
+    a.load(x + i * 8);
+    b.load(x + (i + stride) * 8);
+    a.to_float(fa);
+    b.to_float(fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += fa[j] + fb[j]; q[j] += fa[j] * fa[j] + fb[j] * fb[j]; }
+  }
+  if (i < nvec) {
+    v8 a;
+    float fa[8];
+    a.load(x + i * 8);
+    a.to_float(fa);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += fa[j]; q[j] += fa[j] * fa[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[c0 + j], s[j]);
+    atomicAdd(&sh[C + c0 + j], q[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(&sums[c], sh[c]);
+}
+
+// mean / invstd from the sums; running statistics updated like torch (unbiased variance, momentum)
+__global__ void rvn_bn_finalize(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ invstd,
+                                float* __restrict__ running_mean, float* __restrict__ running_var, float count, float eps,
+                                float momentum, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sums[c] / count;
+  const float var = fmaxf(sums[C + c] / count - m * m, 0.f);
+  mean[c] = m;
+  invstd[c] = rsqrtf(var + eps);
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+  }
+}
+
+// y = act((x - mean) * invstd * gamma + beta + residual)
+__global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                    __nv_bfloat16* __restrict__ y, size_t nvec, int C, int relu) {
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(tid % (C / 8)) * 8;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = gamma[c0 + j] * invstd[c0 + j];
+    sf[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+  }
+  for (size_t i = tid; i < nvec; i += stride) {
+    v8 a, o;
+    float f[8];
+    a.load(x + i * 8);
+    a.to_float(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sf[j]);
+    if (res != nullptr) {
+      v8 r;
+      float rf[8];
+      r.load(res + i * 8);
+      r.to_float(rf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += rf[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    o.from_float(f);
+    o.store(y + i * 8);
+  }
+}
+
+// sums[0..C) += sum dz ; sums[C..2C) += sum dz * xhat      with dz = dy * (y > 0) when relu
+__global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                         const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                                         const float* __restrict__ invstd, float* __restrict__ sums, size_t nvec, int C,
+                                                         int relu) {
+  extern __shared__ float sh[];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(tid % (C / 8)) * 8;
+  float mu[8], is[8], s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; s[j] = 0.f; q[j] = 0.f; }
+  for (size_t i = tid; i < nvec; i += stride) {
+    v8 a, b;
+    float g[8], xv[8];
+    a.load(dy + i * 8);
+    b.load(x + i * 8);
+    a.to_float(g);
+    b.to_float(xv);
+    if (relu) {
+      v8 c;
+      float yv[8];
+      c.load(y + i * 8);
+      c.to_float(yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += g[j];
+      q[j] += g[j] * (xv[j] - mu[j]) * is[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[c0 + j], s[j]);
+    atomicAdd(&sh[C + c0 + j], q[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(&sums[c], sh[c]);
+}
+
+// dx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dres = dz (gradient of the fused residual branch)
+__global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                        const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
+                                                        __nv_bfloat16* __restrict__ dres, size_t nvec, int C, float count, int relu) {
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(tid % (C / 8)) * 8;
+  float mu[8], is[8], gi[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[c0 + j];
+    is[j] = invstd[c0 + j];
+    gi[j] = gamma[c0 + j] * is[j];
+    m1[j] = sums[c0 + j] / count;
+    m2[j] = sums[C + c0 + j] / count;
+  }
+  for (size_t i = tid; i < nvec; i += stride) {
+    v8 a, b, o;
+    float g[8], xv[8];
+    a.load(dy + i * 8);
+    b.load(x + i * 8);
+    a.to_float(g);
+    b.to_float(xv);
+    if (relu) {
+      v8 c;
+      float yv[8];
+      c.load(y + i * 8);
+      c.to_float(yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    }
+    if (dres != nullptr) {
+      o.from_float(g);
+      o.store(dres + i * 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = gi[j] * (g[j] - m1[j] - (xv[j] - mu[j]) * is[j] * m2[j]);
+    o.from_float(g);
+    o.store(dx + i * 8);
+  }
+}
+
+}  // namespace rvn
+
+// grid such that (grid * 256) % (C/8) == 0 and there are ~`waves` x num_sms CTAs
+static int bn_grid(size_t nvec, int C, int num_sms, int waves) {
+  const int groups = C / 8;
+  int g = 1;                                      // smallest grid multiple that keeps threads pinned to one channel group
+  while ((static_cast<long long>(g) * 256) % groups != 0) ++g;
+  long long want = static_cast<long long>(num_sms) * waves;
+  const long long max_useful = static_cast<long long>((nvec + 255) / 256);
+  if (want > max_useful) want = max_useful;
+  long long grid = (want / g) * g;
+  if (grid < g) grid = g;
+  return static_cast<int>(grid);
+}
+
+extern "C" int rvn_batchnorm_forward(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
+                                     float* running_var, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
+                                     float momentum, int relu, int training, int num_sms, cudaStream_t stream) {
+  if (C % 8 != 0 || C > 4096) return -2;
+  const size_t nvec = static_cast<size_t>(M) * C / 8;
+  using T = const __nv_bfloat16*;
+  if (training) {
+    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream);
+    rvn::rvn_bn_stats<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)x, sums, nvec, C);
+    rvn::rvn_bn_finalize<<<(C + 127) / 128, 128, 0, stream>>>(sums, mean, invstd, running_mean, running_var, static_cast<float>(M), eps,
+                                                               momentum, C);
+  }
+  rvn::rvn_bn_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)x, (T)res, gamma, beta, mean, invstd, (__nv_bfloat16*)y, nvec, C,
+                                                                      relu);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// sums (2*C fp32) holds {dbeta = sum dz, dgamma = sum dz*xhat} on return
+extern "C" int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const float* gamma, const float* mean,
+                                      const float* invstd, float* sums, void* dx, void* dres, long long M, int C, int relu, int num_sms,
+                                      cudaStream_t stream) {
+  if (C % 8 != 0 || C > 4096) return -2;
+  const size_t nvec = static_cast<size_t>(M) * C / 8;
+  using T = const __nv_bfloat16*;
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream);
+  rvn::rvn_bn_bwd_reduce<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)dy, (T)y, (T)x, mean, invstd, sums, nvec, C,
+                                                                                            relu);
+  rvn::rvn_bn_bwd_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)dy, (T)y, (T)x, gamma, mean, invstd, sums, (__nv_bfloat16*)dx,
+                                                                          (__nv_bfloat16*)dres, nvec, C, static_cast<float>(M), relu);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}

@@ -352,6 +352,10 @@ class _ConvNHWC(torch.autograd.Function):
         if native_dx:
             dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2])
             calls['conv_dgrad'] += 1
+        if need_dw and NATIVE_CONV_WGRAD:
+            dw = C().conv_wgrad_nhwc(dy, x, w.shape[1], w.shape[2], stride, pad, dil).to(w.dtype)
+            calls['conv_wgrad'] += 1
+            need_dw = False
         if need_dw or (need_dx and not native_dx) or ctx.has_bias:
             # library path on NCHW-shaped channels_last views (zero-copy)
             gx, gw, gb = torch.ops.aten.convolution_backward(
@@ -406,3 +410,53 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
 
 
 IMPLICIT_GEMM_CONV = True
+NATIVE_CONV_WGRAD = True
+
+
+class _BatchNormAct(torch.autograd.Function):
+    """y = relu(BN(x) + residual) on NHWC activations (ops/csrc/norm_nhwc.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, relu, eps):
+        gamma, beta = weight.float(), bias.float()
+        y, mean, invstd = C().batchnorm_fwd(x, residual, gamma, beta, None, None, eps, relu, True)
+        calls['batchnorm_fwd'] += 1
+        ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, invstd)
+        ctx.mark_non_differentiable(mean, invstd)
+        return y, mean, invstd
+
+    @staticmethod
+    def backward(ctx, dy, _dm, _di):
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = C().batchnorm_bwd(dy.contiguous(), y, x, gamma, mean, invstd, ctx.relu, ctx.has_res and ctx.relu)
+        calls['batchnorm_bwd'] += 1
+        if ctx.has_res and not ctx.relu:
+            dres = dy
+        return dx, dgamma.to(torch.bfloat16), dbeta.to(torch.bfloat16), (dres if ctx.has_res else None), None, None
+
+
+def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
+    """x / residual / result: NCHW-shaped channels_last bf16 tensors.  Training mode updates the running statistics."""
+    n, c, h, w = x.shape
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    x2 = x.permute(0, 2, 3, 1)
+    r2 = None
+    if residual is not None:
+        if not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        r2 = residual.permute(0, 2, 3, 1)
+    if training:
+        y2, mean, invstd = _BatchNormAct.apply(x2, weight, bias, r2, relu, eps)
+        if running_mean is not None:
+            with torch.no_grad():
+                count = x.numel() // c
+                var = (1.0 / (invstd * invstd) - eps).clamp_min_(0.0)
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_((var * (count / max(count - 1, 1))).to(running_var.dtype), alpha=momentum)
+    else:
+        invstd = torch.rsqrt(running_var.float() + eps)
+        y2 = C().batchnorm_fwd(x2, r2, weight.float(), bias.float(), running_mean.float(), invstd, eps, relu, False)[0]
+        calls['batchnorm_eval'] += 1
+    return y2.permute(0, 3, 1, 2)

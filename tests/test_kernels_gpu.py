@@ -212,6 +212,40 @@ def test_conv2d_implicit_gemm(N, C, H, W, K, R, stride, pad):
     assert native.calls['conv_fwd'] + native.calls['conv1x1_as_gemm'] > 0
 
 
+@pytest.mark.parametrize('N,C,H,W', [(8, 64, 56, 56), (4, 256, 28, 28), (3, 2048, 7, 7), (2, 48, 17, 17)])
+@pytest.mark.parametrize('relu,with_res', [(True, False), (True, True), (False, False)])
+def test_batchnorm_relu_add(N, C, H, W, relu, with_res):
+    from ravnest_b200 import ops
+    torch.manual_seed(14)
+    x = (_rand(N, C, H, W) * 2 + 0.5).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    res = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last).requires_grad_(True) if with_res else None
+    g = (1 + 0.2 * torch.randn(C, device=DEV)).bfloat16().requires_grad_(True)
+    b = _rand(C, scale=0.2).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=DEV, dtype=torch.bfloat16), torch.ones(C, device=DEV, dtype=torch.bfloat16)
+    y = ops.batch_norm_act(x, g, b, rm, rv, res, relu, True, 0.1, 1e-5)
+    gy = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    xr, gr, br = (t.detach().float().requires_grad_(True) for t in (x, g, b))
+    rr = res.detach().float().requires_grad_(True) if with_res else None
+    rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    yr = torch.nn.functional.batch_norm(xr, rm2, rv2, gr, br, True, 0.1, 1e-5)
+    if with_res:
+        yr = yr + rr
+    if relu:
+        yr = torch.relu(yr)
+    yr.backward(gy.float())
+    assert _rel_err(y, yr) < 1.5e-2
+    assert _rel_err(x.grad, xr.grad) < 3e-2
+    assert _rel_err(g.grad, gr.grad) < 3e-2 and _rel_err(b.grad, br.grad) < 3e-2
+    if with_res:
+        assert _rel_err(res.grad, rr.grad) < 2e-2
+    assert _rel_err(rm, rm2) < 2e-2 and _rel_err(rv, rv2) < 2e-2
+    # eval mode uses the running statistics
+    ye = ops.batch_norm_act(x.detach(), g.detach(), b.detach(), rm, rv, None, relu, False, 0.1, 1e-5)
+    yer = torch.nn.functional.batch_norm(x.detach().float(), rm.float(), rv.float(), g.detach().float(), b.detach().float(), False, 0.1, 1e-5)
+    assert _rel_err(ye, torch.relu(yer) if relu else yer) < 1.5e-2
+
+
 # ----------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize('B,S,heads,causal,padded', [(2, 128, 2, False, False), (8, 512, 12, False, True), (2, 384, 4, True, False),
                                                      (3, 200, 2, False, True), (2, 200, 2, True, True)])

@@ -41,13 +41,31 @@ def test_cnn_split_matches_reference_boundaries():
 
 
 def test_resnet50_split_matches_survey_table():
-    m = models.resnet50(num_classes=200).eval()
+    """Split policy parity on the reference's own model (torchvision resnet50, cluster_formation.py:23-25)."""
+    import torchvision
+    m = torchvision.models.resnet50(num_classes=200).eval()
     x = torch.rand(2, 3, 224, 224)
     r = split_model(m, [0.2, 0.2, 0.2, 0.4], (x,))
     assert [_n(s.module) for s in r.stages] == [4337216, 4731392, 3412992, 11436232]
     # cuts land mid-bottleneck: multi-tensor boundaries, one tensor skips a stage
     assert r.stages[1].input_template() == {0: {'submod_0': 0}, 1: {'submod_0': 1}}
     assert r.stages[1].output_template() == {0: {'target': ['submod_2']}, 1: {'target': ['submod_3']}}
+    for s in r.stages:
+        s.module.eval()
+    assert torch.allclose(r.run_local(x), m(x), atol=1e-5)
+
+
+def test_fused_resnet50_splits_and_matches_torchvision():
+    """Our ResNet-50 (fused BN+ReLU+add blocks) keeps torchvision's parameter names and numerics and splits 4 ways."""
+    import torchvision
+    m = models.resnet50(num_classes=200).eval()
+    t = torchvision.models.resnet50(num_classes=200).eval()
+    assert not t.load_state_dict(m.state_dict()).missing_keys
+    x = torch.rand(2, 3, 96, 96)
+    assert torch.allclose(m(x), t(x), atol=1e-5)
+    r = split_model(m, [0.2, 0.2, 0.2, 0.4], (x,))
+    sizes = [_n(s.module) for s in r.stages]
+    assert len(sizes) == 4 and sum(sizes) == 23917832 and sizes[0] == 4337216
     for s in r.stages:
         s.module.eval()
     assert torch.allclose(r.run_local(x), m(x), atol=1e-5)
