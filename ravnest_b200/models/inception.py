@@ -50,15 +50,17 @@ class Mixed(nn.Module):
                 self.add_module(name, BasicConv2d(ch, out_ch, **kw))
                 fork_names.append(name)
             self.program.append((pool, names, fork_names))
+        self.avg3 = rnn.AvgPool2d(3, stride=1, padding=1)
+        self.max3 = rnn.MaxPool2d(3, stride=2)
 
     def forward(self, x):
         outs = []
         for pool, names, fork_names in self.program:
             y = x
             if pool == 'avg':
-                y = F.avg_pool2d(y, kernel_size=3, stride=1, padding=1)
+                y = self.avg3(y)
             elif pool == 'max':
-                y = F.max_pool2d(y, kernel_size=3, stride=2)
+                y = self.max3(y)
             for n in names:
                 y = getattr(self, n)(y)
             if fork_names:

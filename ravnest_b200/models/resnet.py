@@ -41,7 +41,7 @@ class ResNet(nn.Module):
         super().__init__()
         self.conv1 = rnn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = rnn.BatchNorm2d(64, relu=True)
-        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.maxpool = rnn.MaxPool2d(3, stride=2, padding=1)
         inplanes = 64
         for i, (planes, blocks) in enumerate(zip((64, 128, 256, 512), layers)):
             stride = 1 if i == 0 else 2

@@ -113,6 +113,20 @@ class BatchNorm2d(nn.BatchNorm2d):
                                   self.training or not self.track_running_stats, self.momentum if self.momentum is not None else 0.1, self.eps)
 
 
+class MaxPool2d(nn.MaxPool2d):
+    def forward(self, x):
+        if self.dilation not in (1, (1, 1)) or self.ceil_mode or self.return_indices:
+            return super().forward(x)
+        return ops.max_pool2d(x, self.kernel_size, self.stride, self.padding)
+
+
+class AvgPool2d(nn.AvgPool2d):
+    def forward(self, x):
+        if self.ceil_mode or not self.count_include_pad or self.divisor_override is not None:
+            return super().forward(x)
+        return ops.avg_pool2d(x, self.kernel_size, self.stride, self.padding)
+
+
 class GELU(nn.Module):
     def __init__(self, approximate='none'):
         super().__init__()
@@ -122,4 +136,4 @@ class GELU(nn.Module):
         return F.gelu(x, approximate=self.approximate)
 
 
-__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'Conv2d', 'BatchNorm2d', 'GELU']
+__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'Conv2d', 'BatchNorm2d', 'MaxPool2d', 'AvgPool2d', 'GELU']

@@ -154,6 +154,28 @@ def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, re
     return F.relu(y) if relu else y
 
 
+def _sq(v):
+    return v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else None)
+
+
+def max_pool2d(x, kernel_size, stride=None, padding=0):
+    stride = kernel_size if stride is None else stride
+    k, s, p = _sq(kernel_size), _sq(stride), _sq(padding)
+    if _native(x) and None not in (k, s, p) and x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and k <= 15:
+        from . import native
+        return native.pool2d(x, k, s, p, True)
+    return F.max_pool2d(x, kernel_size, stride, padding)
+
+
+def avg_pool2d(x, kernel_size, stride=None, padding=0):
+    stride = kernel_size if stride is None else stride
+    k, s, p = _sq(kernel_size), _sq(stride), _sq(padding)
+    if _native(x) and None not in (k, s, p) and x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and k <= 15:
+        from . import native
+        return native.pool2d(x, k, s, p, False)
+    return F.avg_pool2d(x, kernel_size, stride, padding)
+
+
 def native_ops_loaded():
     """Names of native kernels that have actually been launched in this process."""
     try:
@@ -163,6 +185,6 @@ def native_ops_loaded():
         return {}
 
 
-__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'max_pool2d', 'avg_pool2d', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
            'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
            'reference_cross_entropy']

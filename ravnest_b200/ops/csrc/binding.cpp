@@ -36,6 +36,10 @@ int rvn_batchnorm_forward(const void* x, const void* res, const float* gamma, co
                           int training, int num_sms, cudaStream_t stream);
 int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* invstd,
                            float* sums, void* dx, void* dres, long long M, int C, int relu, int num_sms, cudaStream_t stream);
+int rvn_pool_forward(const void* x, void* y, void* arg, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, int is_max,
+                     int num_sms, cudaStream_t stream);
+int rvn_pool_backward(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
+                      int is_max, int num_sms, cudaStream_t stream);
 int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
 }
 
@@ -382,6 +386,33 @@ std::vector<torch::Tensor> batchnorm_bwd(const torch::Tensor& dy, const c10::opt
   return {dx, dres, sums.narrow(0, C, C), sums.narrow(0, 0, C)};
 }
 
+// x [N,H,W,C] bf16 NHWC -> {y [N,Ho,Wo,C], argmax (uint8, max pooling only)}
+std::vector<torch::Tensor> pool_fwd(const torch::Tensor& x, int64_t k, int64_t stride, int64_t pad, bool is_max) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.dim() == 4 && x.scalar_type() == torch::kBFloat16 && x.size(3) % 8 == 0, "pool expects NHWC bf16, C % 8 == 0");
+  const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  auto y = torch::empty({N, Ho, Wo, C}, x.options());
+  torch::Tensor arg = is_max ? torch::empty({N, Ho, Wo, C}, x.options().dtype(torch::kUInt8)) : torch::Tensor();
+  check(rvn_pool_forward(x.data_ptr(), y.data_ptr(), is_max ? arg.data_ptr() : nullptr, N, H, W, C, Ho, Wo, static_cast<int>(k),
+                         static_cast<int>(stride), static_cast<int>(pad), is_max, sm_count(), cur_stream()),
+        "pool_fwd");
+  if (is_max) return {y, arg};
+  return {y};
+}
+
+torch::Tensor pool_bwd(const torch::Tensor& dy, const c10::optional<torch::Tensor>& arg, int64_t H, int64_t W, int64_t k, int64_t stride,
+                       int64_t pad, bool is_max) {
+  c10::cuda::CUDAGuard guard(dy.device());
+  TORCH_CHECK(dy.is_contiguous() && dy.dim() == 4, "pool_bwd expects contiguous NHWC dy");
+  const int N = dy.size(0), Ho = dy.size(1), Wo = dy.size(2), C = dy.size(3);
+  auto dx = torch::empty({N, H, W, C}, dy.options());
+  check(rvn_pool_backward(dy.data_ptr(), is_max ? arg.value().data_ptr() : nullptr, dx.data_ptr(), N, static_cast<int>(H), static_cast<int>(W), C,
+                          Ho, Wo, static_cast<int>(k), static_cast<int>(stride), static_cast<int>(pad), is_max, sm_count(), cur_stream()),
+        "pool_bwd");
+  return dx;
+}
+
 // ---------------------------------------------------------------------------------------------- fused optimizers
 PeerPtrs make_peers(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank) {
   PeerPtrs pp{};
@@ -456,6 +487,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("column_sum", &column_sum);
   m.def("act_bwd", &act_bwd);
   m.def("conv_nhwc", &conv_nhwc);
+  m.def("pool_fwd", &pool_fwd);
+  m.def("pool_bwd", &pool_bwd);
   m.def("batchnorm_fwd", &batchnorm_fwd);
   m.def("batchnorm_bwd", &batchnorm_bwd);
   m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc);

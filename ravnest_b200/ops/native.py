@@ -460,3 +460,28 @@ def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, re
         y2 = C().batchnorm_fwd(x2, r2, weight.float(), bias.float(), running_mean.float(), invstd, eps, relu, False)[0]
         calls['batchnorm_eval'] += 1
     return y2.permute(0, 3, 1, 2)
+
+
+class _PoolNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad, is_max):
+        outs = C().pool_fwd(x, k, stride, pad, is_max)
+        calls['pool_fwd'] += 1
+        ctx.cfg = (x.shape[1], x.shape[2], k, stride, pad, is_max)
+        ctx.save_for_backward(outs[1] if is_max else None)
+        return outs[0]
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        H, W, k, stride, pad, is_max = ctx.cfg
+        calls['pool_bwd'] += 1
+        return C().pool_bwd(dy.contiguous(), arg, H, W, k, stride, pad, is_max), None, None, None, None
+
+
+def pool2d(x, kernel_size, stride, padding, is_max):
+    """Square max / average pooling of NCHW-shaped channels_last bf16 tensors on the NHWC kernels."""
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = _PoolNHWC.apply(x.permute(0, 2, 3, 1), int(kernel_size), int(stride), int(padding), bool(is_max))
+    return y.permute(0, 3, 1, 2)

@@ -246,6 +246,24 @@ def test_batchnorm_relu_add(N, C, H, W, relu, with_res):
     assert _rel_err(ye, torch.relu(yer) if relu else yer) < 1.5e-2
 
 
+@pytest.mark.parametrize('N,C,H,W,k,s,p,is_max', [(4, 64, 112, 112, 3, 2, 1, True), (2, 288, 32, 32, 3, 2, 0, True), (2, 192, 17, 17, 3, 1, 1, False),
+                                                  (3, 64, 9, 9, 2, 2, 0, True)])
+def test_pooling_nhwc(N, C, H, W, k, s, p, is_max):
+    from ravnest_b200 import ops
+    torch.manual_seed(15)
+    x = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    fn = ops.max_pool2d if is_max else ops.avg_pool2d
+    ref_fn = torch.nn.functional.max_pool2d if is_max else torch.nn.functional.avg_pool2d
+    y = fn(x, k, s, p)
+    g = _rand(*y.shape).contiguous(memory_format=torch.channels_last)
+    y.backward(g)
+    xr = x.detach().float().requires_grad_(True)
+    yr = ref_fn(xr, k, s, p)
+    yr.backward(g.float())
+    assert y.shape == yr.shape and _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 1e-2
+
+
 # ----------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize('B,S,heads,causal,padded', [(2, 128, 2, False, False), (8, 512, 12, False, True), (2, 384, 4, True, False),
                                                      (3, 200, 2, False, True), (2, 200, 2, True, True)])
