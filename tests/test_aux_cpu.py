@@ -1,0 +1,89 @@
+"""Aux subsystems on CPU: fault injection, heartbeat, tracing, compression, GA tie-break, misc helpers."""
+import os
+import time
+
+import pytest
+import torch
+
+import ravnest_b200 as rv
+from ravnest_b200.communication import compress_tensor, decompress_tensor, split_along_largest_axis
+from ravnest_b200.runtime.mailbox import Mailbox
+from ravnest_b200.runtime.watchdog import FaultInjector, Heartbeat
+from ravnest_b200.utils.tracing import StageTracer
+
+
+def test_fault_injector_rules():
+    fi = FaultInjector('drop_forward:3,delay_backward:5:0.05,kill:9')
+    assert fi.check('forward', 2) is None
+    assert fi.check('forward', 3) == 'drop'
+    t0 = time.time()
+    assert fi.check('backward', 5) is None and time.time() - t0 >= 0.05
+    with pytest.raises(SystemExit):
+        fi.check('forward', 9)
+    assert [k for k, _ in fi.fired] == ['drop_forward', 'delay_backward', 'kill']
+
+
+def test_heartbeat_detects_dead_peer():
+    class T:
+        def __init__(self):
+            self.alive = True
+
+        def ping(self, peer, timeout=1.0):
+            return self.alive
+
+    t, dead = T(), []
+    hb = Heartbeat(t, [('127.0.0.1', 1)], period=0.02, misses_to_fail=2, on_failure=dead.append)
+    hb.start()
+    time.sleep(0.1)
+    assert not hb.dead_peers()
+    t.alive = False
+    time.sleep(0.15)
+    hb.stop()
+    assert dead == [('127.0.0.1', 1)] and hb.dead_peers() == [('127.0.0.1', 1)]
+
+
+def test_mailbox_serves_backward_first_and_blocks_when_full():
+    mb = Mailbox(capacity=2)
+    mb.put('forward', 'f0')
+    mb.put('forward', 'f1')
+    assert not mb.has_room('forward') and mb.has_room('backward')
+    mb.put('backward', 'b0')
+    assert mb.get(0.1) == ('backward', 'b0')
+    assert mb.get(0.1) == ('forward', 'f0')
+    assert mb.get(0.1) == ('forward', 'f1')
+    assert mb.get(0.05) is None
+
+
+def test_tracer_on_cpu_is_a_noop_but_counts_idle(tmp_path):
+    tr = StageTracer('node_0', torch.device('cpu'), path=str(tmp_path / 'm.jsonl'))
+    with tr.phase('forward', 1):
+        pass
+    tr.idle(0.25)
+    s = tr.summary()
+    assert s['mailbox_idle_s'] == 0.25 and s['node'] == 'node_0'
+    assert os.path.exists(tr.dump())
+
+
+def test_fp16_compression_round_trip_clamps():
+    x = torch.tensor([1.0, -2.5, 1e6, -1e6])
+    c = compress_tensor(x)
+    assert c.dtype == torch.float16 and torch.isfinite(c).all()
+    assert decompress_tensor(c, torch.float32).dtype == torch.float32
+    assert compress_tensor(torch.ones(2, dtype=torch.float64)).dtype == torch.float32
+    idx = torch.arange(3)
+    assert compress_tensor(idx) is idx
+
+
+def test_ring_chunks_split_along_largest_axis():
+    chunks = split_along_largest_axis(torch.zeros(3, 10, 4), 4)
+    assert [c.shape[1] for c in chunks] == [3, 3, 2, 2] and all(c.shape[0] == 3 for c in chunks)
+    assert len(split_along_largest_axis(torch.tensor(1.0), 3)) == 3
+
+
+def test_set_seed_and_memory_estimate():
+    rv.set_seed(7)
+    a = torch.rand(3)
+    rv.set_seed(7)
+    assert torch.equal(a, torch.rand(3))
+    from ravnest_b200 import models
+    assert rv.get_memory_reqs(models.CNN_Net(), input_size=(64, 1, 8, 8)) >= 1
