@@ -302,8 +302,15 @@ def main():
     run(max(3, args.warmup), 'dev', False)
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
+    node.tracer.resolve(block=True)
+    exposed0 = node.tracer.totals_ms.get('exposed_comm', 0.0)
     dev_ms, dev_wall = timed(args.steps, 'dev', False)
     clocks = sampler.summary()
+    node.tracer.resolve(block=True)
+    exposed = torch.tensor([(node.tracer.totals_ms.get('exposed_comm', 0.0) - exposed0) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(exposed, op=dist.ReduceOp.MAX)
+    exposed_ms = float(exposed)
     result = None
     e2e = None
     if not args.no_e2e:
@@ -324,7 +331,10 @@ def main():
                        'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': 'LAMB' if args.model == 'bert' else 'SGD-momentum',
                        'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)', 'cuda_graphs': not args.no_graphs,
                        'l2': 'working set (weights+activations, >1 GB/step) exceeds the 126 MB L2; no explicit flush'},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'wall_ms_per_step': dev_wall / args.steps,
+            'clocks': clocks, 'e2e': e2e,
+            'gpu_launches': (launches or {}).get('ours_per_step', 0) * args.steps if isinstance(launches, dict) else 0,
+            'gpu_launches_detail': launches, 'wall_ms_per_step': dev_wall / args.steps,
+            'exposed_comm_ms_per_step': exposed_ms,
         }
         if args.layers:
             result['invalid'] = 'debug run with --layers'
