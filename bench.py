@@ -30,7 +30,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'baseline', 'reference'])
-    ap.add_argument('--model', default='bert', choices=['bert', 'resnet50'])
+    ap.add_argument('--model', default='bert', choices=['bert', 'resnet50', 'inception', 'sorter'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--update-frequency', type=int, default=None)
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
@@ -86,6 +86,10 @@ class ClockSampler(threading.Thread):
 def topology_for(model, n):
     if model == 'bert':
         return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}[n]
+    if model == 'inception':                      # BASELINE.json config #4: 3-stage pipeline (use --gpus 3 via torchrun, or a grid)
+        return {1: (1, 1), 2: (2, 1), 3: (3, 1), 4: (2, 2), 6: (3, 2), 8: (2, 4)}[n]
+    if model == 'sorter':                         # config #5: pure pipeline, one stage per GPU
+        return (n, 1)
     return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}[n]
 
 
@@ -101,6 +105,11 @@ def build_model(args):
         example = {'input_ids': torch.randint(0, cfg.vocab_size, (2, S)), 'attention_mask': torch.ones(2, S, dtype=torch.long),
                    'token_type_ids': torch.zeros(2, S, dtype=torch.long)}
         return model, (), example, B
+    if args.model == 'inception':
+        return models.Inception3(), (torch.rand(2, 3, 32, 32),), {}, 64
+    if args.model == 'sorter':
+        cfg = models.GPTConfig(model_type='gpt-nano', vocab_size=3, block_size=11)
+        return models.GPT(cfg), (torch.randint(0, 3, (2, 11)),), {}, 64
     model = models.resnet50(num_classes=200)
     return model, (torch.rand(2, 3, 224, 224),), {}, 100
 
@@ -141,13 +150,18 @@ class SyntheticBert:
 
 
 class SyntheticImages:
-    def __init__(self, n, batch, classes, device=None, seed=0, dtype=None):
+    def __init__(self, n, batch, classes, device=None, seed=0, dtype=None, size=224, tokens=None):
         import torch
         g = torch.Generator().manual_seed(seed)
         self.items = []
         for _ in range(n):
-            x = torch.randn(batch, 3, 224, 224, generator=g)
-            y = torch.randint(0, classes, (batch,), generator=g)
+            if tokens is not None:                 # GPT-Sorter: [batch, 11] int64 inputs, targets with -1 on the input half
+                x = torch.randint(0, classes, (batch, tokens), generator=g)
+                y = torch.sort(x[:, :6], dim=1)[0]
+                y = torch.cat([torch.full((batch, 5), -1, dtype=torch.long), y], dim=1)
+            else:
+                x = torch.randn(batch, 3, size, size, generator=g)
+                y = torch.randint(0, classes, (batch,), generator=g)
             if device is not None:
                 x, y = x.to(device), y.to(device)
             elif torch.cuda.is_available():
@@ -235,10 +249,23 @@ def main():
         feed = lambda node, item: node.forward_compute(input_ids=item['input_ids'], attention_mask=item['attention_mask'],
                                                        token_type_ids=item['token_type_ids'])
         metric, unit = 'bert_base_pretraining_samples_per_sec', 'samples/s'
+    elif args.model == 'sorter':
+        upd = args.update_frequency or 1
+        pool_dev = SyntheticImages(4, batch, 3, device=dev, seed=replica, tokens=11)
+        pool_host = SyntheticImages(4, batch, 3, device=None, seed=replica, tokens=11)
+
+        def criterion(outputs, targets):
+            return torch.nn.functional.cross_entropy(outputs.reshape(-1, outputs.size(-1)).float(), targets[1].reshape(-1).to(dev, non_blocking=True),
+                                                     ignore_index=-1)
+
+        node_kwargs = dict(optimizer=torch.optim.Adam, optimizer_params={}, update_frequency=upd, dtype=torch.bfloat16)
+        feed = lambda node, item: node.forward_compute(tensors=item[0])
+        metric, unit = 'gpt_sorter_samples_per_sec', 'samples/s'
     else:
         upd = args.update_frequency or 1
-        pool_dev = SyntheticImages(2, batch, 200, device=dev, seed=replica)
-        pool_host = SyntheticImages(2, batch, 200, device=None, seed=replica)
+        size, classes = (32, 10) if args.model == 'inception' else (224, 200)
+        pool_dev = SyntheticImages(2, batch, classes, device=dev, seed=replica, size=size)
+        pool_host = SyntheticImages(2, batch, classes, device=None, seed=replica, size=size)
         loss_fct = torch.nn.CrossEntropyLoss()
 
         def criterion(outputs, targets):
@@ -247,7 +274,7 @@ def main():
         node_kwargs = dict(optimizer=torch.optim.SGD, optimizer_params={'lr': 0.01, 'momentum': 0.9, 'weight_decay': 5e-4},
                            update_frequency=upd, dtype=torch.bfloat16)
         feed = lambda node, item: node.forward_compute(tensors=item[0])
-        metric, unit = 'resnet50_images_per_sec', 'images/s'
+        metric, unit = ('inception_v3_images_per_sec' if args.model == 'inception' else 'resnet50_images_per_sec'), 'images/s'
 
     labels = {'dev': iter(pool_dev), 'host': iter(pool_host)}
 
@@ -326,9 +353,10 @@ def main():
             'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic (random tokens/images of the benchmark shape; random-init weights)',
             'impl': args.impl,
-            'config': {'model': 'bert-base-uncased BertForPreTraining (110.1M)' if args.model == 'bert' else 'resnet50(num_classes=200)',
+            'config': {'model': {'bert': 'bert-base-uncased BertForPreTraining (110.1M)', 'resnet50': 'resnet50(num_classes=200) (23.9M)',
+                                 'inception': 'Inception3 CIFAR variant (21.6M)', 'sorter': 'minGPT gpt-nano (85.7K)'}[args.model],
                        'global_batch': replicas * batch, 'per_replica_batch': batch, 'seq_len': 512 if args.model == 'bert' else None,
-                       'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': 'LAMB' if args.model == 'bert' else 'SGD-momentum',
+                       'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': {'bert': 'LAMB', 'sorter': 'Adam'}.get(args.model, 'SGD-momentum'),
                        'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)', 'cuda_graphs': not args.no_graphs,
                        'l2': 'working set (weights+activations, >1 GB/step) exceeds the 126 MB L2; no explicit flush'},
             'clocks': clocks, 'e2e': e2e,

@@ -370,6 +370,38 @@ class _ConvNHWC(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+class _Conv1x1(torch.autograd.Function):
+    """Pointwise convolution on NHWC activations: forward and dgrad are plain GEMMs over the channel dimension; the weight
+    gradient reduces over ALL pixels (K = N*H*W, up to 3e5 for ResNet's first stage) into a handful of output tiles, so it runs
+    on the split-K wgrad kernel (pixel patches as the reduction dimension, fp32 atomics) instead of the TT GEMM."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, w2, bias):
+        n, h, w, c = x_nhwc.shape
+        y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, bias, 0, None, False, 0)[0]
+        calls['conv1x1_as_gemm'] += 1
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x_nhwc, w2)
+        return y2.view(n, h, w, w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2 = ctx.saved_tensors
+        n, h, w, c = x.shape
+        dy = dy.contiguous()
+        dy2 = dy.view(n * h * w, w2.shape[0])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = C().gemm(dy2, False, w2, True, None, 0, None, False, 0)[0].view(n, h, w, c)
+            calls['gemm_dgrad'] += 1
+        if ctx.needs_input_grad[1]:
+            dw = C().conv_wgrad_nhwc(dy, x, 1, 1, 1, 0, 1).view(w2.shape[0], c).to(w2.dtype)
+            calls['conv_wgrad'] += 1
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _bias_grad(dy2, w2)
+        return dx, dw, db
+
+
 def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
@@ -392,11 +424,8 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
             x = x[:, :, ::sh, ::sw]
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        n, c, h, w = x.shape
-        x2 = x.permute(0, 2, 3, 1).reshape(n * h * w, c)                  # zero-copy NHWC view
-        y2 = linear(x2, weight.reshape(cout, c), bias, None)
-        calls['conv1x1_as_gemm'] += 1
-        return y2.view(n, h, w, cout).permute(0, 3, 1, 2)                 # NCHW-shaped, channels_last-strided
+        y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight.reshape(cout, cin), bias)      # zero-copy NHWC view in, NHWC out
+        return y.permute(0, 3, 1, 2)                                      # NCHW-shaped, channels_last-strided
     if base_ok and sh == sw and ph == pw and dh == dw_ and kh == kw and sh in (1, 2) and IMPLICIT_GEMM_CONV:
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
