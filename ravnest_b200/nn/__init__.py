@@ -107,10 +107,10 @@ class BatchNorm2d(nn.BatchNorm2d):
         self.relu = relu
 
     def forward(self, x, residual=None):
-        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
-            self.num_batches_tracked.add_(1)
-        return ops.batch_norm_act(x, self.weight, self.bias, self.running_mean, self.running_var, residual, self.relu,
-                                  self.training or not self.track_running_stats, self.momentum if self.momentum is not None else 0.1, self.eps)
+        training = self.training or not self.track_running_stats
+        nbt = self.num_batches_tracked if (self.training and self.track_running_stats) else None
+        return ops.batch_norm_act(x, self.weight, self.bias, self.running_mean, self.running_var, residual, self.relu, training,
+                                  self.momentum if self.momentum is not None else 0.1, self.eps, num_batches_tracked=nbt)
 
 
 class MaxPool2d(nn.MaxPool2d):

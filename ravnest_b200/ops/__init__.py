@@ -143,11 +143,16 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 
-def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
-    """``relu(batch_norm(x) + residual)`` (the tail of every ResNet / Inception conv block) in one pass over the activation."""
+def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5,
+                   num_batches_tracked=None):
+    """``relu(batch_norm(x) + residual)`` (the tail of every ResNet / Inception conv block) in one pass over the activation.
+    ``num_batches_tracked`` (optional int64 buffer) is incremented in training mode, inside the statistics kernel on the native path."""
     if _native(x, weight) and x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
         from . import native
-        return native.batch_norm_act(x, weight, bias, running_mean, running_var, residual, relu, training, momentum, eps)
+        return native.batch_norm_act(x, weight, bias, running_mean, running_var, residual, relu, training, momentum, eps,
+                                     num_batches_tracked)
+    if training and num_batches_tracked is not None:
+        num_batches_tracked.add_(1)
     y = F.batch_norm(x, running_mean, running_var, weight, bias, training, momentum, eps)
     if residual is not None:
         y = y + residual

@@ -5,23 +5,26 @@
 #include <cuda_runtime.h>
 #include <torch/extension.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 extern "C" {
 int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
                   const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out, int ld_preact,
-                  void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int num_sms,
+                  int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int num_sms,
                   cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
-                           void* dx_drop, void* dgamma, void* dbeta, float* acc, int num_sms, int rows, int H, const long long* rng,
-                           float dropout_p, cudaStream_t stream);
+                           void* dx_drop, void* dgamma, void* dbeta, float* acc, unsigned* counters, int accumulate, int num_sms, int rows,
+                           int H, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_ce_forward(const void* logits, int ld, const int64_t* target, float* lse, float* stats, float* loss, int rows, int V,
                    int64_t ignore_index, cudaStream_t stream);
 int rvn_ce_backward(const void* logits, int ld, const int64_t* target, const float* lse, const float* stats, const float* gscale,
                     void* dlogits, int ld_out, int rows, int V, int64_t ignore_index, cudaStream_t stream);
-int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, int num_sms, cudaStream_t stream);
+int rvn_column_sum(const void* x, int ld, float* ws, unsigned* counters, void* out, int accumulate, int rows, int C, int num_sms,
+                   cudaStream_t stream);
 int rvn_fmha_forward(const void* qkv, void* out, float* lse, const float* kbias, int B, int S, int heads, int causal, float scale,
                      const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const float* lse, const float* kbias, float* delta, float* dq_accum,
@@ -31,11 +34,12 @@ int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, in
                      int Cout, int R, int S, int stride, int pad, int dil, int transposed, int num_sms, cudaStream_t stream);
 int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
                    int stride, int pad, int dil, int num_sms, cudaStream_t stream);
-int rvn_batchnorm_forward(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                          float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps, float momentum, int relu,
-                          int training, int num_sms, cudaStream_t stream);
-int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const float* gamma, const float* mean, const float* invstd,
-                           float* sums, void* dx, void* dres, long long M, int C, int relu, int num_sms, cudaStream_t stream);
+int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean, void* running_var,
+                          long long* batches_tracked, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
+                          float momentum, int relu, int training, int param_bf16, int stats_bf16, int num_sms, cudaStream_t stream);
+int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const void* gamma, const float* mean, const float* invstd,
+                           float* sums, void* dx, void* dres, void* dgamma, void* dbeta, long long M, int C, int relu, int param_bf16,
+                           int accumulate, int num_sms, cudaStream_t stream);
 int rvn_pool_forward(const void* x, void* y, void* arg, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, int is_max,
                      int num_sms, cudaStream_t stream);
 int rvn_pool_backward(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
@@ -89,10 +93,11 @@ int ld_of(const torch::Tensor& t) {
 }
 
 // D[M,N] = epi(op(A) * op(B)^T).  A: [M,K] (a_mn=false) or [K,M] (a_mn=true); B: [N,K] (b_mn=false) or [K,N] (b_mn=true).
-// Returns {D} or {D, preact}.  D is allocated with a row stride rounded up to 8 elements; a narrowed view is returned.
+// store_preact: 0 none, 1 also return the pre-activation z, 2 also return act'(z).  aux_mode (with dact_in): 1 D = acc * act'(aux),
+// 2 D = acc + aux, 3 D = acc * aux.  Returns {D} or {D, preact}.  D is allocated with a row stride rounded up to 8 elements; a narrowed view is returned.
 std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::Tensor& B, bool b_mn,
                                 const c10::optional<torch::Tensor>& bias, int64_t act,
-                                const c10::optional<torch::Tensor>& dact_in, bool store_preact, int64_t block_n,
+                                const c10::optional<torch::Tensor>& dact_in, int64_t store_preact, int64_t block_n,
                                 int64_t aux_mode, const c10::optional<torch::Tensor>& out,
                                 const c10::optional<torch::Tensor>& b_copy_dst, const c10::optional<torch::Tensor>& bcopy_flags,
                                 int64_t bcopy_epoch) {
@@ -149,7 +154,7 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   unsigned* flags_ptr = bcopy_ptr != nullptr ? reinterpret_cast<unsigned*>(bcopy_flags->data_ptr<int>()) : nullptr;
   check(rvn_gemm_bf16(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
                       dact_ptr, ld_dact, static_cast<int>(aux_mode), preact_ptr, store_preact ? static_cast<int>(P.stride(0)) : ldd,
-                      bcopy_ptr, ld_bcopy, flags_ptr, static_cast<unsigned>(bcopy_epoch), static_cast<int>(block_n), sm_count(),
+                      static_cast<int>(store_preact), bcopy_ptr, ld_bcopy, flags_ptr, static_cast<unsigned>(bcopy_epoch), static_cast<int>(block_n), sm_count(),
                       cur_stream()),
         "gemm_bf16");
   std::vector<torch::Tensor> res;
@@ -195,22 +200,63 @@ std::vector<torch::Tensor> layernorm_fwd(const torch::Tensor& x, const c10::opti
   return {y, mean, rstd};
 }
 
-// returns {dsum (grad of the normalised sum == grad of the residual), dx (== dsum, or dsum o mask with dropout), dgamma, dbeta}
+// Zero-at-rest reduction workspace of the column reducers (rowwise.cu: last_block_of_column), one per device.  The engine issues
+// all compute of a process on ONE stream (eagerly or as graph replays), which is what makes sharing it safe; it must exist before
+// a CUDA-graph capture starts (every capture in this code base is preceded by eager warm-up steps, which create it).
+struct ReduceWs {
+  torch::Tensor sums;       // fp32 [kReduceCap]
+  torch::Tensor counters;   // int32 [kReduceCap / 256 + 1]
+};
+static constexpr int64_t kReduceCap = 1 << 17;
+static ReduceWs& reduce_ws(const torch::Device& dev, int64_t need) {
+  TORCH_CHECK(need <= kReduceCap, "column reduction wider than the workspace (", need, " > ", kReduceCap, ")");
+  static std::mutex mu;
+  static std::map<int, ReduceWs> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(static_cast<int>(dev.index()));
+  if (it == cache.end()) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(cur_stream(), &st);
+    TORCH_CHECK(st == cudaStreamCaptureStatusNone, "reduction workspace must be created before CUDA-graph capture (run one eager step first)");
+    ReduceWs w;
+    w.sums = torch::zeros({kReduceCap}, torch::TensorOptions().device(dev).dtype(torch::kFloat32));
+    w.counters = torch::zeros({kReduceCap / 256 + 1}, torch::TensorOptions().device(dev).dtype(torch::kInt32));
+    it = cache.emplace(static_cast<int>(dev.index()), std::move(w)).first;
+  }
+  return it->second;
+}
+
+// returns {dsum (grad of the normalised sum == grad of the residual), dx (== dsum, or dsum o mask with dropout), dgamma, dbeta};
+// with grad_gamma / grad_beta given the parameter gradients are accumulated into them in place (undefined tensors returned)
 std::vector<torch::Tensor> layernorm_bwd(const torch::Tensor& dy, const torch::Tensor& x, const torch::Tensor& gamma,
                                          const torch::Tensor& mean, const torch::Tensor& rstd, const c10::optional<torch::Tensor>& rng,
-                                         double dropout_p) {
+                                         double dropout_p, const c10::optional<torch::Tensor>& grad_gamma,
+                                         const c10::optional<torch::Tensor>& grad_beta) {
   c10::cuda::CUDAGuard guard(x.device());
   const int H = x.size(-1);
   const int rows = x.numel() / H;
   auto dsum = torch::empty_like(x);
   const long long* rp = dropout_p > 0.0 ? rng_ptr(rng) : nullptr;
   torch::Tensor dx = rp != nullptr ? torch::empty_like(x) : dsum;
-  auto dgamma = torch::empty({H}, x.options());
-  auto dbeta = torch::empty({H}, x.options());
-  auto acc = torch::empty({2 * static_cast<int64_t>(H)}, x.options().dtype(torch::kFloat32));
+  const bool acc_mode = grad_gamma.has_value() && grad_gamma->defined() && grad_beta.has_value() && grad_beta->defined();
+  torch::Tensor dgamma, dbeta;
+  void *dg_ptr, *db_ptr;
+  if (acc_mode) {
+    TORCH_CHECK(grad_gamma->scalar_type() == torch::kBFloat16 && grad_beta->scalar_type() == torch::kBFloat16 && grad_gamma->is_contiguous() &&
+                    grad_beta->is_contiguous() && grad_gamma->numel() == H && grad_beta->numel() == H, "bad LayerNorm gradient accumulators");
+    dg_ptr = grad_gamma->data_ptr();
+    db_ptr = grad_beta->data_ptr();
+  } else {
+    dgamma = torch::empty({H}, x.options());
+    dbeta = torch::empty({H}, x.options());
+    dg_ptr = dgamma.data_ptr();
+    db_ptr = dbeta.data_ptr();
+  }
+  ReduceWs& ws = reduce_ws(x.device(), 2 * static_cast<int64_t>(H));
   check(rvn_layernorm_backward(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
-                               dsum.data_ptr(), rp != nullptr ? dx.data_ptr() : nullptr, dgamma.data_ptr(), dbeta.data_ptr(),
-                               acc.data_ptr<float>(), sm_count(), rows, H, rp, static_cast<float>(dropout_p), cur_stream()),
+                               dsum.data_ptr(), rp != nullptr ? dx.data_ptr() : nullptr, dg_ptr, db_ptr, ws.sums.data_ptr<float>(),
+                               reinterpret_cast<unsigned*>(ws.counters.data_ptr<int>()), acc_mode ? 1 : 0, sm_count(), rows, H, rp,
+                               static_cast<float>(dropout_p), cur_stream()),
         "layernorm_bwd");
   return {dsum, dx, dgamma, dbeta};
 }
@@ -243,11 +289,24 @@ torch::Tensor ce_bwd(const torch::Tensor& logits, const torch::Tensor& target, c
   return ld_out == V ? d : d.narrow(1, 0, V);
 }
 
-torch::Tensor column_sum(const torch::Tensor& x) {
+// bf16 column sums of a 2-D bf16 matrix (bias gradients).  With ``into`` given the sums are ADDED to it in place (the flat gradient
+// bucket) and it is returned; otherwise a fresh bf16 [C] tensor is returned.
+torch::Tensor column_sum(const torch::Tensor& x, const c10::optional<torch::Tensor>& into) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == torch::kBFloat16, "column_sum expects 2-D bf16");
-  auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
-  check(rvn_column_sum(x.data_ptr(), x.stride(0), out.data_ptr<float>(), x.size(0), x.size(1), sm_count(), cur_stream()), "column_sum");
+  const int64_t C = x.size(1);
+  const bool acc_mode = into.has_value() && into->defined();
+  torch::Tensor out;
+  if (acc_mode) {
+    TORCH_CHECK(into->scalar_type() == torch::kBFloat16 && into->is_contiguous() && into->numel() == C, "bad column_sum accumulator");
+    out = *into;
+  } else {
+    out = torch::empty({C}, x.options());
+  }
+  ReduceWs& ws = reduce_ws(x.device(), C);
+  check(rvn_column_sum(x.data_ptr(), x.stride(0), ws.sums.data_ptr<float>(), reinterpret_cast<unsigned*>(ws.counters.data_ptr<int>()),
+                       out.data_ptr(), acc_mode ? 1 : 0, x.size(0), C, sm_count(), cur_stream()),
+        "column_sum");
   return out;
 }
 
@@ -343,14 +402,24 @@ torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, i
   return dw;
 }
 
-// x: [..., C] bf16 contiguous (NHWC flattened); gamma/beta/mean/invstd fp32 [C].  training: batch statistics are computed (mean, invstd
-// returned); eval: the given mean / invstd are applied.  Returns {y, mean, invstd}
+// x: [..., C] bf16 contiguous (NHWC flattened); gamma / beta in the parameter dtype (bf16 or fp32), mean / invstd fp32 [C].
+// training: batch statistics are computed (mean, invstd returned) and, when given, running_mean / running_var / num_batches_tracked
+// are updated by the finalize kernel; eval: the given mean / invstd are applied.  Returns {y, mean, invstd}
+static int is_bf16_or_f32(const torch::Tensor& t, const char* what) {
+  TORCH_CHECK(t.scalar_type() == torch::kBFloat16 || t.scalar_type() == torch::kFloat32, what, " must be bf16 or fp32");
+  TORCH_CHECK(t.is_contiguous(), what, " must be contiguous");
+  return t.scalar_type() == torch::kBFloat16;
+}
+
 std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::optional<torch::Tensor>& res, const torch::Tensor& gamma,
                                          const torch::Tensor& beta, const c10::optional<torch::Tensor>& mean_in,
-                                         const c10::optional<torch::Tensor>& invstd_in, double eps, bool relu, bool training) {
+                                         const c10::optional<torch::Tensor>& invstd_in, double eps, bool relu, bool training,
+                                         const c10::optional<torch::Tensor>& running_mean, const c10::optional<torch::Tensor>& running_var,
+                                         const c10::optional<torch::Tensor>& batches_tracked, double momentum) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kBFloat16, "batchnorm expects contiguous bf16 NHWC input");
-  TORCH_CHECK(gamma.scalar_type() == torch::kFloat32 && beta.scalar_type() == torch::kFloat32, "gamma / beta must be fp32");
+  const int pbf = is_bf16_or_f32(gamma, "gamma");
+  TORCH_CHECK(beta.scalar_type() == gamma.scalar_type() && beta.is_contiguous(), "beta must match gamma");
   const int C = x.size(-1);
   const long long M = x.numel() / C;
   auto f32 = x.options().dtype(torch::kFloat32);
@@ -360,30 +429,62 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
   auto sums = torch::empty({2 * static_cast<int64_t>(C)}, f32);
   const void* res_ptr = (res.has_value() && res->defined()) ? res->data_ptr() : nullptr;
   if (res_ptr) TORCH_CHECK(res->is_contiguous() && res->numel() == x.numel(), "residual must match x");
-  check(rvn_batchnorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr<float>(), beta.data_ptr<float>(), nullptr, nullptr, mean.data_ptr<float>(),
-                              invstd.data_ptr<float>(), sums.data_ptr<float>(), y.data_ptr(), M, C, static_cast<float>(eps), 0.f, relu,
-                              training, sm_count(), cur_stream()),
+  void *rm = nullptr, *rv = nullptr;
+  long long* nbt = nullptr;
+  int sbf = 0;
+  if (training && running_mean.has_value() && running_mean->defined()) {
+    sbf = is_bf16_or_f32(*running_mean, "running_mean");
+    TORCH_CHECK(running_var.has_value() && running_var->scalar_type() == running_mean->scalar_type() && running_var->is_contiguous(),
+                "running_var must match running_mean");
+    rm = running_mean->data_ptr();
+    rv = running_var->data_ptr();
+    if (batches_tracked.has_value() && batches_tracked->defined()) {
+      TORCH_CHECK(batches_tracked->scalar_type() == torch::kInt64, "num_batches_tracked must be int64");
+      nbt = reinterpret_cast<long long*>(batches_tracked->data_ptr());
+    }
+  }
+  check(rvn_batchnorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr(), beta.data_ptr(), rm, rv, nbt, mean.data_ptr<float>(),
+                              invstd.data_ptr<float>(), sums.data_ptr<float>(), y.data_ptr(), M, C, static_cast<float>(eps),
+                              static_cast<float>(momentum), relu, training, pbf, sbf, sm_count(), cur_stream()),
         "batchnorm_fwd");
   return {y, mean, invstd};
 }
 
-// returns {dx, dres (dz, defined only when want_dres), dgamma fp32, dbeta fp32}
+// returns {dx, dres (dz, defined only when want_dres), dgamma, dbeta} — dgamma / dbeta in gamma's dtype; when grad_gamma / grad_beta
+// are given the parameter gradients are accumulated into them in place and undefined tensors are returned instead
 std::vector<torch::Tensor> batchnorm_bwd(const torch::Tensor& dy, const c10::optional<torch::Tensor>& y, const torch::Tensor& x,
                                          const torch::Tensor& gamma, const torch::Tensor& mean, const torch::Tensor& invstd, bool relu,
-                                         bool want_dres) {
+                                         bool want_dres, const c10::optional<torch::Tensor>& grad_gamma,
+                                         const c10::optional<torch::Tensor>& grad_beta) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(dy.is_contiguous() && x.is_contiguous(), "batchnorm_bwd expects contiguous tensors");
+  const int pbf = is_bf16_or_f32(gamma, "gamma");
   const int C = x.size(-1);
   const long long M = x.numel() / C;
   auto sums = torch::empty({2 * static_cast<int64_t>(C)}, x.options().dtype(torch::kFloat32));
   auto dx = torch::empty_like(x);
-  torch::Tensor dres;
+  torch::Tensor dres, dgamma, dbeta;
   if (want_dres) dres = torch::empty_like(x);
+  const bool acc = grad_gamma.has_value() && grad_gamma->defined() && grad_beta.has_value() && grad_beta->defined();
+  void *dg_ptr, *db_ptr;
+  if (acc) {
+    TORCH_CHECK(grad_gamma->scalar_type() == gamma.scalar_type() && grad_beta->scalar_type() == gamma.scalar_type() &&
+                    grad_gamma->is_contiguous() && grad_beta->is_contiguous() && grad_gamma->numel() == C && grad_beta->numel() == C,
+                "gradient accumulators must match gamma");
+    dg_ptr = grad_gamma->data_ptr();
+    db_ptr = grad_beta->data_ptr();
+  } else {
+    dgamma = torch::empty_like(gamma);
+    dbeta = torch::empty_like(gamma);
+    dg_ptr = dgamma.data_ptr();
+    db_ptr = dbeta.data_ptr();
+  }
   const void* y_ptr = relu ? y.value().data_ptr() : nullptr;
-  check(rvn_batchnorm_backward(dy.data_ptr(), y_ptr, x.data_ptr(), gamma.data_ptr<float>(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
-                               sums.data_ptr<float>(), dx.data_ptr(), want_dres ? dres.data_ptr() : nullptr, M, C, relu, sm_count(), cur_stream()),
+  check(rvn_batchnorm_backward(dy.data_ptr(), y_ptr, x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                               sums.data_ptr<float>(), dx.data_ptr(), want_dres ? dres.data_ptr() : nullptr, dg_ptr, db_ptr, M, C, relu, pbf,
+                               acc ? 1 : 0, sm_count(), cur_stream()),
         "batchnorm_bwd");
-  return {dx, dres, sums.narrow(0, C, C), sums.narrow(0, 0, C)};
+  return {dx, dres, dgamma, dbeta};
 }
 
 // x [N,H,W,C] bf16 NHWC -> {y [N,Ho,Wo,C], argmax (uint8, max pooling only)}
@@ -481,10 +582,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none(),
         py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0);
   m.def("layernorm_fwd", &layernorm_fwd);
-  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("gamma"), py::arg("mean"), py::arg("rstd"), py::arg("rng"),
+        py::arg("dropout_p"), py::arg("grad_gamma") = py::none(), py::arg("grad_beta") = py::none());
   m.def("ce_fwd", &ce_fwd);
   m.def("ce_bwd", &ce_bwd);
-  m.def("column_sum", &column_sum);
+  m.def("column_sum", &column_sum, py::arg("x"), py::arg("into") = py::none());
   m.def("act_bwd", &act_bwd);
   m.def("conv_nhwc", &conv_nhwc);
   m.def("pool_fwd", &pool_fwd);

@@ -2,7 +2,8 @@
 // shared memory by TMA (128B swizzle), fp32 accumulators in TMEM (double-buffered so the epilogue of tile i
 // overlaps the MMAs of tile i+1), persistent CTAs (one per SM), warp-specialised:
 //   warp 0 : TMA producer      warp 1 : MMA issuer (one elected lane)     warp 2 : TMEM allocator
-//   warps 4-7 : epilogue  (tcgen05.ld -> bias / activation / activation-gradient -> bf16 -> swizzled smem -> TMA store)
+//   warps 4-11: epilogue  (tcgen05.ld -> bias / activation / activation-gradient -> bf16 -> swizzled smem -> TMA store); two warps
+//               per TMEM lane quadrant, each taking one 32-column half of the 64-column slab (GELU epilogues are issue-bound)
 //
 //   D[M,N] = epi( A * B ),  A is M x K, B is N x K ("K-major", row-major [rows, K]) or their transposes stored
 //   row-major [K, rows] ("MN-major") — so forward (x W^T), dgrad (dY W) and wgrad (dY^T x) all run on the same
@@ -22,8 +23,8 @@ namespace rvn {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
 constexpr int SLAB_N = 64;           // epilogue staging slab: 128 rows x 64 cols bf16 = 16 KB
 constexpr int SLAB_BYTES = BLOCK_M * SLAB_N * 2;
 
@@ -34,9 +35,9 @@ struct GemmParams {
   const __nv_bfloat16* bias;      // [N] or nullptr
   const __nv_bfloat16* dact_in;   // [M, ld_aux] auxiliary input tile or nullptr
   int ld_aux;
-  int aux_mode;                   // 1: D = acc * act'(aux)  (activation gradient)   2: D = acc + aux  (gradient accumulation)
+  int aux_mode;                   // 1: D = acc * act'(aux)   2: D = acc + aux (gradient accumulation)   3: D = acc * aux
   int act;                        // Act
-  int store_preact;               // also write the pre-activation through map_aux
+  int store_preact;               // also write through map_aux: 1 the pre-activation z, 2 the activation derivative act'(z)
   int b_copy;                     // K2: B lives in a PEER's HBM.  The (otherwise idle) epilogue warps of all CTAs first pull it
   const __nv_bfloat16* b_peer;    //     tile by tile over NVLink into the local buffer (every SM issues peer loads: one SM alone gets
   __nv_bfloat16* b_local;         //     ~5 GB/s, the whole chip ~750 GB/s) and publish flags[n_blk * num_k_blocks + kb] = epoch;
@@ -58,11 +59,30 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + slack for manual 1024 B alignment
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU and its derivative from ONE exponential: with t = 1 / (1 + p |x|/sqrt2) (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7),
+//   erfc(|x|/sqrt2) = poly(t) * exp(-x^2/2)   and   pdf(x) = exp(-x^2/2) / sqrt(2 pi)
+// so cdf, gelu = x cdf and gelu' = cdf + x pdf cost one ex2, one rcp and ~12 FMAs (libdevice erff alone is ~2x that and branches).
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {
+  const float ax = fabsf(x);
+  const float e = exp2f(-0.72134752044448170f * x * x);              // exp(-x^2/2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;                        // 0.5 * erfc(|x|/sqrt2)
+  cdf = x >= 0.0f ? 1.0f - half_erfc : half_erfc;
+  pdf_x = 0.39894228040143268f * x * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, px;
+  gelu_parts(x, cdf, px);
+  return x * cdf;
+}
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, px;
+  gelu_parts(x, cdf, px);
+  return cdf + px;
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
@@ -226,8 +246,9 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ================================================================ epilogue (128 threads, one row each)
-    const int ewarp = warp - 4;                 // TMEM lane quadrant == warp index % 4
+    // ================================================================ epilogue (256 threads: one row x one 32-column half each)
+    const int ewarp = (warp - 4) & 3;           // TMEM lane quadrant == warp index % 4
+    const int half = (warp - 4) >> 2;           // which 32-column half of every 64-column slab this warp owns
     const int row_in_tile = ewarp * 32 + lane_id();
     const bool issuer = threadIdx.x == 128;
     int acc = 0;
@@ -277,8 +298,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
           if (one_buffer) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         named_bar_sync(1, EPI_THREADS);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
           uint32_t v[32];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BN + slab * SLAB_N + half * 32;
           tmem_ld_32x32(taddr, v);
@@ -303,22 +323,28 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
           }
           if (p.store_preact) {
+            float g[32];
+            if (p.store_preact == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) g[i] = apply_dact(f[i], p.act);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) g[i] = f[i];
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               const int chunk = half * 4 + (i >> 3);
               uint4 o;
-              o.x = pack_bf16x2(f[i], f[i + 1]); o.y = pack_bf16x2(f[i + 2], f[i + 3]);
-              o.z = pack_bf16x2(f[i + 4], f[i + 5]); o.w = pack_bf16x2(f[i + 6], f[i + 7]);
+              o.x = pack_bf16x2(g[i], g[i + 1]); o.y = pack_bf16x2(g[i + 2], g[i + 3]);
+              o.z = pack_bf16x2(g[i + 4], g[i + 5]); o.w = pack_bf16x2(g[i + 6], g[i + 7]);
               *reinterpret_cast<uint4*>(buf_aux + row_in_tile * 128 + ((chunk ^ (row_in_tile & 7)) << 4)) = o;
             }
           }
           if (has_aux_in) {
             // auxiliary input slab (pre-activation z, or the gradient tile being accumulated into) arrives through TMA
             // (coalesced 128 B rows into swizzled smem); its load was issued one slab ahead, so this wait is usually free
-            if (half == 0) {
-              mbar_wait(aux_bar, aux_phase);
-              aux_phase ^= 1;
-            }
+            mbar_wait(aux_bar, aux_phase);
+            aux_phase ^= 1;
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               const int chunk = half * 4 + (i >> 3);
@@ -330,6 +356,9 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (p.aux_mode == 2) {
                   f[i + 2 * j] += zf.x;
                   f[i + 2 * j + 1] += zf.y;
+                } else if (p.aux_mode == 3) {
+                  f[i + 2 * j] *= zf.x;
+                  f[i + 2 * j + 1] *= zf.y;
                 } else {
                   f[i + 2 * j] *= apply_dact(zf.x, p.act);
                   f[i + 2 * j + 1] *= apply_dact(zf.y, p.act);
@@ -470,7 +499,7 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 // C entry point used by binding.cpp.  Layout flags: a_mn / b_mn = operand stored [K, rows] instead of [rows, K].
 extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
                              int K, const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out,
-                             int ld_preact, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n,
+                             int ld_preact, int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n,
                              int num_sms, cudaStream_t stream) {
   rvn::GemmParams p{};
   p.M = M; p.N = N; p.K = K;
@@ -479,7 +508,7 @@ extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   p.ld_aux = ld_dact;
   p.aux_mode = dact_in != nullptr ? aux_mode : 0;
   p.act = act;
-  p.store_preact = preact_out != nullptr ? 1 : 0;
+  p.store_preact = preact_out != nullptr ? (preact_mode == 2 ? 2 : 1) : 0;
   p.bcopy_flags = bcopy_flags;
   p.bcopy_epoch = bcopy_epoch;
 #define RVN_DISPATCH(BN_)                                                                                              \

@@ -35,6 +35,15 @@ struct v8 {
   }
 };
 
+// per-channel parameters / statistics arrive in the module's own dtype (bf16 under a bf16 Node, fp32 otherwise): no cast launches
+__device__ __forceinline__ float ldp(const void* p, int i, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void stp(void* p, int i, float v, int is_bf16) {
+  if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[i] = v;
+}
+
 // sums[0..C) += sum_r x[r,c];  sums[C..2C) += sum_r x[r,c]^2      (total threads % (C/8) == 0)
 __global__ void __launch_bounds__(256) rvn_bn_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ sums, size_t nvec, int C) {
   extern __shared__ float sh[];                     // [2][C]
@@ -76,33 +85,34 @@ __global__ void __launch_bounds__(256) rvn_bn_stats(const __nv_bfloat16* __restr
 
 // mean / invstd from the sums; running statistics updated like torch (unbiased variance, momentum)
 __global__ void rvn_bn_finalize(const float* __restrict__ sums, float* __restrict__ mean, float* __restrict__ invstd,
-                                float* __restrict__ running_mean, float* __restrict__ running_var, float count, float eps,
-                                float momentum, int C) {
+                                void* __restrict__ running_mean, void* __restrict__ running_var, long long* __restrict__ batches_tracked,
+                                float count, float eps, float momentum, int C, int stats_bf16) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && batches_tracked != nullptr) *batches_tracked += 1;
   if (c >= C) return;
   const float m = sums[c] / count;
   const float var = fmaxf(sums[C + c] / count - m * m, 0.f);
   mean[c] = m;
   invstd[c] = rsqrtf(var + eps);
   if (running_mean != nullptr) {
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+    stp(running_mean, c, (1.f - momentum) * ldp(running_mean, c, stats_bf16) + momentum * m, stats_bf16);
+    stp(running_var, c, (1.f - momentum) * ldp(running_var, c, stats_bf16) + momentum * var * (count / fmaxf(count - 1.f, 1.f)), stats_bf16);
   }
 }
 
 // y = act((x - mean) * invstd * gamma + beta + residual)
 __global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
-                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const void* __restrict__ gamma, const void* __restrict__ beta,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                    __nv_bfloat16* __restrict__ y, size_t nvec, int C, int relu) {
+                                                    __nv_bfloat16* __restrict__ y, size_t nvec, int C, int relu, int param_bf16) {
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int c0 = static_cast<int>(tid % (C / 8)) * 8;
   float sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = gamma[c0 + j] * invstd[c0 + j];
-    sf[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+    sc[j] = ldp(gamma, c0 + j, param_bf16) * invstd[c0 + j];
+    sf[j] = ldp(beta, c0 + j, param_bf16) - mean[c0 + j] * sc[j];
   }
   for (size_t i = tid; i < nvec; i += stride) {
     v8 a, o;
@@ -174,10 +184,20 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __
 
 // dx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dres = dz (gradient of the fused residual branch)
 __global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                                                        const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const __nv_bfloat16* __restrict__ x, const void* __restrict__ gamma,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
-                                                        __nv_bfloat16* __restrict__ dres, size_t nvec, int C, float count, int relu) {
+                                                        __nv_bfloat16* __restrict__ dres, void* __restrict__ dgamma,
+                                                        void* __restrict__ dbeta, size_t nvec, int C, float count, int relu,
+                                                        int param_bf16, int accumulate) {
+  if (blockIdx.x == 0 && dgamma != nullptr) {       // parameter gradients in the parameter dtype, optionally accumulated in place
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float dg = sums[C + c] + (accumulate ? ldp(dgamma, c, param_bf16) : 0.f);
+      const float db = sums[c] + (accumulate ? ldp(dbeta, c, param_bf16) : 0.f);
+      stp(dgamma, c, dg, param_bf16);
+      stp(dbeta, c, db, param_bf16);
+    }
+  }
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int c0 = static_cast<int>(tid % (C / 8)) * 8;
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __r
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[c0 + j];
     is[j] = invstd[c0 + j];
-    gi[j] = gamma[c0 + j] * is[j];
+    gi[j] = ldp(gamma, c0 + j, param_bf16) * is[j];
     m1[j] = sums[c0 + j] / count;
     m2[j] = sums[C + c0 + j] / count;
   }
@@ -231,27 +251,28 @@ static int bn_grid(size_t nvec, int C, int num_sms, int waves) {
   return static_cast<int>(grid);
 }
 
-extern "C" int rvn_batchnorm_forward(const void* x, const void* res, const float* gamma, const float* beta, float* running_mean,
-                                     float* running_var, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
-                                     float momentum, int relu, int training, int num_sms, cudaStream_t stream) {
+extern "C" int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean,
+                                     void* running_var, long long* batches_tracked, float* mean, float* invstd, float* sums, void* y,
+                                     long long M, int C, float eps, float momentum, int relu, int training, int param_bf16,
+                                     int stats_bf16, int num_sms, cudaStream_t stream) {
   if (C % 8 != 0 || C > 4096) return -2;
   const size_t nvec = static_cast<size_t>(M) * C / 8;
   using T = const __nv_bfloat16*;
   if (training) {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream);
     rvn::rvn_bn_stats<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)x, sums, nvec, C);
-    rvn::rvn_bn_finalize<<<(C + 127) / 128, 128, 0, stream>>>(sums, mean, invstd, running_mean, running_var, static_cast<float>(M), eps,
-                                                               momentum, C);
+    rvn::rvn_bn_finalize<<<(C + 127) / 128, 128, 0, stream>>>(sums, mean, invstd, running_mean, running_var, batches_tracked,
+                                                               static_cast<float>(M), eps, momentum, C, stats_bf16);
   }
   rvn::rvn_bn_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)x, (T)res, gamma, beta, mean, invstd, (__nv_bfloat16*)y, nvec, C,
-                                                                      relu);
+                                                                      relu, param_bf16);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 // sums (2*C fp32) holds {dbeta = sum dz, dgamma = sum dz*xhat} on return
-extern "C" int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const float* gamma, const float* mean,
-                                      const float* invstd, float* sums, void* dx, void* dres, long long M, int C, int relu, int num_sms,
-                                      cudaStream_t stream) {
+extern "C" int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const void* gamma, const float* mean,
+                                      const float* invstd, float* sums, void* dx, void* dres, void* dgamma, void* dbeta, long long M,
+                                      int C, int relu, int param_bf16, int accumulate, int num_sms, cudaStream_t stream) {
   if (C % 8 != 0 || C > 4096) return -2;
   const size_t nvec = static_cast<size_t>(M) * C / 8;
   using T = const __nv_bfloat16*;
@@ -259,6 +280,7 @@ extern "C" int rvn_batchnorm_backward(const void* dy, const void* y, const void*
   rvn::rvn_bn_bwd_reduce<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)dy, (T)y, (T)x, mean, invstd, sums, nvec, C,
                                                                                             relu);
   rvn::rvn_bn_bwd_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)dy, (T)y, (T)x, gamma, mean, invstd, sums, (__nv_bfloat16*)dx,
-                                                                          (__nv_bfloat16*)dres, nvec, C, static_cast<float>(M), relu);
+                                                                          (__nv_bfloat16*)dres, dgamma, dbeta, nvec, C, static_cast<float>(M),
+                                                                          relu, param_bf16, accumulate);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

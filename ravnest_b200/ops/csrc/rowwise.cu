@@ -197,10 +197,31 @@ __global__ void __launch_bounds__(256) rvn_layernorm_bwd_dx(const __nv_bfloat16*
   }
 }
 
-// acc[0][c] += sum_r dy[r,c] * xhat[r,c];  acc[1][c] += sum_r dy[r,c]   (column reduce; same tiling as rvn_colsum)
+// Self-cleaning split reduction shared by the column reducers below: partial sums are added with fp32 atomics into a
+// workspace that is ZERO AT REST; the last CTA of a column block (ticket counter) converts the totals into the output
+// (optionally accumulating into it: the flat gradient bucket), then zeroes the workspace slots and its counter again.
+// No memset, no finalize kernel, no cast / AccumulateGrad launch per parameter.
+__device__ __forceinline__ bool last_block_of_column(unsigned* counter, unsigned parts) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == parts - 1;
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+__device__ __forceinline__ void finalize_column(float* ws, __nv_bfloat16* out, int c, int accumulate) {
+  const float total = __ldcg(ws + c);
+  ws[c] = 0.f;
+  out[c] = __float2bfloat16(accumulate ? total + __bfloat162float(out[c]) : total);
+}
+
+// dgamma[c] (+)= sum_r dy[r,c] * xhat[r,c];  dbeta[c] (+)= sum_r dy[r,c]   (column reduce; same tiling as rvn_colsum)
 __global__ void __launch_bounds__(256) rvn_layernorm_bwd_params(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                                                                float* __restrict__ acc, int rows, int H, int rows_per_block) {
+                                                                float* __restrict__ acc, unsigned* __restrict__ counters,
+                                                                __nv_bfloat16* __restrict__ dgamma, __nv_bfloat16* __restrict__ dbeta,
+                                                                int accumulate, int rows, int H, int rows_per_block) {
   __shared__ float sh[2][8][256];
   const int cg = threadIdx.x & 31;
   const int rl = threadIdx.x >> 5;
@@ -240,14 +261,12 @@ __global__ void __launch_bounds__(256) rvn_layernorm_bwd_params(const __nv_bfloa
     atomicAdd(&acc[c], t0);
     atomicAdd(&acc[H + c], t1);
   }
-}
-
-__global__ void __launch_bounds__(256) rvn_layernorm_bwd_finalize(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dgamma,
-                                                                  __nv_bfloat16* __restrict__ dbeta, int H) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < H) {
-    dgamma[c] = __float2bfloat16(acc[c]);
-    dbeta[c] = __float2bfloat16(acc[H + c]);
+  if (last_block_of_column(counters + blockIdx.x, gridDim.y)) {
+    if (c < H) {
+      finalize_column(acc, dgamma, c, accumulate);
+      finalize_column(acc + H, dbeta, c, accumulate);
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
   }
 }
 
@@ -352,10 +371,12 @@ __global__ void rvn_ce_finalize(const float* __restrict__ stats, float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ column sum (bias grad)
-// out[c] += sum_r x[r, c]; x bf16 [rows, ld] (ld % 8 == 0).  256 threads = 32 column groups (8 columns, one 16 B load each)
-// x 8 row lanes; grid = (ceil(C/256), row_chunks); fp32 atomics into a zeroed buffer.
-__global__ void __launch_bounds__(256) rvn_colsum(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ out, int rows,
-                                                  int C, int rows_per_block) {
+// out[c] (+)= sum_r x[r, c]; x bf16 [rows, ld] (ld % 8 == 0).  256 threads = 32 column groups (8 columns, one 16 B load each)
+// x 8 row lanes; grid = (ceil(C/256), row_chunks); fp32 atomics into the zero-at-rest workspace, last CTA per column block
+// writes the bf16 result (see last_block_of_column).
+__global__ void __launch_bounds__(256) rvn_colsum(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ ws,
+                                                  unsigned* __restrict__ counters, __nv_bfloat16* __restrict__ out, int accumulate,
+                                                  int rows, int C, int rows_per_block) {
   __shared__ float sh[8][256];
   const int cg = threadIdx.x & 31;
   const int rl = threadIdx.x >> 5;
@@ -386,7 +407,11 @@ __global__ void __launch_bounds__(256) rvn_colsum(const __nv_bfloat16* __restric
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-    atomicAdd(&out[c], t);
+    atomicAdd(&ws[c], t);
+  }
+  if (last_block_of_column(counters + blockIdx.x, gridDim.y)) {
+    if (c < C) finalize_column(ws, out, c, accumulate);
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
   }
 }
 
@@ -414,10 +439,12 @@ extern "C" int rvn_layernorm_forward(const void* x, const void* res, const void*
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// acc: 2*H fp32 scratch (zeroed here)
+// acc: >= 2*H fp32 zero-at-rest workspace, counters: >= ceil(H/256) zero-at-rest tickets (both left zeroed again on completion);
+// accumulate != 0 adds the parameter gradients into dgamma / dbeta instead of overwriting them
 extern "C" int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                                      void* dsum, void* dx_drop, void* dgamma, void* dbeta, float* acc, int num_sms, int rows, int H,
-                                      const long long* rng, float dropout_p, cudaStream_t stream) {
+                                      void* dsum, void* dx_drop, void* dgamma, void* dbeta, float* acc, unsigned* counters,
+                                      int accumulate, int num_sms, int rows, int H, const long long* rng, float dropout_p,
+                                      cudaStream_t stream) {
   if (H % 8 != 0) return -2;
   const int vpl = (H / 8 + 31) / 32;
   using T = const __nv_bfloat16*;
@@ -425,15 +452,14 @@ extern "C" int rvn_layernorm_backward(const void* dy, const void* x, const void*
   dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
   RVN_LN_DISPATCH(rvn::rvn_layernorm_bwd_dx, <<<grid, block, 0, stream>>>((T)dy, (T)x, (T)gamma, mean, rstd, (__nv_bfloat16*)dsum,
                                                                           (__nv_bfloat16*)dx_drop, rows, H, rng, dropout_p))
-  cudaMemsetAsync(acc, 0, sizeof(float) * 2 * H, stream);
   const int col_blocks = (H + 255) / 256;
   int chunks = (2 * num_sms + col_blocks - 1) / col_blocks;
   if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
   if (chunks < 1) chunks = 1;
   const int rpb = (rows + chunks - 1) / chunks;
   dim3 pgrid(col_blocks, (rows + rpb - 1) / rpb);
-  rvn::rvn_layernorm_bwd_params<<<pgrid, 256, 0, stream>>>((T)dy, (T)x, mean, rstd, acc, rows, H, rpb);
-  rvn::rvn_layernorm_bwd_finalize<<<(H + 255) / 256, 256, 0, stream>>>(acc, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, H);
+  rvn::rvn_layernorm_bwd_params<<<pgrid, 256, 0, stream>>>((T)dy, (T)x, mean, rstd, acc, counters, (__nv_bfloat16*)dgamma,
+                                                           (__nv_bfloat16*)dbeta, accumulate, rows, H, rpb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
@@ -452,14 +478,15 @@ extern "C" int rvn_ce_backward(const void* logits, int ld, const int64_t* target
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-extern "C" int rvn_column_sum(const void* x, int ld, float* out, int rows, int C, int num_sms, cudaStream_t stream) {
+extern "C" int rvn_column_sum(const void* x, int ld, float* ws, unsigned* counters, void* out, int accumulate, int rows, int C,
+                              int num_sms, cudaStream_t stream) {
   const int col_blocks = (C + 255) / 256;
   int chunks = (2 * num_sms + col_blocks - 1) / col_blocks;
   if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
   if (chunks < 1) chunks = 1;
   const int rpb = (rows + chunks - 1) / chunks;
   dim3 grid(col_blocks, (rows + rpb - 1) / rpb);
-  rvn::rvn_colsum<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, out, rows, C, rpb);
+  rvn::rvn_colsum<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, ld, ws, counters, (__nv_bfloat16*)out, accumulate, rows, C, rpb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

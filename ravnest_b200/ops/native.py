@@ -95,8 +95,21 @@ def _wgrad(dy2, x2, weight):
     return C().gemm(dy2, True, x2, True, None, 0, None, False, 0)[0]
 
 
+def _vec_grad(param):
+    """The flat-bucket gradient view of a 1-D bf16 ParamStore leaf (bias / norm scale), or None."""
+    g = param.grad
+    if ACCUMULATE_INTO_GRAD and g is not None and g.dtype == torch.bfloat16 and g.dim() == 1 and g.is_contiguous():
+        return g
+    return None
+
+
 def _bias_grad(dy2, bias):
+    """db = column sums of dy, added straight into the gradient bucket by the reducing kernel when the leaf carries one."""
     calls['colsum'] += 1
+    g = _vec_grad(bias) if bias.dtype == torch.bfloat16 else None
+    if g is not None:
+        C().column_sum(dy2, g)
+        return None
     return C().column_sum(dy2).to(bias.dtype)
 
 
@@ -154,7 +167,7 @@ class _MLP(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2, activation):
         x2 = _as2d(x)
         act = _ACT[activation]
-        h, z = _forward_gemm(x2, w1, b1, act, True)
+        h, z = _forward_gemm(x2, w1, b1, act, 2)        # z := act'(pre-activation): the backward epilogue is one multiply
         y = _forward_gemm(h, w2, b2, 0, False)[0]
         calls['gemm_fwd'] += 2
         ctx.act = act
@@ -166,7 +179,7 @@ class _MLP(torch.autograd.Function):
     def backward(ctx, dy):
         x2, w1, b1, w2, b2, h, z = ctx.saved_tensors
         dy2 = _pad_rows(dy.reshape(-1, w2.shape[0]), w2.shape[0])
-        dz = C().gemm(dy2, False, w2, True, None, ctx.act, z, False, 0, 1)[0]      # (dy W2) * act'(z)
+        dz = C().gemm(dy2, False, w2, True, None, ctx.act, z, False, 0, 3)[0]      # (dy W2) * act'(z), z holds act'(z)
         calls['gemm_dgrad_dact'] += 1
         dw2 = _wgrad(dy2, h, w2) if ctx.needs_input_grad[3] else None
         db2 = _bias_grad(dy2, b2) if (b2 is not None and ctx.needs_input_grad[4]) else None
@@ -210,13 +223,16 @@ class _LayerNorm(torch.autograd.Function):
         y, mean, rstd = outs[0], outs[1], outs[2]
         ctx.has_res = residual is not None
         ctx.dropout_p = dropout_p
-        ctx.save_for_backward(outs[3] if len(outs) > 3 else xc, weight, mean, rstd, rng)
+        ctx.save_for_backward(outs[3] if len(outs) > 3 else xc, weight, bias, mean, rstd, rng)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        s, weight, mean, rstd, rng = ctx.saved_tensors
-        dsum, dx, dg, db = C().layernorm_bwd(dy.contiguous(), s, weight, mean, rstd, rng, ctx.dropout_p)
+        s, weight, bias, mean, rstd, rng = ctx.saved_tensors
+        gg, gb = _vec_grad(weight), _vec_grad(bias)
+        acc = gg is not None and gb is not None and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
+        dsum, dx, dg, db = C().layernorm_bwd(dy.contiguous(), s, weight, mean, rstd, rng, ctx.dropout_p,
+                                             gg if acc else None, gb if acc else None)
         calls['layernorm_bwd'] += 1
         return dx, dg, db, None, (dsum if ctx.has_res else None), None
 
@@ -326,22 +342,40 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
+def _conv_grad_acc(weight, dw_f32_ohwi):
+    """Add an fp32 OHWI weight gradient into the leaf's flat-bucket gradient (one fused cast+add launch) when the bucket view has
+    the same physical order; otherwise hand a parameter-shaped gradient back to autograd."""
+    g = weight.grad
+    if ACCUMULATE_INTO_GRAD and g is not None:
+        g_ohwi = g.permute(0, 2, 3, 1)
+        if g_ohwi.is_contiguous():
+            g_ohwi.add_(dw_f32_ohwi.view(g_ohwi.shape))
+            calls['conv_wgrad_acc'] += 1
+            return None
+    return dw_f32_ohwi.view(weight.shape[0], weight.shape[2], weight.shape[3], weight.shape[1]).to(weight.dtype).permute(0, 3, 1, 2)
+
+
 class _ConvNHWC(torch.autograd.Function):
-    """Implicit-GEMM convolution (ops/csrc/conv_sm100.cu) on NHWC activations.  Forward and the stride-1 data gradient run
-    on the tcgen05 kernel; the weight gradient (and stride-2 data gradients) still go through cuDNN — tracked in DESIGN.md."""
+    """Implicit-GEMM convolution (ops/csrc/conv_sm100.cu) on NHWC activations: forward, stride-1 data gradient and the split-K
+    weight gradient run on the tcgen05 kernels; stride-2 data gradients still go through cuDNN (tracked in DESIGN.md).
+    ``weight`` is the [O, I, kh, kw] parameter itself; stored channels_last (ParamStore does) its OHWI view is free."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, w_ohwi, bias, stride, pad, dil, relu):
+    def forward(ctx, x_nhwc, weight, bias, stride, pad, dil, relu):
+        w_ohwi = weight.permute(0, 2, 3, 1)
+        if not w_ohwi.is_contiguous():
+            w_ohwi = w_ohwi.contiguous()
+            calls['conv_weight_permute'] += 1
         y = C().conv_nhwc(x_nhwc, w_ohwi, bias, stride, pad, dil, relu, False, 0, 0)
         calls['conv_fwd'] += 1
         ctx.cfg = (stride, pad, dil, relu)
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x_nhwc, w_ohwi, y if relu else None)
+        ctx.save_for_backward(x_nhwc, weight, w_ohwi, y if relu else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, y = ctx.saved_tensors
+        x, weight, w, y = ctx.saved_tensors
         stride, pad, dil, relu = ctx.cfg
         dy = dy.contiguous()
         if relu:
@@ -353,7 +387,7 @@ class _ConvNHWC(torch.autograd.Function):
             dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2])
             calls['conv_dgrad'] += 1
         if need_dw and NATIVE_CONV_WGRAD:
-            dw = C().conv_wgrad_nhwc(dy, x, w.shape[1], w.shape[2], stride, pad, dil).to(w.dtype)
+            dw = _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, w.shape[1], w.shape[2], stride, pad, dil))
             calls['conv_wgrad'] += 1
             need_dw = False
         if need_dw or (need_dx and not native_dx) or ctx.has_bias:
@@ -361,11 +395,11 @@ class _ConvNHWC(torch.autograd.Function):
             gx, gw, gb = torch.ops.aten.convolution_backward(
                 dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), [w.shape[0]] if ctx.has_bias else None,
                 [stride, stride], [pad, pad], [dil, dil], False, [0, 0], 1, [need_dx and not native_dx, need_dw, ctx.has_bias])
-            fallbacks['conv_wgrad'] += 1
+            fallbacks['conv_dgrad_s2' if not need_dw else 'conv_wgrad'] += 1
             if need_dx and not native_dx:
                 dx = gx.permute(0, 2, 3, 1).contiguous()
             if need_dw:
-                dw = gw.permute(0, 2, 3, 1).contiguous()
+                dw = gw
             db = gb
         return dx, dw, db, None, None, None, None
 
@@ -376,17 +410,18 @@ class _Conv1x1(torch.autograd.Function):
     on the split-K wgrad kernel (pixel patches as the reduction dimension, fp32 atomics) instead of the TT GEMM."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, w2, bias):
+    def forward(ctx, x_nhwc, weight, bias):
         n, h, w, c = x_nhwc.shape
+        w2 = weight.reshape(weight.shape[0], c)
         y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, bias, 0, None, False, 0)[0]
         calls['conv1x1_as_gemm'] += 1
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x_nhwc, w2)
+        ctx.save_for_backward(x_nhwc, weight, w2)
         return y2.view(n, h, w, w2.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x, w2 = ctx.saved_tensors
+        x, weight, w2 = ctx.saved_tensors
         n, h, w, c = x.shape
         dy = dy.contiguous()
         dy2 = dy.view(n * h * w, w2.shape[0])
@@ -395,7 +430,7 @@ class _Conv1x1(torch.autograd.Function):
             dx = C().gemm(dy2, False, w2, True, None, 0, None, False, 0)[0].view(n, h, w, c)
             calls['gemm_dgrad'] += 1
         if ctx.needs_input_grad[1]:
-            dw = C().conv_wgrad_nhwc(dy, x, 1, 1, 1, 0, 1).view(w2.shape[0], c).to(w2.dtype)
+            dw = _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, 1, 1, 1, 0, 1))
             calls['conv_wgrad'] += 1
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy2, w2)
@@ -424,15 +459,12 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
             x = x[:, :, ::sh, ::sw]
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight.reshape(cout, cin), bias)      # zero-copy NHWC view in, NHWC out
+        y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight, bias)           # zero-copy NHWC view in, NHWC out
         return y.permute(0, 3, 1, 2)                                      # NCHW-shaped, channels_last-strided
     if base_ok and sh == sw and ph == pw and dh == dw_ and kh == kw and sh in (1, 2) and IMPLICIT_GEMM_CONV:
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        w_ohwi = weight.permute(0, 2, 3, 1)
-        if not w_ohwi.is_contiguous():
-            w_ohwi = w_ohwi.contiguous()                                  # free when the module is channels_last
-        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), w_ohwi, bias, sh, ph, dh, False)
+        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), weight, bias, sh, ph, dh, False)
         return y.permute(0, 3, 1, 2)
     fallbacks['conv2d'] += 1
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
@@ -443,29 +475,35 @@ NATIVE_CONV_WGRAD = True
 
 
 class _BatchNormAct(torch.autograd.Function):
-    """y = relu(BN(x) + residual) on NHWC activations (ops/csrc/norm_nhwc.cu)."""
+    """y = relu(BN(x) + residual) on NHWC activations (ops/csrc/norm_nhwc.cu).  gamma / beta / running statistics are consumed in
+    the module's dtype; the finalize kernel updates the running statistics and ``num_batches_tracked``; the parameter gradients
+    are accumulated straight into the flat gradient bucket when the leaves carry one (no cast / add launches per layer)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu, eps):
-        gamma, beta = weight.float(), bias.float()
-        y, mean, invstd = C().batchnorm_fwd(x, residual, gamma, beta, None, None, eps, relu, True)
+    def forward(ctx, x, weight, bias, residual, relu, eps, running_mean, running_var, batches_tracked, momentum):
+        y, mean, invstd = C().batchnorm_fwd(x, residual, weight, bias, None, None, eps, relu, True, running_mean, running_var,
+                                            batches_tracked, momentum)
         calls['batchnorm_fwd'] += 1
         ctx.relu, ctx.has_res = relu, residual is not None
-        ctx.save_for_backward(x, y if relu else None, gamma, mean, invstd)
-        ctx.mark_non_differentiable(mean, invstd)
-        return y, mean, invstd
+        ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
+        return y
 
     @staticmethod
-    def backward(ctx, dy, _dm, _di):
-        x, y, gamma, mean, invstd = ctx.saved_tensors
-        dx, dres, dgamma, dbeta = C().batchnorm_bwd(dy.contiguous(), y, x, gamma, mean, invstd, ctx.relu, ctx.has_res and ctx.relu)
+    def backward(ctx, dy):
+        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        gg, gb = weight.grad, bias.grad
+        acc = (ACCUMULATE_INTO_GRAD and gg is not None and gb is not None and gg.dtype == weight.dtype and gb.dtype == weight.dtype
+               and gg.is_contiguous() and gb.is_contiguous() and ctx.needs_input_grad[1] and ctx.needs_input_grad[2])
+        dx, dres, dgamma, dbeta = C().batchnorm_bwd(dy.contiguous(), y, x, weight, mean, invstd, ctx.relu, ctx.has_res and ctx.relu,
+                                                    gg if acc else None, gb if acc else None)
         calls['batchnorm_bwd'] += 1
         if ctx.has_res and not ctx.relu:
             dres = dy
-        return dx, dgamma.to(torch.bfloat16), dbeta.to(torch.bfloat16), (dres if ctx.has_res else None), None, None
+        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None
 
 
-def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5):
+def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5,
+                   num_batches_tracked=None):
     """x / residual / result: NCHW-shaped channels_last bf16 tensors.  Training mode updates the running statistics."""
     n, c, h, w = x.shape
     if not x.is_contiguous(memory_format=torch.channels_last):
@@ -477,16 +515,13 @@ def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, re
             residual = residual.contiguous(memory_format=torch.channels_last)
         r2 = residual.permute(0, 2, 3, 1)
     if training:
-        y2, mean, invstd = _BatchNormAct.apply(x2, weight, bias, r2, relu, eps)
-        if running_mean is not None:
-            with torch.no_grad():
-                count = x.numel() // c
-                var = (1.0 / (invstd * invstd) - eps).clamp_min_(0.0)
-                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
-                running_var.mul_(1 - momentum).add_((var * (count / max(count - 1, 1))).to(running_var.dtype), alpha=momentum)
+        y2 = _BatchNormAct.apply(x2, weight, bias, r2, relu, eps, running_mean, running_var,
+                                 num_batches_tracked if running_mean is not None else None, momentum)
+        if running_mean is None and num_batches_tracked is not None:
+            num_batches_tracked.add_(1)
     else:
         invstd = torch.rsqrt(running_var.float() + eps)
-        y2 = C().batchnorm_fwd(x2, r2, weight.float(), bias.float(), running_mean.float(), invstd, eps, relu, False)[0]
+        y2 = C().batchnorm_fwd(x2, r2, weight, bias, running_mean.float(), invstd, eps, relu, False, None, None, None, 0.0)[0]
         calls['batchnorm_eval'] += 1
     return y2.permute(0, 3, 1, 2)
 

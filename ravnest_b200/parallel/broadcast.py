@@ -44,8 +44,8 @@ class WeightBroadcaster:
         peer_flat = self.sym.peer_tensor(self.leader)
         n = 0
         with torch.no_grad():
-            for name, off, numel, shape, leaf in zip(st.names, st.offsets, st.numels, st.shapes, slot.leaves):
-                src = peer_flat[off:off + numel].view(shape)
+            for k, (name, shape, leaf) in enumerate(zip(st.names, st.shapes, slot.leaves)):
+                src = st.view_of(peer_flat, k)
                 if len(shape) == 2 and shape[1] % 8 == 0 and st.compute_dtype == torch.bfloat16 and not name.endswith('embeddings.weight'):
                     native.arm_peer_weight(leaf, src)          # consumed (and landed locally) by the first GEMM that uses it
                     n += 1

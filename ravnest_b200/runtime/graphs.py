@@ -110,8 +110,8 @@ class GraphedStage:
         # private weight copy + leaves that accumulate into the stage's flat gradient bucket
         self.wbuf = torch.empty_like(store.current.flat)
         self.params = {}
-        for name, o, n, s, g in zip(store.names, store.offsets, store.numels, store.shapes, store.grad_views):
-            leaf = self.wbuf[o:o + n].view(s).detach().requires_grad_(True)
+        for k, (name, g) in enumerate(zip(store.names, store.grad_views)):
+            leaf = store.view_of(self.wbuf, k).detach().requires_grad_(True)
             leaf.grad = g
             self.params[name] = leaf
 

@@ -53,8 +53,11 @@ class ParamStore:
         self.total = max(off, align)
         self.master = torch.zeros(self.total, dtype=master_dtype, device=self.device)
         self.grad = torch.zeros(self.total, dtype=self.compute_dtype, device=self.device)
-        self.master_views = [self.master[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
-        self.grad_views = [self.grad[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+        # spatial convolution weights live in OHWI (channels_last) order inside every flat buffer: the implicit-GEMM kernels read
+        # them K-major without a per-step permute copy and their OHWI weight gradients add into the bucket as a dense stream
+        self.channels_last = [len(s) == 4 and s[2] * s[3] > 1 for s in self.shapes]
+        self.master_views = self.views_of(self.master)
+        self.grad_views = self.views_of(self.grad)
         with torch.no_grad():
             for view, (_, p) in zip(self.master_views, named):
                 view.copy_(p.detach().to(self.device, master_dtype))
@@ -71,11 +74,22 @@ class ParamStore:
         self.bind_module()
 
     # ------------------------------------------------------------------ construction helpers
+    def view_of(self, flat: torch.Tensor, k: int) -> torch.Tensor:
+        """Parameter ``k`` as a (possibly channels_last-strided) view of a flat buffer laid out like this store."""
+        o, n, s = self.offsets[k], self.numels[k], self.shapes[k]
+        seg = flat[o:o + n]
+        if self.channels_last[k]:
+            return seg.view(s[0], s[2], s[3], s[1]).permute(0, 3, 1, 2)
+        return seg.view(s)
+
+    def views_of(self, flat: torch.Tensor) -> List[torch.Tensor]:
+        return [self.view_of(flat, k) for k in range(len(self.shapes))]
+
     def _make_slot(self, index: int) -> Slot:
         flat = torch.zeros(self.total, dtype=self.compute_dtype, device=self.device)
         leaves, pdict = [], OrderedDict()
-        for name, o, n, s, g in zip(self.names, self.offsets, self.numels, self.shapes, self.grad_views):
-            leaf = flat[o:o + n].view(s).detach().requires_grad_(True)
+        for k, (name, g) in enumerate(zip(self.names, self.grad_views)):
+            leaf = self.view_of(flat, k).detach().requires_grad_(True)
             leaf.grad = g            # every version accumulates into the one flat gradient buffer
             leaves.append(leaf)
             pdict[name] = leaf
@@ -131,15 +145,15 @@ class ParamStore:
 
     def attach_master_grads(self) -> None:
         flat = self.master_grad()
-        for p, o, n, s in zip(self.master_params, self.offsets, self.numels, self.shapes):
-            p.grad = flat[o:o + n].view(s)
+        for k, p in enumerate(self.master_params):
+            p.grad = self.view_of(flat, k)
 
     def rebind_grad(self, new_flat: torch.Tensor) -> None:
         """Move the gradient bucket into externally allocated (e.g. symmetric / peer-mapped) memory."""
         assert new_flat.numel() == self.total and new_flat.dtype == self.grad.dtype
         new_flat.copy_(self.grad)
         self.grad = new_flat
-        self.grad_views = [self.grad[o:o + n].view(s) for o, n, s in zip(self.offsets, self.numels, self.shapes)]
+        self.grad_views = self.views_of(self.grad)
         for slot in self.slots:
             for leaf, g in zip(slot.leaves, self.grad_views):
                 leaf.grad = g
