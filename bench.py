@@ -34,6 +34,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--update-frequency', type=int, default=None)
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
+    ap.add_argument('--proportions', default=None, help='comma-separated parameter shares per stage (reference policy) instead of the compute-balanced plan')
     ap.add_argument('--no-graphs', action='store_true', help='disable CUDA-graph capture of the stage step')
     ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
     return ap.parse_args()
@@ -220,11 +221,11 @@ def main():
     model, ex_args, ex_kwargs, batch = build_model(args)
     if rank == 0:
         os.makedirs(home, exist_ok=True)
-        props = None
-        if args.model == 'bert' and stages == 2:
-            props = [0.67, 0.33]            # root: embeddings + 7 layers; leaf: 5 layers + the 30522-wide MLM head (balanced step time)
+        # stages are balanced by the planner's step-time estimate (balance='compute'), not by parameter bytes
+        props = [float(v) for v in args.proportions.split(',')] if args.proportions else None
         rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
-                      node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props)
+                      node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props,
+                      balance='params' if props else 'compute')
     if world > 1:
         dist.barrier(group=gloo)
     del model

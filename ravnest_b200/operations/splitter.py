@@ -176,6 +176,85 @@ def choose_split_points(gm: fx.GraphModule, proportions: Sequence[float]) -> Lis
     return boundaries
 
 
+# ------------------------------------------------------------------------------------------------
+# compute-balanced planning (B200 grids: every stage owns an identical GPU, so what must be equal is
+# the stage's STEP TIME, not its parameter bytes — ResNet-50's first half of the parameters is ~95 % of
+# its work).  The reference only knows the parameter-share policy above (operations/utils.py:430-435).
+# ------------------------------------------------------------------------------------------------
+_PEAK_FLOPS = 8.0e14        # sustained dense bf16 of one B200 as seen by mid-sized GEMM / conv tiles
+_HBM_BPS = 6.4e12           # measured copy bandwidth (MEASURED_PEAKS.json)
+_LAUNCH_S = 3.0e-6          # per-kernel floor
+
+
+class _ByteCounter(torch.utils._python_dispatch.TorchDispatchMode):
+    """Counts aten calls and the bytes of the tensors they produce (as 2-byte elements: the engine computes in bf16)."""
+
+    def __init__(self):
+        super().__init__()
+        self.ops = 0
+        self.bytes = 0
+
+    def __torch_dispatch__(self, func, types, args=(), kwargs=None):
+        out = func(*args, **(kwargs or {}))
+        self.ops += 1
+        for t in (out if isinstance(out, (tuple, list)) else (out,)):
+            if isinstance(t, torch.Tensor) and t.is_floating_point():
+                self.bytes += t.numel() * 2
+        return out
+
+
+class _CostProp(fx.Interpreter):
+    def run_node(self, n: fx.Node) -> Any:
+        from torch.utils.flop_counter import FlopCounterMode
+        if n.op not in ('call_module', 'call_function', 'call_method'):
+            return super().run_node(n)
+        with FlopCounterMode(display=False) as fc, _ByteCounter() as bc:
+            out = super().run_node(n)
+        flops = float(fc.get_total_flops())
+        # forward + backward: 3x the GEMM work, ~3x the elementwise traffic (read x, write y, read dy, write dx ...)
+        n.meta['ravnest_cost'] = 3.0 * flops / _PEAK_FLOPS + 3.0 * bc.bytes / _HBM_BPS + 2.0 * bc.ops * _LAUNCH_S
+        n.meta['ravnest_flops'] = flops
+        return out
+
+
+def estimate_costs(gm: fx.GraphModule, inputs: Sequence[Any]) -> Dict[fx.Node, float]:
+    """Per-node step-time estimate (seconds, forward + backward on one B200) from one instrumented run on the example inputs."""
+    was_training = gm.training
+    gm.eval()
+    try:
+        with torch.no_grad():
+            _CostProp(gm).run(*inputs)
+    finally:
+        gm.train(was_training)
+    return {n: float(n.meta.get('ravnest_cost', 0.0)) for n in gm.graph.nodes}
+
+
+def choose_split_points_by_cost(gm: fx.GraphModule, proportions: Sequence[float], costs: Dict[fx.Node, float]) -> List[fx.Node]:
+    """First node of stage 1..n-1 such that stage i's estimated step time is ``proportions[i]`` of the total."""
+    n_stages = len(proportions)
+    if n_stages <= 1:
+        return []
+    nodes = _compute_nodes(gm)
+    if len(nodes) < n_stages:
+        raise ValueError('model has too few operations ({}) for {} stages'.format(len(nodes), n_stages))
+    total = sum(costs.get(n, 0.0) for n in nodes) or 1.0
+    share = sum(proportions)
+    targets, acc = [], 0.0
+    for p in proportions[:-1]:
+        acc += p / share
+        targets.append(acc * total)
+    prefix = [0.0]
+    for n in nodes:
+        prefix.append(prefix[-1] + costs.get(n, 0.0))
+    cuts: List[int] = []
+    for t in targets:
+        lo = (cuts[-1] + 1) if cuts else 1
+        hi = len(nodes) - (n_stages - 1 - len(cuts))          # leave one node for every later stage
+        best = min(range(lo, hi + 1), key=lambda i: abs(prefix[i] - t))
+        cuts.append(best)
+    return [nodes[c] for c in cuts]
+
+
 def _compute_nodes(gm: fx.GraphModule) -> List[fx.Node]:
     return [n for n in gm.graph.nodes if n.op in ('call_module', 'call_function', 'call_method')]
 
@@ -234,6 +313,7 @@ class SplitResult:
         self.model_input_names = model_input_names
         self.model_inputs_template = model_inputs_template
         self.model_input_meta = model_input_meta
+        self.stage_costs: Optional[List[float]] = None       # balance='compute': estimated seconds per stage step
 
     def run_local(self, *inputs):
         """Chain the stages in-process (used for the planner's self-check and tests)."""
@@ -353,18 +433,26 @@ def nudge_proportions(proportions: List[float]) -> List[float]:
 
 
 def split_model(model: nn.Module, proportions: Sequence[float], example_args: Sequence = (),
-                example_kwargs: Optional[Dict] = None, check: bool = True) -> SplitResult:
-    """Trace + threshold policy + carve.  ``check`` runs the chained stages once and compares
-    against the traced module on the example inputs (the reference only checks "does not raise")."""
+                example_kwargs: Optional[Dict] = None, check: bool = True, balance: str = 'params') -> SplitResult:
+    """Trace + split policy + carve.  ``balance='params'`` is the reference's parameter-share threshold policy;
+    ``balance='compute'`` makes ``proportions`` shares of the estimated step time (``estimate_costs``).  ``check`` runs the
+    chained stages once and compares against the traced module on the example inputs (the reference only checks "does not raise")."""
+    assert balance in ('params', 'compute')
     example_kwargs = dict(example_kwargs or {})
     gm, input_names = trace_model(model, example_args, example_kwargs)
     flat_inputs = list(example_args) + [example_kwargs[k] for k in input_names[len(example_args):]]
     propagate_meta(gm, flat_inputs)
+    costs = estimate_costs(gm, flat_inputs) if balance == 'compute' else None
     attempt = list(proportions)
     last_err = None
     for _ in range(2):
         try:
-            result = split_graph(gm, choose_split_points(gm, attempt), input_names)
+            points = choose_split_points(gm, attempt) if costs is None else choose_split_points_by_cost(gm, attempt, costs)
+            result = split_graph(gm, points, input_names)
+            if costs is not None:       # estimated step time per stage (seconds), for the plan file / logs
+                order = _compute_nodes(gm)
+                edges = [0] + [order.index(b) for b in points] + [len(order)]
+                result.stage_costs = [sum(costs.get(n, 0.0) for n in order[a:b]) for a, b in zip(edges[:-1], edges[1:])]
             if check:
                 was = gm.training
                 gm.eval()

@@ -213,11 +213,11 @@ def write_split(result: SplitResult, cluster_path: str, node_paths: Sequence[str
 
 
 def split_model_equal(model=None, num_splits=None, proportions=None, example_args=(), example_kwargs=None,
-                      cluster_path=None, node_paths=None, model_input_node=None) -> SplitResult:
+                      cluster_path=None, node_paths=None, model_input_node=None, balance='params') -> SplitResult:
     """Split + self-check + write artefacts (reference operations/utils.py:265-349)."""
     if proportions is None:
-        proportions = equal_proportions(num_splits)
-    result = split_model(model, proportions, example_args, example_kwargs or {}, check=True)
+        proportions = equal_proportions(num_splits) if balance == 'params' else [1.0 / num_splits] * num_splits
+    result = split_model(model, proportions, example_args, example_kwargs or {}, check=True, balance=balance)
     write_split(result, cluster_path, node_paths)
     return result
 
@@ -251,7 +251,7 @@ def default_gpu_configs(n: int, base_port: int = 8080, host: str = '127.0.0.1') 
 
 
 def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False, *, topology=None,
-               proportions=None, base_dir=None, node_configs=None, seed=42, verbose=False):
+               proportions=None, balance=None, base_dir=None, node_configs=None, seed=42, verbose=False):
     """Plan the whole job: form clusters, split the model per cluster, derive DP rings and write
     ``node_data/cluster_<c>/<ip:port>/{submod.pt, submod_<k>_{input,output}.pkl, model_inputs.pkl, plan.json}``
     plus ``node_data/nodes/node_<id>.json`` (reference operations/utils.py:380-547).
@@ -276,10 +276,15 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
     for cluster in clusters:
         chain = cluster.ordered_nodes()
         _wire_chain(chain)
-        props = list(proportions) if proportions is not None and len(proportions) == len(chain) else equal_proportions(len(chain))
-        split_model_equal(model=model, proportions=props, example_args=example_args, example_kwargs=example_kwargs,
-                          cluster_path=os.path.join(root, 'cluster_{}'.format(cluster.cid)),
-                          node_paths=[n.address for n in chain], model_input_node=chain[0].address)
+        # reference policy: parameter shares (heterogeneous hosts are sized by RAM).  GPU grids are homogeneous, so unless the
+        # caller pins ``proportions`` the stages are balanced by estimated step time instead (balance='compute').
+        mode = balance or ('compute' if (topology is not None and proportions is None) else 'params')
+        props = list(proportions) if proportions is not None and len(proportions) == len(chain) else None
+        res = split_model_equal(model=model, num_splits=len(chain), proportions=props, example_args=example_args,
+                                example_kwargs=example_kwargs, cluster_path=os.path.join(root, 'cluster_{}'.format(cluster.cid)),
+                                node_paths=[n.address for n in chain], model_input_node=chain[0].address, balance=mode)
+        if verbose and res.stage_costs:
+            print('cluster', cluster.cid, 'estimated stage step times (ms):', [round(1e3 * c, 3) for c in res.stage_costs])
 
     home = os.path.dirname(root.rstrip('/')) or '.'
     for node in pool:

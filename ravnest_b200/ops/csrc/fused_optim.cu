@@ -142,6 +142,50 @@ __device__ __forceinline__ void reduced_grad4(const PeerPtrs& pp, size_t i, floa
   for (int j = 0; j < 4; ++j) g[j] *= scale;
 }
 
+// U vectors of 4 elements per thread (idx = i0 + u * step), ALL of one peer's loads issued before any is consumed: peer memory
+// is ~2.5 us away and is not cached in the local L2, so link bandwidth = bytes in flight / latency.  Measured on 2 GPUs with one
+// 8-byte load per thread per peer: 172 GB/s; U = 4 puts 148 x 512 x 32 B = 2.4 MB in flight per peer.
+constexpr int GRAD_U = 4;
+template <typename G>
+__device__ __forceinline__ void reduced_grad_tile(const PeerPtrs& pp, size_t i0, size_t step, size_t end, float scale,
+                                                  float (&g)[GRAD_U][4]) {
+  const G* own = static_cast<const G*>(pp.grad[pp.rank]);
+#pragma unroll
+  for (int u = 0; u < GRAD_U; ++u) {
+    const size_t idx = i0 + u * step;
+    if (idx < end) {
+      load4<G>(own, idx, g[u]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[u][j] = 0.f;
+    }
+  }
+  for (int p = 1; p < pp.n; ++p) {                       // start at rank+1 so replicas spread over the links
+    int q = pp.rank + p;
+    if (q >= pp.n) q -= pp.n;
+    const G* src = static_cast<const G*>(pp.grad[q]);
+    float t[GRAD_U][4];
+#pragma unroll
+    for (int u = 0; u < GRAD_U; ++u) {
+      const size_t idx = i0 + u * step;
+      if (idx < end) {
+        load4<G>(src, idx, t[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GRAD_U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[u][j] += t[u][j];
+  }
+#pragma unroll
+  for (int u = 0; u < GRAD_U; ++u)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[u][j] *= scale;
+}
+
 // ------------------------------------------------------------------------------------------------ SGD / Adam
 // kind: 0 = SGD(momentum, wd, nesterov), 1 = Adam (L2 wd) / AdamW (decoupled wd)
 template <typename G, typename W, int KIND>
@@ -150,10 +194,19 @@ __global__ void __launch_bounds__(512) rvn_fused_allreduce_update(PeerPtrs pp, O
                                                                   W* __restrict__ w_out, G* __restrict__ own_grad_zero, size_t n,
                                                                   uint32_t epoch, uint32_t* done_counter) {
   cross_gpu_barrier(pp, 0, epoch);
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
-  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+  const size_t step = static_cast<size_t>(blockDim.x) * 4;
+  const size_t tile = step * GRAD_U;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * tile; base < n; base += static_cast<size_t>(gridDim.x) * tile) {
+   const size_t i0 = base + threadIdx.x * 4;
+   float gt[GRAD_U][4];
+   reduced_grad_tile<G>(pp, i0, step, n, a.grad_scale, gt);
+#pragma unroll
+   for (int u = 0; u < GRAD_U; ++u) {
+    const size_t i = i0 + u * step;
+    if (i >= n) break;
     float g[4], w[4];
-    reduced_grad4<G>(pp, i, a.grad_scale, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = gt[u][j];
     load4<float>(master, i, w);
     if (KIND == 0) {
       float mom[4];
@@ -187,6 +240,7 @@ __global__ void __launch_bounds__(512) rvn_fused_allreduce_update(PeerPtrs pp, O
     }
     store4<float>(master, i, w);
     store4<W>(w_out, i, w);
+   }
   }
   exit_barrier(pp, MAX_PEERS + 1, epoch, done_counter);
   (void)own_grad_zero;
@@ -206,9 +260,18 @@ __global__ void __launch_bounds__(512) rvn_fused_allreduce_lamb1(PeerPtrs pp, Op
   const int param = chunk_param[blockIdx.x];
   const size_t s = chunk_start[blockIdx.x], e = chunk_end[blockIdx.x];
   float wsq = 0.f, usq = 0.f;
-  for (size_t i = s + threadIdx.x * 4; i < e; i += blockDim.x * 4) {
+  const size_t step = static_cast<size_t>(blockDim.x) * 4;
+  for (size_t base = s; base < e; base += step * GRAD_U) {
+   const size_t i0 = base + threadIdx.x * 4;
+   float gt[GRAD_U][4];
+   reduced_grad_tile<G>(pp, i0, step, e, a.grad_scale, gt);
+#pragma unroll
+   for (int u = 0; u < GRAD_U; ++u) {
+    const size_t i = i0 + u * step;
+    if (i >= e) break;
     float g[4], w[4], m1[4], v1[4];
-    reduced_grad4<G>(pp, i, a.grad_scale, g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] = gt[u][j];
     load4<float>(master, i, w);
     load4<float>(m, i, m1);
     load4<float>(v, i, v1);
@@ -224,6 +287,7 @@ __global__ void __launch_bounds__(512) rvn_fused_allreduce_lamb1(PeerPtrs pp, Op
     }
     store4<float>(m, i, m1);
     store4<float>(v, i, v1);
+   }
   }
   __shared__ float red[2][16];
 #pragma unroll
@@ -276,12 +340,19 @@ __global__ void __launch_bounds__(512) rvn_fused_average(PeerPtrs pp, float* __r
                                                          uint32_t epoch, uint32_t* done_counter) {
   cross_gpu_barrier(pp, 0, epoch);
   const float inv = 1.f / pp.n;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
-  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-    float g[4];
-    reduced_grad4<float>(pp, i, inv, g);
-    store4<float>(master_out, i, g);
-    store4<W>(w_out, i, g);
+  const size_t step = static_cast<size_t>(blockDim.x) * 4;
+  const size_t tile = step * GRAD_U;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * tile; base < n; base += static_cast<size_t>(gridDim.x) * tile) {
+    const size_t i0 = base + threadIdx.x * 4;
+    float gt[GRAD_U][4];
+    reduced_grad_tile<float>(pp, i0, step, n, inv, gt);
+#pragma unroll
+    for (int u = 0; u < GRAD_U; ++u) {
+      const size_t i = i0 + u * step;
+      if (i >= n) break;
+      store4<float>(master_out, i, gt[u]);
+      store4<W>(w_out, i, gt[u]);
+    }
   }
   exit_barrier(pp, MAX_PEERS + 1, epoch, done_counter);
 }

@@ -142,3 +142,27 @@ def test_grid_topology_plan(workdir):
     assert [m['rank'] for m in metas] == [0, 0, 1, 1] and all(m['ring_size'] == 2 for m in metas)
     assert metas[0]['dp_peer_node_ids'] == [0, 2] and metas[1]['dp_peer_node_ids'] == [1, 3]
     assert list(metas[0]['param_addresses'][0]) == ['127.0.0.1:8082']          # same stage of the next replica
+
+
+def test_compute_balanced_split_equalises_estimated_step_time():
+    """B200 grids balance stages by estimated step time: ResNet-50's parameter-share split puts ~95 % of the work in stage 0."""
+    import torchvision
+    from ravnest_b200.operations.splitter import split_model
+    torch.manual_seed(0)
+    model = torchvision.models.resnet50(num_classes=10)
+    x = torch.randn(2, 3, 64, 64)
+    by_cost = split_model(model, [0.25] * 4, (x,), balance='compute')
+    costs = by_cost.stage_costs
+    assert len(costs) == 4 and max(costs) / min(costs) < 1.35
+    params = [sum(p.numel() for p in st.module.parameters()) for st in by_cost.stages]
+    assert params[0] < params[-1] / 4                      # early stages: few parameters, most of the activation work
+    by_params = split_model(model, [0.2, 0.2, 0.2, 0.4], (x,), balance='params')
+    assert by_params.stage_costs is None
+    # both plans compute the same function
+    model.eval()
+    with torch.no_grad():
+        ref = model(x)
+        for plan in (by_cost, by_params):
+            for st in plan.stages:
+                st.module.eval()
+            assert torch.allclose(plan.run_local(x), ref, atol=1e-5)
