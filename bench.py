@@ -34,6 +34,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--update-frequency', type=int, default=None)
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
+    ap.add_argument('--balance', default='measured', choices=['measured', 'compute', 'params'], help='stage-balancing policy of the planner')
     ap.add_argument('--proportions', default=None, help='comma-separated parameter shares per stage (reference policy) instead of the compute-balanced plan')
     ap.add_argument('--no-graphs', action='store_true', help='disable CUDA-graph capture of the stage step')
     ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
@@ -223,9 +224,11 @@ def main():
         os.makedirs(home, exist_ok=True)
         # stages are balanced by the planner's step-time estimate (balance='compute'), not by parameter bytes
         props = [float(v) for v in args.proportions.split(',')] if args.proportions else None
+        ex_tensors = [t for t in list(ex_args) + list(ex_kwargs.values()) if hasattr(t, 'shape')]
+        cost_scale = batch / max(1, ex_tensors[0].shape[0])          # the plan is traced on a 2-sample example of the real shape
         rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
                       node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props,
-                      balance='params' if props else 'compute')
+                      balance='params' if props else args.balance, cost_scale=cost_scale, plan_device=dev)
     if world > 1:
         dist.barrier(group=gloo)
     del model

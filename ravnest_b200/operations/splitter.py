@@ -181,9 +181,12 @@ def choose_split_points(gm: fx.GraphModule, proportions: Sequence[float]) -> Lis
 # the stage's STEP TIME, not its parameter bytes — ResNet-50's first half of the parameters is ~95 % of
 # its work).  The reference only knows the parameter-share policy above (operations/utils.py:430-435).
 # ------------------------------------------------------------------------------------------------
-_PEAK_FLOPS = 8.0e14        # sustained dense bf16 of one B200 as seen by mid-sized GEMM / conv tiles
+# Calibrated on the measured single-GPU steps (profiles/RESULTS_r1.md): ResNet-50 batch 100 = 16.6 ms for 0.82 TFLOP forward and
+# 7.5 GB of produced activations; BERT-base 8 x 512 = 8.3 ms for 0.24 TFLOP and 2.5 GB.
+_PEAK_FLOPS = 6.0e14        # dense bf16 as sustained by the mid-sized GEMM / implicit-GEMM tiles of these models (fwd + bwd = 3x fwd flops)
 _HBM_BPS = 6.4e12           # measured copy bandwidth (MEASURED_PEAKS.json)
-_LAUNCH_S = 3.0e-6          # per-kernel floor
+_ACT_PASSES = 9.0           # HBM passes per produced activation byte over forward + backward (norm / activation / residual traffic)
+_LAUNCH_S = 1.0e-6          # per-kernel floor inside a CUDA graph
 
 
 class _ByteCounter(torch.utils._python_dispatch.TorchDispatchMode):
@@ -204,6 +207,10 @@ class _ByteCounter(torch.utils._python_dispatch.TorchDispatchMode):
 
 
 class _CostProp(fx.Interpreter):
+    def __init__(self, gm, scale: float = 1.0):
+        super().__init__(gm)
+        self.scale = scale
+
     def run_node(self, n: fx.Node) -> Any:
         from torch.utils.flop_counter import FlopCounterMode
         if n.op not in ('call_module', 'call_function', 'call_method'):
@@ -212,21 +219,75 @@ class _CostProp(fx.Interpreter):
             out = super().run_node(n)
         flops = float(fc.get_total_flops())
         # forward + backward: 3x the GEMM work, ~3x the elementwise traffic (read x, write y, read dy, write dx ...)
-        n.meta['ravnest_cost'] = 3.0 * flops / _PEAK_FLOPS + 3.0 * bc.bytes / _HBM_BPS + 2.0 * bc.ops * _LAUNCH_S
+        n.meta['ravnest_cost'] = self.scale * (3.0 * flops / _PEAK_FLOPS + _ACT_PASSES * bc.bytes / _HBM_BPS) + 2.0 * bc.ops * _LAUNCH_S
         n.meta['ravnest_flops'] = flops
         return out
 
 
-def estimate_costs(gm: fx.GraphModule, inputs: Sequence[Any]) -> Dict[fx.Node, float]:
-    """Per-node step-time estimate (seconds, forward + backward on one B200) from one instrumented run on the example inputs."""
+def estimate_costs(gm: fx.GraphModule, inputs: Sequence[Any], scale: float = 1.0) -> Dict[fx.Node, float]:
+    """Per-node step-time estimate (seconds, forward + backward on one B200) from one instrumented run on the example inputs.
+    ``scale`` = training batch / example batch when the plan is made on a smaller example than the job will run."""
     was_training = gm.training
     gm.eval()
     try:
         with torch.no_grad():
-            _CostProp(gm).run(*inputs)
+            _CostProp(gm, scale).run(*inputs)
     finally:
         gm.train(was_training)
     return {n: float(n.meta.get('ravnest_cost', 0.0)) for n in gm.graph.nodes}
+
+
+def measure_costs(gm: fx.GraphModule, inputs: Sequence[Any], device, dtype=torch.bfloat16, batch_scale: int = 1,
+                  iters: int = 3) -> Dict[fx.Node, float]:
+    """Profile-guided planning: run a copy of the traced model on ``device`` in the compute dtype with the REAL per-replica batch
+    (the example tiled ``batch_scale`` times along dim 0) and time every node's forward with CUDA events on the native kernels.
+    The step-time share of a node is taken as proportional to its forward time (backward ~ 2x forward for GEMM, conv, norm and
+    attention alike), which is what the split needs."""
+    import copy
+    dev = torch.device(device)
+    twin = copy.deepcopy(gm).to(dev)
+    for p in list(twin.parameters()) + list(twin.buffers()):
+        if p.is_floating_point():
+            p.data = p.data.to(dtype)
+    twin.train()
+
+    def stage(t):
+        if not isinstance(t, torch.Tensor):
+            return t
+        if batch_scale > 1 and t.dim() >= 1:
+            t = t.repeat(batch_scale, *([1] * (t.dim() - 1)))
+        t = t.to(dev)
+        if t.is_floating_point():
+            t = t.to(dtype)
+            if t.dim() == 4:
+                t = t.contiguous(memory_format=torch.channels_last)
+        return t
+
+    args = [stage(t) for t in inputs]
+    samples: Dict[str, List[float]] = {}
+
+    class _Timed(fx.Interpreter):
+        def run_node(self, n: fx.Node) -> Any:
+            if n.op not in ('call_module', 'call_function', 'call_method'):
+                return super().run_node(n)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = super().run_node(n)
+            e1.record()
+            pending.append((n.name, e0, e1))
+            return out
+
+    with torch.no_grad():
+        for it in range(iters + 2):
+            pending: List[Tuple[str, Any, Any]] = []
+            _Timed(twin).run(*args)
+            torch.cuda.synchronize(dev)
+            if it >= 2:                                  # two warm-up passes (descriptor caches, cuDNN heuristics, allocator)
+                for name, e0, e1 in pending:
+                    samples.setdefault(name, []).append(e0.elapsed_time(e1) * 1e-3)
+    del twin
+    by_name = {k: sorted(v)[len(v) // 2] for k, v in samples.items()}
+    return {n: 3.0 * by_name.get(n.name, 0.0) for n in gm.graph.nodes}
 
 
 def choose_split_points_by_cost(gm: fx.GraphModule, proportions: Sequence[float], costs: Dict[fx.Node, float]) -> List[fx.Node]:
@@ -433,16 +494,24 @@ def nudge_proportions(proportions: List[float]) -> List[float]:
 
 
 def split_model(model: nn.Module, proportions: Sequence[float], example_args: Sequence = (),
-                example_kwargs: Optional[Dict] = None, check: bool = True, balance: str = 'params') -> SplitResult:
+                example_kwargs: Optional[Dict] = None, check: bool = True, balance: str = 'params',
+                cost_scale: float = 1.0, device=None, dtype=torch.bfloat16) -> SplitResult:
     """Trace + split policy + carve.  ``balance='params'`` is the reference's parameter-share threshold policy;
-    ``balance='compute'`` makes ``proportions`` shares of the estimated step time (``estimate_costs``).  ``check`` runs the
+    ``balance='compute'`` makes ``proportions`` shares of the estimated step time (``estimate_costs``); ``balance='measured'``
+    times every node on ``device`` with the native kernels at the real batch (``measure_costs``; falls back to the estimate
+    when no GPU is visible).  ``check`` runs the
     chained stages once and compares against the traced module on the example inputs (the reference only checks "does not raise")."""
-    assert balance in ('params', 'compute')
+    assert balance in ('params', 'compute', 'measured')
     example_kwargs = dict(example_kwargs or {})
     gm, input_names = trace_model(model, example_args, example_kwargs)
     flat_inputs = list(example_args) + [example_kwargs[k] for k in input_names[len(example_args):]]
     propagate_meta(gm, flat_inputs)
-    costs = estimate_costs(gm, flat_inputs) if balance == 'compute' else None
+    costs = None
+    if balance == 'measured' and torch.cuda.is_available():
+        costs = measure_costs(gm, flat_inputs, device or torch.device('cuda', torch.cuda.current_device()), dtype,
+                              batch_scale=max(1, int(round(cost_scale))))
+    elif balance in ('compute', 'measured'):
+        costs = estimate_costs(gm, flat_inputs, cost_scale)
     attempt = list(proportions)
     last_err = None
     for _ in range(2):

@@ -213,11 +213,12 @@ def write_split(result: SplitResult, cluster_path: str, node_paths: Sequence[str
 
 
 def split_model_equal(model=None, num_splits=None, proportions=None, example_args=(), example_kwargs=None,
-                      cluster_path=None, node_paths=None, model_input_node=None, balance='params') -> SplitResult:
+                      cluster_path=None, node_paths=None, model_input_node=None, balance='params', cost_scale=1.0, device=None) -> SplitResult:
     """Split + self-check + write artefacts (reference operations/utils.py:265-349)."""
     if proportions is None:
         proportions = equal_proportions(num_splits) if balance == 'params' else [1.0 / num_splits] * num_splits
-    result = split_model(model, proportions, example_args, example_kwargs or {}, check=True, balance=balance)
+    result = split_model(model, proportions, example_args, example_kwargs or {}, check=True, balance=balance, cost_scale=cost_scale,
+                         device=device)
     write_split(result, cluster_path, node_paths)
     return result
 
@@ -251,7 +252,7 @@ def default_gpu_configs(n: int, base_port: int = 8080, host: str = '127.0.0.1') 
 
 
 def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False, *, topology=None,
-               proportions=None, balance=None, base_dir=None, node_configs=None, seed=42, verbose=False):
+               proportions=None, balance=None, cost_scale=1.0, plan_device=None, base_dir=None, node_configs=None, seed=42, verbose=False):
     """Plan the whole job: form clusters, split the model per cluster, derive DP rings and write
     ``node_data/cluster_<c>/<ip:port>/{submod.pt, submod_<k>_{input,output}.pkl, model_inputs.pkl, plan.json}``
     plus ``node_data/nodes/node_<id>.json`` (reference operations/utils.py:380-547).
@@ -282,7 +283,8 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
         props = list(proportions) if proportions is not None and len(proportions) == len(chain) else None
         res = split_model_equal(model=model, num_splits=len(chain), proportions=props, example_args=example_args,
                                 example_kwargs=example_kwargs, cluster_path=os.path.join(root, 'cluster_{}'.format(cluster.cid)),
-                                node_paths=[n.address for n in chain], model_input_node=chain[0].address, balance=mode)
+                                node_paths=[n.address for n in chain], model_input_node=chain[0].address, balance=mode,
+                                cost_scale=cost_scale, device=plan_device)
         if verbose and res.stage_costs:
             print('cluster', cluster.cid, 'estimated stage step times (ms):', [round(1e3 * c, 3) for c in res.stage_costs])
 
