@@ -205,6 +205,9 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({'error': 'no CUDA device visible; bench.py needs a B200'}))
         return 1
+    import faulthandler
+    # a hung multi-GPU run must be cheap and diagnosable: dump every thread's stack and exit instead of burning the box
+    faulthandler.dump_traceback_later(int(os.environ.get('RVN_BENCH_WATCHDOG', '300')), exit=True)
     rank, world, dev = init_distributed()
     gloo = dist.new_group(backend='gloo') if world > 1 else None
     if args.impl == 'baseline':
@@ -335,13 +338,22 @@ def main():
     sampler.start()
     node.tracer.resolve(block=True)
     exposed0 = node.tracer.totals_ms.get('exposed_comm', 0.0)
+    busy0 = sum(v for k, v in node.tracer.totals_ms.items() if k != 'exposed_comm')
     dev_ms, dev_wall = timed(args.steps, 'dev', False)
     clocks = sampler.summary()
     node.tracer.resolve(block=True)
-    exposed = torch.tensor([(node.tracer.totals_ms.get('exposed_comm', 0.0) - exposed0) / args.steps], device=dev)
+    own_exposed = (node.tracer.totals_ms.get('exposed_comm', 0.0) - exposed0) / args.steps
+    exposed = torch.tensor([own_exposed], device=dev)
     if world > 1:
         dist.all_reduce(exposed, op=dist.ReduceOp.MAX)
     exposed_ms = float(exposed)
+    # device time each rank's stage spent in its own handlers (forward / backward / update ...) per step: the balance of the plan
+    busy = (sum(v for k, v in node.tracer.totals_ms.items() if k != 'exposed_comm') - busy0) / args.steps - own_exposed
+    busy_all = [None] * world
+    if world > 1:
+        dist.all_gather_object(busy_all, round(busy, 3), group=gloo)
+    else:
+        busy_all = [round(busy, 3)]
     result = None
     e2e = None
     if not args.no_e2e:
@@ -366,7 +378,7 @@ def main():
             'clocks': clocks, 'e2e': e2e,
             'gpu_launches': (launches or {}).get('ours_per_step', 0) * args.steps if isinstance(launches, dict) else 0,
             'gpu_launches_detail': launches, 'wall_ms_per_step': dev_wall / args.steps,
-            'exposed_comm_ms_per_step': exposed_ms,
+            'exposed_comm_ms_per_step': exposed_ms, 'stage_busy_ms_per_rank': busy_all,
         }
         if args.layers:
             result['invalid'] = 'debug run with --layers'

@@ -89,6 +89,26 @@ class _Groups:
                 ranks = [chains[cid][s] for cid in sorted(chains)]
                 self.dp[s] = dist.new_group(ranks=ranks)
                 self.dp_ranks[s] = ranks
+        self._warm_up()
+
+    def _warm_up(self) -> None:
+        """NCCL builds a communicator on first use, from whichever thread gets there (receiver thread for one lane, scheduler
+        thread for the other): two stages initialising their two lanes in opposite order can block each other inside the
+        library.  So every communicator is created HERE, one at a time, in the same global order on every rank."""
+        if dist.get_backend() != 'nccl':
+            return
+        me = dist.get_rank()
+        dev = torch.device('cuda', torch.cuda.current_device())
+        done = set()
+        for (src, dst, lane), g in self.pair.items():
+            if me in (src, dst) and id(g) not in done:
+                dist.all_reduce(torch.zeros(1, device=dev), group=g)
+                torch.cuda.synchronize(dev)
+                done.add(id(g))
+        for s, g in self.dp.items():
+            if me in self.dp_ranks[s]:
+                dist.all_reduce(torch.zeros(1, device=dev), group=g)
+                torch.cuda.synchronize(dev)
 
     @classmethod
     def get(cls, chains: Dict[int, List[int]]) -> '_Groups':

@@ -14,10 +14,10 @@ from ravnest_b200 import models
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _launch(workdir, port, extra):
+def _launch(workdir, port, extra, stages=2, replicas=2, proportions=(0.5, 0.5)):
     rv.set_seed(42)
-    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(32, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
-                  node_configs=rv.default_gpu_configs(4), proportions=[0.5, 0.5], base_dir=str(workdir))
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(32, 1, 8, 8),), topology={'stages': stages, 'replicas': replicas},
+                  node_configs=rv.default_gpu_configs(4), proportions=list(proportions) if proportions else None, base_dir=str(workdir))
     env = dict(os.environ, RAVNEST_HOME=str(workdir), OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '4', '--master-addr', '127.0.0.1',
            '--master-port', str(port), os.path.join(HERE, 'dist_worker.py')] + extra
@@ -38,3 +38,13 @@ def test_two_by_two_grid_over_gloo(workdir, free_ports, dp_mode, recompute):
         assert res[1]['checksum'] == pytest.approx(res[3]['checksum'], rel=1e-6)
     losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_1.txt'))]
     assert len(losses) == 12 and losses[-1] < losses[0]
+
+
+@pytest.mark.slow
+def test_four_stage_pipeline_over_gloo(workdir, free_ports):
+    """root -> stem -> stem -> leaf on the torch.distributed transport, stages balanced by the planner's step-time estimate."""
+    res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '2', '--recompute', '0'], stages=4, replicas=1, proportions=None)
+    assert [r['node_type'] for r in res] == ['root', 'stem', 'stem', 'leaf']
+    assert all(r['n_backwards'] == 16 for r in res[:3])                  # 2 epochs x 8 batches, one replica
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_3.txt'))]
+    assert len(losses) == 16 and losses[-1] < losses[0]
