@@ -207,8 +207,17 @@ def main():
         return 1
     import faulthandler
     # a hung multi-GPU run must be cheap and diagnosable: dump every thread's stack and exit instead of burning the box
-    faulthandler.dump_traceback_later(int(os.environ.get('RVN_BENCH_WATCHDOG', '300')), exit=True)
+    watchdog_s = int(os.environ.get('RVN_BENCH_WATCHDOG', '300'))
+
+    def milestone(text):
+        """Re-arm the watchdog (each phase gets the full budget) and, with RAVNEST_TRACE_STARTUP=1, log progress on stderr."""
+        faulthandler.dump_traceback_later(watchdog_s, exit=True)
+        if os.environ.get('RAVNEST_TRACE_STARTUP', '0') == '1':
+            print('[rank {} t={:.1f}] {}'.format(os.environ.get('RANK', '0'), time.time() % 10000, text), file=sys.stderr, flush=True)
+
+    milestone('imports done')
     rank, world, dev = init_distributed()
+    milestone('process group up')
     gloo = dist.new_group(backend='gloo') if world > 1 else None
     if args.impl == 'baseline':
         ops.set_backend('torch')
@@ -232,9 +241,11 @@ def main():
         rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
                       node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props,
                       balance='params' if props else args.balance, cost_scale=cost_scale, plan_device=dev)
+    milestone('plan written' if rank == 0 else 'waiting for the plan')
     if world > 1:
         dist.barrier(group=gloo)
     del model
+    milestone('building node')
 
     cfg = rv.load_node_json_configs('node_{}'.format(rank), base_dir=home)
     replica = cfg['rank']
@@ -333,7 +344,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
 
+    milestone('node up, warm-up')
     run(max(3, args.warmup), 'dev', False)
+    milestone('warm-up done, timing')
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     node.tracer.resolve(block=True)

@@ -52,6 +52,14 @@ def init_distributed(backend: Optional[str] = None, device: Optional[torch.devic
     return rank, world, dev
 
 
+def _milestone(text: str) -> None:
+    """Start-up progress on stderr when RAVNEST_TRACE_STARTUP=1 (multi-GPU hangs are expensive to reproduce)."""
+    if os.environ.get('RAVNEST_TRACE_STARTUP', '0') == '1':
+        import sys
+        import time
+        print('[rank {} t={:.1f}] {}'.format(os.environ.get('RANK', '0'), time.time() % 10000, text), file=sys.stderr, flush=True)
+
+
 def _load_chains(base_dir: str) -> Dict[int, List[int]]:
     import json
     folder = os.path.join(base_dir, 'node_data', 'nodes')
@@ -80,7 +88,9 @@ class _Groups:
             chain = chains[cid]
             for a, b in zip(chain[:-1], chain[1:]):
                 for lane, (src, dst) in ((FORWARD, (a, b)), (BACKWARD, (b, a))):
-                    g = dist.new_group(ranks=sorted([a, b]))
+                    # tensors: one NCCL communicator per (pair, direction) so the two lanes never serialise on one comm stream;
+                    # headers: a gloo pair group (explicit backends: the default 'cuda:nccl,cpu:gloo' would build both per group)
+                    g = dist.new_group(ranks=sorted([a, b]), backend='nccl' if need_gloo else None)
                     self.pair[(src, dst, lane)] = g
                     self.header[(src, dst, lane)] = dist.new_group(ranks=sorted([a, b]), backend='gloo') if need_gloo else g
         lengths = {len(c) for c in chains.values()}
@@ -89,7 +99,9 @@ class _Groups:
                 ranks = [chains[cid][s] for cid in sorted(chains)]
                 self.dp[s] = dist.new_group(ranks=ranks)
                 self.dp_ranks[s] = ranks
+        _milestone('groups created: {} pair lanes, {} dp'.format(len(self.pair), len(self.dp)))
         self._warm_up()
+        _milestone('communicators warm')
 
     def _warm_up(self) -> None:
         """NCCL builds a communicator on first use, from whichever thread gets there (receiver thread for one lane, scheduler
