@@ -47,8 +47,11 @@ def init_distributed(backend: Optional[str] = None, device: Optional[torch.devic
     if not dist.is_initialized():
         if backend is None:
             backend = 'cuda:nccl,cpu:gloo' if use_cuda else 'gloo'
-        kwargs = {'device_id': dev} if use_cuda else {}
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+        # NOT bound to a device (no ``device_id=``): on a device-bound default group every later ``new_group`` — even a gloo-only
+        # one — makes its NON-members run a blocking nocolor ``ncclCommSplit`` that the members of a gloo group never join; with
+        # more than two stages per chain that desynchronises the split sequence and dead-locks group creation (seen on 4 x B200).
+        # Communicators are created lazily instead and warmed up in one global order by ``_Groups._warm_up``.
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, dev
 
 
