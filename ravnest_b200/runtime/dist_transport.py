@@ -107,19 +107,21 @@ class _Groups:
         _milestone('communicators warm')
 
     def _warm_up(self) -> None:
-        """NCCL builds a communicator on first use, from whichever thread gets there (receiver thread for one lane, scheduler
-        thread for the other): two stages initialising their two lanes in opposite order can block each other inside the
-        library.  So every communicator is created HERE, one at a time, in the same global order on every rank."""
-        if dist.get_backend() != 'nccl':
+        """NCCL builds a communicator on first use (for unbatched p2p on a 2-rank group: a dedicated one), from whichever thread
+        gets there first — and that creation synchronises the device, which invalidates a CUDA-graph capture in progress on
+        another thread.  So every communicator the transport will use is created HERE, before any node thread exists, one at a
+        time and in the same global order on every rank: a real send/recv per lane, an all-reduce per DP group."""
+        if not torch.cuda.is_available() or 'nccl' not in str(dist.get_backend()).lower():
             return
         me = dist.get_rank()
         dev = torch.device('cuda', torch.cuda.current_device())
-        done = set()
         for (src, dst, lane), g in self.pair.items():
-            if me in (src, dst) and id(g) not in done:
-                dist.all_reduce(torch.zeros(1, device=dev), group=g)
+            if me == src:
+                dist.send(torch.ones(8, device=dev), dst=dst, group=g)
+            elif me == dst:
+                dist.recv(torch.empty(8, device=dev), src=src, group=g)
+            if me in (src, dst):
                 torch.cuda.synchronize(dev)
-                done.add(id(g))
         for s, g in self.dp.items():
             if me in self.dp_ranks[s]:
                 dist.all_reduce(torch.zeros(1, device=dev), group=g)
