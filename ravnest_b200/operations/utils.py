@@ -19,7 +19,7 @@ import json
 import math
 import os
 import shutil
-from typing import Dict, List, Optional, Sequence
+from typing import Tuple, Dict, List, Optional, Sequence
 
 import torch
 
@@ -274,6 +274,7 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
         clusters = cluster_formation(full_model_size, pool, seed=seed)
 
     os.makedirs(os.path.join(root, 'nodes'), exist_ok=True)
+    plans: Dict[Tuple, SplitResult] = {}           # identical chains (GPU grids) share one traced / measured plan
     for cluster in clusters:
         chain = cluster.ordered_nodes()
         _wire_chain(chain)
@@ -281,10 +282,15 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
         # caller pins ``proportions`` the stages are balanced by estimated step time instead (balance='compute').
         mode = balance or ('compute' if (topology is not None and proportions is None) else 'params')
         props = list(proportions) if proportions is not None and len(proportions) == len(chain) else None
-        res = split_model_equal(model=model, num_splits=len(chain), proportions=props, example_args=example_args,
-                                example_kwargs=example_kwargs, cluster_path=os.path.join(root, 'cluster_{}'.format(cluster.cid)),
-                                node_paths=[n.address for n in chain], model_input_node=chain[0].address, balance=mode,
-                                cost_scale=cost_scale, device=plan_device)
+        key = (len(chain), tuple(props) if props else None, mode)
+        if key in plans:
+            res = plans[key]
+            write_split(res, os.path.join(root, 'cluster_{}'.format(cluster.cid)), [n.address for n in chain])
+        else:
+            res = plans[key] = split_model_equal(
+                model=model, num_splits=len(chain), proportions=props, example_args=example_args, example_kwargs=example_kwargs,
+                cluster_path=os.path.join(root, 'cluster_{}'.format(cluster.cid)), node_paths=[n.address for n in chain],
+                model_input_node=chain[0].address, balance=mode, cost_scale=cost_scale, device=plan_device)
         if verbose and res.stage_costs:
             print('cluster', cluster.cid, 'estimated stage step times (ms):', [round(1e3 * c, 3) for c in res.stage_costs])
 
