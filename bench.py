@@ -345,6 +345,11 @@ def main():
         return float(ms[0]), float(ms[1])
 
     milestone('node up, warm-up')
+    # untimed pre-warm in addition to the W warm-up steps: CUDA-graph capture of a stage needs graph_warmup eager forwards, two
+    # eager backwards and then one capture per in-flight pass (cluster_length + 2 instances) — none of that may land in the
+    # timed region whatever W the caller picks
+    prewarm = 12 + 2 * stages
+    run(prewarm, 'dev', False)
     run(max(3, args.warmup), 'dev', False)
     milestone('warm-up done, timing')
     sampler = ClockSampler(dev.index or 0)
@@ -386,7 +391,7 @@ def main():
                                  'inception': 'Inception3 CIFAR variant (21.6M)', 'sorter': 'minGPT gpt-nano (85.7K)'}[args.model],
                        'global_batch': replicas * batch, 'per_replica_batch': batch, 'seq_len': 512 if args.model == 'bert' else None,
                        'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': {'bert': 'LAMB', 'sorter': 'Adam'}.get(args.model, 'SGD-momentum'),
-                       'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)', 'cuda_graphs': not args.no_graphs,
+                       'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)', 'cuda_graphs': not args.no_graphs, 'prewarm_steps_before_warmup': prewarm,
                        'l2': 'working set (weights+activations, >1 GB/step) exceeds the 126 MB L2; no explicit flush'},
             'clocks': clocks, 'e2e': e2e,
             'gpu_launches': (launches or {}).get('ours_per_step', 0) * args.steps if isinstance(launches, dict) else 0,

@@ -92,6 +92,7 @@ class Compute:
         self.graph_warmup = 3
         self._graph = None
         self._graph_seen = 0
+        self._eager_backwards = 0
         self._graph_failed = False
         self._stage_graphs = []
         self._max_stage_graphs = cluster_length + 2
@@ -190,7 +191,10 @@ class Compute:
             if not gs.busy and gs.signature == sig:
                 return gs
         self._graph_seen += 1
-        if self._graph_seen <= self.graph_warmup or len(self._stage_graphs) >= self._max_stage_graphs:
+        # capture records forward AND backward: both must have run eagerly first (cuDNN autotuning, lazily created workspaces
+        # and allocator growth are illegal inside a capture).  Deep pipelines see several forwards before the first backward
+        # comes back, so counting forwards alone is not enough (4-stage ResNet: capture invalidated on every non-leaf stage).
+        if (self._graph_seen <= self.graph_warmup or self._eager_backwards < 2 or len(self._stage_graphs) >= self._max_stage_graphs):
             return None
         try:
             gs = GraphedStage(self, self._prepare_inputs(args, need_grad=False), input_grads)
@@ -251,6 +255,7 @@ class Compute:
                 gs.append(g)
             if outs:
                 torch.autograd.backward(outs, gs)
+            self._eager_backwards += 1
             in_grads = [a.grad if isinstance(a, torch.Tensor) and a.requires_grad else None for a in fl.inputs]
             self.store.release(fl.slot)
             del self.flights[fpid]
