@@ -197,9 +197,15 @@ class Compute:
         if (self._graph_seen <= self.graph_warmup or self._eager_backwards < 2 or len(self._stage_graphs) >= self._max_stage_graphs):
             return None
         try:
-            gs = GraphedStage(self, self._prepare_inputs(args, need_grad=False), input_grads)
-            self._stage_graphs.append(gs)
-            return gs
+            # capture every instance the schedule can ever need (one per in-flight pass) NOW, inside the warm-up, instead of
+            # lazily when the in-flight depth first reaches a new maximum (that used to land a ~30 ms capture in steady state)
+            prepared = self._prepare_inputs(args, need_grad=False)
+            first = None
+            while len(self._stage_graphs) < self._max_stage_graphs:
+                gs = GraphedStage(self, prepared, input_grads)
+                self._stage_graphs.append(gs)
+                first = first or gs
+            return first
         except Exception as err:
             self._graph_failed = True
             import warnings
