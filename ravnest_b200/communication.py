@@ -29,6 +29,11 @@ FP16_MAX = 65504.0
 # ----------------------------------------------------------------------------------------------
 def compress_tensor(t: torch.Tensor) -> torch.Tensor:
     if t.dtype == torch.float32:
+        if t.is_cuda:
+            from . import ops
+            if ops.backend() == 'native':
+                from .ops import native
+                return native.pack_for_wire(t, 'fp16')          # clamp + cast in one pass (K12)
         return t.clamp(-FP16_MAX, FP16_MAX).to(torch.float16)
     if t.dtype == torch.float64:
         return t.to(torch.float32)

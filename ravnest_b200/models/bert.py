@@ -38,11 +38,11 @@ class BertEmbeddings(nn.Module):
 
     def __init__(self, cfg: BertConfig):
         super().__init__()
-        self.word_embeddings = rnn.Embedding(cfg.vocab_size, cfg.hidden_size)
+        self.word_embeddings = rnn.Embedding(cfg.vocab_size, cfg.hidden_size, padding_idx=getattr(cfg, 'pad_token_id', 0))
         self.position_embeddings = rnn.Embedding(cfg.max_position_embeddings, cfg.hidden_size)
         self.token_type_embeddings = rnn.Embedding(cfg.type_vocab_size, cfg.hidden_size)
         self.LayerNorm = rnn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
-        self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
+        self.dropout = rnn.Dropout(cfg.hidden_dropout_prob)
 
     def forward(self, input_ids, token_type_ids):
         pos = torch.arange(input_ids.shape[1], device=input_ids.device)
@@ -56,7 +56,7 @@ class BertSelfOutput(nn.Module):
         super().__init__()
         self.dense = rnn.Linear(cfg.hidden_size, cfg.hidden_size)
         self.LayerNorm = rnn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
-        self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
+        self.dropout = rnn.Dropout(cfg.hidden_dropout_prob)
 
 
 class BertAttention(nn.Module):
@@ -77,7 +77,7 @@ class BertOutput(nn.Module):
         super().__init__()
         self.dense = rnn.Linear(cfg.intermediate_size, cfg.hidden_size)
         self.LayerNorm = rnn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
-        self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
+        self.dropout = rnn.Dropout(cfg.hidden_dropout_prob)
 
 
 class BertLayer(nn.Module):

@@ -65,7 +65,7 @@ class CausalSelfAttention(nn.Module):
         self.core = rnn.SelfAttention(cfg.n_embd, cfg.n_head, cfg.attn_pdrop, causal=True, qkv_name='c_attn')
         self.c_attn = self.core.c_attn
         self.c_proj = rnn.Linear(cfg.n_embd, cfg.n_embd)
-        self.resid_dropout = nn.Dropout(cfg.resid_pdrop)
+        self.resid_dropout = rnn.Dropout(cfg.resid_pdrop)
 
     def forward(self, x):
         return self.resid_dropout(self.c_proj(self.core(x)))
@@ -79,7 +79,7 @@ class MLP(nn.Module):
         super().__init__()
         self.c_fc = rnn.Linear(cfg.n_embd, 4 * cfg.n_embd, activation='gelu_tanh')
         self.c_proj = rnn.Linear(4 * cfg.n_embd, cfg.n_embd)
-        self.dropout = nn.Dropout(cfg.resid_pdrop)
+        self.dropout = rnn.Dropout(cfg.resid_pdrop)
 
     def forward(self, x):
         return self.dropout(self.c_proj(self.c_fc(x)))
@@ -103,7 +103,7 @@ class _Transformer(nn.Module):
         super().__init__()
         self.emb = _Positions(cfg)
         self.wte, self.wpe = self.emb.wte, self.emb.wpe
-        self.drop = nn.Dropout(cfg.embd_pdrop)
+        self.drop = rnn.Dropout(cfg.embd_pdrop)
         self.h = nn.ModuleList([Block(cfg) for _ in range(cfg.n_layer)])
         self.ln_f = rnn.LayerNorm(cfg.n_embd)
 

@@ -131,7 +131,7 @@ class Inception3(nn.Module):
         self.Mixed_7b = _inception_e(1280)
         self.Mixed_7c = _inception_e(2048)
         self.avgpool = nn.AdaptiveAvgPool2d(1)
-        self.dropout = nn.Dropout(0.5)
+        self.dropout = rnn.Dropout(0.5)
         self.flatten = nn.Flatten(1)
         self.fc = nn.Linear(2048, num_classes)
         self._blocks = ['Conv2d_1a_3x3', 'Mixed_5b', 'Mixed_5c', 'Mixed_5d', 'Mixed_6a', 'Mixed_6b', 'Mixed_6c',

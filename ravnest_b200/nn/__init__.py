@@ -42,11 +42,18 @@ class LayerNorm(nn.LayerNorm):
 
 class Embedding(nn.Embedding):
     def forward(self, idx):
-        return ops.embedding(idx, self.weight)
+        if self.max_norm is not None or self.sparse or self.scale_grad_by_freq:
+            return super().forward(idx)
+        return ops.embedding(idx, self.weight, self.padding_idx)
 
 
 class Dropout(nn.Dropout):
-    pass
+    """``nn.Dropout`` on the Philox kernel (CUDA): no mask tensor; recompute and backward replay the forward's mask."""
+
+    def forward(self, x):
+        if self.inplace:
+            return super().forward(x)
+        return ops.dropout(x, self.p, self.training)
 
 
 class SelfAttention(nn.Module):

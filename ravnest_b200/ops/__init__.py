@@ -115,8 +115,21 @@ def mlp(x, w1, b1, w2, b2, activation='gelu'):
     return reference_linear(reference_linear(x, w1, b1, activation), w2, b2, None)
 
 
-def embedding(idx, weight):
-    return reference_embedding(idx, weight)
+def embedding(idx, weight, padding_idx=None):
+    if _native(idx, weight):
+        from . import native
+        return native.embedding(idx, weight, padding_idx)
+    return F.embedding(idx, weight, padding_idx)
+
+
+def dropout(x, p=0.5, training=True):
+    """Dropout whose mask is a pure function of (seed, step, position) on the native path: nothing is saved for backward."""
+    if not training or p <= 0.0:
+        return x
+    if _native(x):
+        from . import native
+        return native.dropout(x, p)
+    return F.dropout(x, p, True)
 
 
 def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
@@ -190,6 +203,6 @@ def native_ops_loaded():
         return {}
 
 
-__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'max_pool2d', 'avg_pool2d', 'layer_norm', 'embedding', 'attention_qkv', 'cross_entropy',
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'max_pool2d', 'avg_pool2d', 'layer_norm', 'embedding', 'dropout', 'attention_qkv', 'cross_entropy',
            'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
            'reference_cross_entropy']

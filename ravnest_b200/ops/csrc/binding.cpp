@@ -45,6 +45,11 @@ int rvn_pool_forward(const void* x, void* y, void* arg, int N, int H, int W, int
 int rvn_pool_backward(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
                       int is_max, int num_sms, cudaStream_t stream);
 int rvn_activation_backward(const void* dy, const void* z, void* dz, size_t n, int act, int num_sms, cudaStream_t stream);
+int rvn_embedding_forward(const int64_t* idx, const void* w, void* out, long long n, int H, long long V, int is_bf16, cudaStream_t stream);
+int rvn_embedding_backward(const int64_t* idx, const void* dy, void* dw, int n, int H, long long V, long long padding_idx, int is_bf16,
+                           cudaStream_t stream);
+int rvn_dropout(const void* x, void* y, size_t n, const long long* rng, float p, int is_bf16, int num_sms, cudaStream_t stream);
+int rvn_pack(const float* x, void* y, size_t n, int mode, int num_sms, cudaStream_t stream);
 }
 
 struct PeerPtrs {
@@ -319,6 +324,69 @@ torch::Tensor act_bwd(const torch::Tensor& dy, const torch::Tensor& z, int64_t a
   return dz;
 }
 
+// ---------------------------------------------------------------------------------------------- K10 / K11 / K12
+static int float_kind(const torch::Tensor& t, const char* what) {
+  TORCH_CHECK(t.scalar_type() == torch::kBFloat16 || t.scalar_type() == torch::kFloat32, what, " must be bf16 or fp32");
+  return t.scalar_type() == torch::kBFloat16;
+}
+
+// out[..., :] = weight[idx[...], :]
+torch::Tensor embedding_fwd(const torch::Tensor& idx, const torch::Tensor& weight) {
+  c10::cuda::CUDAGuard guard(weight.device());
+  TORCH_CHECK(idx.scalar_type() == torch::kInt64 && idx.is_cuda() && weight.dim() == 2 && weight.is_contiguous(), "embedding expects int64 indices and a contiguous table");
+  const int bf = float_kind(weight, "embedding table");
+  auto ids = idx.contiguous();
+  auto shape = ids.sizes().vec();
+  shape.push_back(weight.size(1));
+  auto out = torch::empty(shape, weight.options());
+  check(rvn_embedding_forward(ids.data_ptr<int64_t>(), weight.data_ptr(), out.data_ptr(), ids.numel(), static_cast<int>(weight.size(1)),
+                              weight.size(0), bf, cur_stream()),
+        "embedding_fwd");
+  return out;
+}
+
+// dW[r] += sum of dy rows whose index is r.  ``into``: accumulate into this [V, H] tensor (the gradient bucket view) and return it;
+// otherwise a zero-filled tensor is created.  Deterministic (no atomics).  Requires numel(idx) <= 16384.
+torch::Tensor embedding_bwd(const torch::Tensor& idx, const torch::Tensor& dy, int64_t num_rows, int64_t padding_idx,
+                            const c10::optional<torch::Tensor>& into) {
+  c10::cuda::CUDAGuard guard(dy.device());
+  const int bf = float_kind(dy, "embedding gradient");
+  auto ids = idx.contiguous();
+  auto g = dy.contiguous();
+  const int H = g.size(-1);
+  TORCH_CHECK(ids.numel() * H == g.numel() && ids.numel() <= 16384, "embedding_bwd: shape mismatch or more than 16384 indices");
+  torch::Tensor dw;
+  if (into.has_value() && into->defined()) {
+    TORCH_CHECK(into->is_contiguous() && into->scalar_type() == g.scalar_type() && into->size(0) == num_rows && into->size(1) == H, "bad accumulator");
+    dw = *into;
+  } else {
+    dw = torch::zeros({num_rows, H}, g.options());
+  }
+  check(rvn_embedding_backward(ids.data_ptr<int64_t>(), g.data_ptr(), dw.data_ptr(), static_cast<int>(ids.numel()), H, num_rows, padding_idx, bf,
+                               cur_stream()),
+        "embedding_bwd");
+  return dw;
+}
+
+// y = x * Philox keep-scale(rng snapshot, position); the backward applies the same call to dy
+torch::Tensor dropout_apply(const torch::Tensor& x, const torch::Tensor& rng, double p) {
+  c10::cuda::CUDAGuard guard(x.device());
+  const int bf = float_kind(x, "dropout input");
+  TORCH_CHECK(x.is_contiguous() && x.numel() % (bf ? 8 : 4) == 0, "dropout expects a contiguous tensor with numel % 8 == 0 (bf16) / % 4 == 0 (fp32)");
+  auto y = torch::empty_like(x);
+  check(rvn_dropout(x.data_ptr(), y.data_ptr(), x.numel(), rng_ptr(rng), static_cast<float>(p), bf, sm_count(), cur_stream()), "dropout");
+  return y;
+}
+
+// fp32 -> fp16 (clamped to the fp16 range; mode 0) or bf16 (mode 1) in one pass
+torch::Tensor pack_f32(const torch::Tensor& x, int64_t mode) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kFloat32, "pack expects contiguous fp32");
+  auto y = torch::empty(x.sizes(), x.options().dtype(mode == 0 ? torch::kFloat16 : torch::kBFloat16));
+  check(rvn_pack(x.data_ptr<float>(), y.data_ptr(), x.numel(), static_cast<int>(mode), sm_count(), cur_stream()), "pack");
+  return y;
+}
+
 // qkv: [B, S, 3H] bf16 contiguous (q | k | v, heads of 64); kbias: optional [B, S] fp32 additive key bias.  Returns {out [B,S,H], lse [B,heads,S]}
 std::vector<torch::Tensor> fmha_fwd(const torch::Tensor& qkv, int64_t heads, const c10::optional<torch::Tensor>& kbias, bool causal,
                                     double scale, const c10::optional<torch::Tensor>& rng, double dropout_p) {
@@ -588,6 +656,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_bwd", &ce_bwd);
   m.def("column_sum", &column_sum, py::arg("x"), py::arg("into") = py::none());
   m.def("act_bwd", &act_bwd);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd", &embedding_bwd, py::arg("idx"), py::arg("dy"), py::arg("num_rows"), py::arg("padding_idx") = -1, py::arg("into") = py::none());
+  m.def("dropout_apply", &dropout_apply);
+  m.def("pack_f32", &pack_f32);
   m.def("conv_nhwc", &conv_nhwc);
   m.def("pool_fwd", &pool_fwd);
   m.def("pool_bwd", &pool_bwd);

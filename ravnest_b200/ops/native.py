@@ -338,6 +338,78 @@ def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0
     return out.transpose(1, 2).reshape(B, S, H)
 
 
+NATIVE_EMBEDDING = True
+NATIVE_DROPOUT = True
+
+
+class _Embedding(torch.autograd.Function):
+    """Row gather forward; deterministic owner-computes scatter backward that adds straight into the table's gradient
+    bucket (ops/csrc/embed_misc.cu) — no sort, no atomics, no AccumulateGrad pass over the 30522 x 768 table."""
+
+    @staticmethod
+    def forward(ctx, idx, weight, padding_idx):
+        calls['embedding_fwd'] += 1
+        ctx.save_for_backward(idx, weight)
+        ctx.padding_idx = padding_idx
+        return C().embedding_fwd(idx, weight)
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx, weight = ctx.saved_tensors
+        calls['embedding_bwd'] += 1
+        g = weight.grad
+        if ACCUMULATE_INTO_GRAD and g is not None and g.dtype == dy.dtype and g.is_contiguous() and g.shape == weight.shape:
+            C().embedding_bwd(idx, dy, weight.shape[0], ctx.padding_idx, g)
+            return None, None, None
+        return None, C().embedding_bwd(idx, dy, weight.shape[0], ctx.padding_idx, None), None
+
+
+def embedding(idx, weight, padding_idx=None):
+    ok = (NATIVE_EMBEDDING and idx.dtype == torch.int64 and weight.dtype in (torch.bfloat16, torch.float32) and weight.is_contiguous()
+          and 0 < idx.numel() <= 16384 and weight.dim() == 2)
+    if not ok:
+        fallbacks['embedding'] += 1
+        return F.embedding(idx, weight, padding_idx)
+    return _Embedding.apply(idx, weight, -1 if padding_idx is None else int(padding_idx))
+
+
+class _Dropout(torch.autograd.Function):
+    """Philox dropout without a mask tensor: backward (and a recompute) regenerate the forward's mask from the saved
+    16-byte {seed, step} snapshot (ops/csrc/embed_misc.cu, philox.cuh)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        rng = next_rng_snapshot(x.device)
+        calls['dropout_fwd'] += 1
+        ctx.p = p
+        ctx.save_for_backward(rng)
+        return C().dropout_apply(x.contiguous(), rng, p)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (rng,) = ctx.saved_tensors
+        calls['dropout_bwd'] += 1
+        return C().dropout_apply(dy.contiguous(), rng, ctx.p), None
+
+
+def dropout(x, p):
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    if not NATIVE_DROPOUT or x.dtype not in (torch.bfloat16, torch.float32) or x.numel() == 0 or x.numel() % vec != 0 or p >= 1.0:
+        fallbacks['dropout'] += 1
+        return F.dropout(x, p, True)
+    if x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+        # the mask only depends on the storage offset: run on the NHWC view so no layout copy is made
+        y = _Dropout.apply(x.permute(0, 2, 3, 1), float(p))
+        return y.permute(0, 3, 1, 2)
+    return _Dropout.apply(x, float(p))
+
+
+def pack_for_wire(t, mode='fp16'):
+    """fp32 activation -> fp16 (clamped) / bf16 in one pass (K12)."""
+    calls['pack'] += 1
+    return C().pack_f32(t.contiguous(), 0 if mode == 'fp16' else 1)
+
+
 def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 

@@ -304,6 +304,74 @@ def test_pooling_nhwc(N, C, H, W, k, s, p, is_max):
     assert _rel_err(x.grad, xr.grad) < 1e-2
 
 
+# ----------------------------------------------------------------------------------------------- embedding / dropout / pack
+@pytest.mark.parametrize('n_shape,V,H,dtype,pad', [((8, 512), 30522, 768, torch.bfloat16, 0), ((64, 11), 3, 48, torch.float32, None),
+                                                    ((512,), 512, 768, torch.bfloat16, None), ((4096,), 2, 768, torch.bfloat16, None),
+                                                    ((700,), 1000, 100, torch.float32, 5)])
+def test_embedding_forward_backward(n_shape, V, H, dtype, pad):
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(21)
+    w = (torch.randn(V, H, device=DEV) * 0.5).to(dtype).requires_grad_(True)
+    if n_shape == (512,):
+        idx = torch.arange(512, device=DEV)
+    else:
+        idx = torch.randint(0, V, n_shape, device=DEV)
+        idx.view(-1)[::7] = min(3, V - 1)                           # a heavily repeated token
+    y = ops.embedding(idx, w, pad)
+    assert torch.equal(y, torch.nn.functional.embedding(idx, w.detach(), pad))
+    gy = (torch.randn(*y.shape, device=DEV) * 0.3).to(dtype)
+    y.backward(gy)
+    wr = w.detach().float().requires_grad_(True)
+    torch.nn.functional.embedding(idx, wr, pad).backward(gy.float())
+    assert _rel_err(w.grad, wr.grad) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    if pad is not None:
+        assert float(w.grad[pad].abs().max()) == 0.0
+    # second backward accumulates in place, and is deterministic
+    g1 = w.grad.clone()
+    ops.embedding(idx, w, pad).backward(gy)
+    assert _rel_err(w.grad, 2 * wr.grad) < (1.5e-2 if dtype == torch.bfloat16 else 1e-5)
+    w.grad = None
+    ops.embedding(idx, w, pad).backward(gy)
+    assert torch.equal(w.grad, g1)
+    assert native.calls['embedding_bwd'] >= 3
+
+
+@pytest.mark.parametrize('shape,dtype', [((4096, 768), torch.bfloat16), ((64, 288, 8, 8), torch.bfloat16), ((100, 128), torch.float32)])
+def test_dropout_replays_mask(shape, dtype):
+    from ravnest_b200 import ops
+    torch.manual_seed(22)
+    p = 0.25
+    x = (torch.randn(*shape, device=DEV) + 3.0).to(dtype)
+    if len(shape) == 4:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y = ops.dropout(x, p, True)
+    kept = (y != 0)
+    assert abs(float(kept.float().mean()) - (1 - p)) < 0.02
+    assert _rel_err(y[kept], x.detach()[kept].float() / (1 - p)) < 1e-2
+    gy = torch.ones_like(y)
+    y.backward(gy)
+    # the backward regenerated exactly the forward's mask
+    assert torch.equal(x.grad != 0, kept)
+    assert _rel_err(x.grad[kept], torch.full_like(x.grad[kept], 1 / (1 - p))) < 1e-2
+    # a second call draws a different mask; eval mode is the identity
+    y2 = ops.dropout(x.detach(), p, True)
+    assert not torch.equal(y2 != 0, kept)
+    assert ops.dropout(x, p, False) is x
+
+
+def test_pack_for_wire():
+    from ravnest_b200.communication import compress_tensor
+    torch.manual_seed(23)
+    x = torch.randn(1000, 77, device=DEV) * 1e4
+    x[0, :4] = torch.tensor([1e9, -1e9, 65504.0, 1e-9], device=DEV)
+    y = compress_tensor(x)
+    assert y.dtype == torch.float16 and torch.equal(y, x.clamp(-65504, 65504).to(torch.float16))
+    from ravnest_b200.ops import native
+    assert torch.equal(native.pack_for_wire(x, 'bf16'), x.to(torch.bfloat16))
+
+
 # ----------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize('B,S,heads,causal,padded', [(2, 128, 2, False, False), (8, 512, 12, False, True), (2, 384, 4, True, False),
                                                      (3, 200, 2, False, True), (2, 200, 2, True, True)])
