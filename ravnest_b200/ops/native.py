@@ -358,6 +358,22 @@ class _Embedding(torch.autograd.Function):
         idx, weight = ctx.saved_tensors
         calls['embedding_bwd'] += 1
         g = weight.grad
+        V, H = weight.shape
+        if V <= 64 and dy.dtype == torch.bfloat16 and H % 8 == 0:
+            # tiny tables (token types, small vocabularies): every row has thousands of contributors, which would serialise on
+            # one owner CTA — dW = onehot(idx)^T dy on the tensor cores instead (A read MN-major: [n, V8] one-hot, K = n)
+            v8 = (V + 7) // 8 * 8
+            flat = idx.reshape(-1)
+            onehot = torch.zeros(flat.numel(), v8, dtype=torch.bfloat16, device=dy.device)
+            onehot.scatter_(1, flat.unsqueeze(1), 1.0)
+            if ctx.padding_idx >= 0:
+                onehot[:, ctx.padding_idx] = 0
+            dw = C().gemm(onehot, True, dy.reshape(-1, H).contiguous(), True, None, 0, None, False, 0)[0][:V]
+            calls['embedding_bwd_gemm'] += 1
+            if ACCUMULATE_INTO_GRAD and g is not None and g.dtype == dw.dtype and g.shape == dw.shape:
+                g.add_(dw)
+                return None, None, None
+            return None, dw, None
         if ACCUMULATE_INTO_GRAD and g is not None and g.dtype == dy.dtype and g.is_contiguous() and g.shape == weight.shape:
             C().embedding_bwd(idx, dy, weight.shape[0], ctx.padding_idx, g)
             return None, None, None
