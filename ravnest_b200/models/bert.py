@@ -110,8 +110,10 @@ class BertEncoder(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.layer = nn.ModuleList([BertLayer(cfg) for _ in range(cfg.num_hidden_layers)])
+        self.mask_bias = rnn.KeyPaddingBias()
 
     def forward(self, x, mask):
+        mask = self.mask_bias(mask)                 # [B, S] 0 / -inf once, not once per layer
         for layer in self.layer:
             x = layer(x, mask)
         return x

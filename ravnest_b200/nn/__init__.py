@@ -120,6 +120,16 @@ class BatchNorm2d(nn.BatchNorm2d):
                                   self.momentum if self.momentum is not None else 0.1, self.eps, num_batches_tracked=nbt)
 
 
+class KeyPaddingBias(nn.Module):
+    """[B, S] attention mask (1 = attend) -> the additive fp32 key bias the attention kernel consumes, computed ONCE per stage
+    forward instead of once per layer (12 x 4 tiny launches per BERT step).  Parameter-free, so state dicts are unaffected;
+    a planner leaf, so a stage cut after it relays the bias instead of the integer mask."""
+    _ravnest_leaf = True
+
+    def forward(self, mask):
+        return ops.key_padding_bias(mask)
+
+
 class MaxPool2d(nn.MaxPool2d):
     def forward(self, x):
         if self.dilation not in (1, (1, 1)) or self.ceil_mode or self.return_indices:
@@ -143,4 +153,4 @@ class GELU(nn.Module):
         return F.gelu(x, approximate=self.approximate)
 
 
-__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'Conv2d', 'BatchNorm2d', 'MaxPool2d', 'AvgPool2d', 'GELU']
+__all__ = ['Linear', 'LayerNorm', 'Embedding', 'Dropout', 'SelfAttention', 'KeyPaddingBias', 'Conv2d', 'BatchNorm2d', 'MaxPool2d', 'AvgPool2d', 'GELU']

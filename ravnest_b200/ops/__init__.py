@@ -77,7 +77,10 @@ def reference_attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dro
         mask = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
         att = att.masked_fill(~mask, float('-inf'))
     if key_padding_mask is not None:
-        att = att.masked_fill(~key_padding_mask.bool()[:, None, None, :], float('-inf'))
+        if key_padding_mask.dtype == torch.float32:
+            att = att + key_padding_mask[:, None, None, :].to(att.dtype)
+        else:
+            att = att.masked_fill(~key_padding_mask.bool()[:, None, None, :], float('-inf'))
     att = torch.softmax(att.float(), dim=-1).to(qkv.dtype)
     if dropout_p > 0.0:
         att = F.dropout(att, dropout_p, True)
@@ -132,7 +135,15 @@ def dropout(x, p=0.5, training=True):
     return F.dropout(x, p, True)
 
 
+def key_padding_bias(mask):
+    """Attention mask [B, S] (non-zero = attend) -> additive fp32 key bias (0 / -inf); an fp32 tensor is taken to be a bias already."""
+    if mask is None or mask.dtype == torch.float32:
+        return mask
+    return torch.zeros(mask.shape, dtype=torch.float32, device=mask.device).masked_fill_(~mask.bool(), float('-inf'))
+
+
 def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
+    """``key_padding_mask``: [B, S] integer / bool mask (non-zero = attend) or the fp32 additive bias made by ``key_padding_bias``."""
     if _native(qkv):
         from . import native
         return native.attention_qkv(qkv, heads, key_padding_mask, causal, dropout_p)
@@ -203,6 +214,6 @@ def native_ops_loaded():
         return {}
 
 
-__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'max_pool2d', 'avg_pool2d', 'layer_norm', 'embedding', 'dropout', 'attention_qkv', 'cross_entropy',
+__all__ = ['native_ops_loaded', 'set_backend', 'backend', 'linear', 'mlp', 'conv2d', 'batch_norm_act', 'max_pool2d', 'avg_pool2d', 'layer_norm', 'embedding', 'dropout', 'attention_qkv', 'key_padding_bias', 'cross_entropy',
            'reference_linear', 'reference_layer_norm', 'reference_embedding', 'reference_attention_qkv',
            'reference_cross_entropy']

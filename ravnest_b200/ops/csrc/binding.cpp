@@ -50,6 +50,7 @@ int rvn_embedding_backward(const int64_t* idx, const void* dy, void* dw, int n, 
                            cudaStream_t stream);
 int rvn_dropout(const void* x, void* y, size_t n, const long long* rng, float p, int is_bf16, int num_sms, cudaStream_t stream);
 int rvn_pack(const float* x, void* y, size_t n, int mode, int num_sms, cudaStream_t stream);
+int rvn_rng_next(long long* state, long long* snap, cudaStream_t stream);
 }
 
 struct PeerPtrs {
@@ -378,6 +379,16 @@ torch::Tensor dropout_apply(const torch::Tensor& x, const torch::Tensor& rng, do
   return y;
 }
 
+// returns a copy of the {seed, step} state and advances step by one
+torch::Tensor rng_next(torch::Tensor state) {
+  c10::cuda::CUDAGuard guard(state.device());
+  TORCH_CHECK(state.scalar_type() == torch::kInt64 && state.numel() >= 2 && state.is_contiguous(), "rng state must be int64[2]");
+  auto snap = torch::empty({2}, state.options());
+  check(rvn_rng_next(reinterpret_cast<long long*>(state.data_ptr<int64_t>()), reinterpret_cast<long long*>(snap.data_ptr<int64_t>()), cur_stream()),
+        "rng_next");
+  return snap;
+}
+
 // fp32 -> fp16 (clamped to the fp16 range; mode 0) or bf16 (mode 1) in one pass
 torch::Tensor pack_f32(const torch::Tensor& x, int64_t mode) {
   c10::cuda::CUDAGuard guard(x.device());
@@ -660,6 +671,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("embedding_bwd", &embedding_bwd, py::arg("idx"), py::arg("dy"), py::arg("num_rows"), py::arg("padding_idx") = -1, py::arg("into") = py::none());
   m.def("dropout_apply", &dropout_apply);
   m.def("pack_f32", &pack_f32);
+  m.def("rng_next", &rng_next);
   m.def("conv_nhwc", &conv_nhwc);
   m.def("pool_fwd", &pool_fwd);
   m.def("pool_bwd", &pool_bwd);

@@ -145,6 +145,13 @@ __global__ void __launch_bounds__(256) rvn_dropout_f32(const float* __restrict__
   }
 }
 
+// snapshot = state; state.step += 1 — the per-consumer RNG bookkeeping as ONE single-thread launch (graph-capturable)
+__global__ void rvn_rng_next_kernel(long long* __restrict__ state, long long* __restrict__ snap) {
+  snap[0] = state[0];
+  snap[1] = state[1];
+  state[1] += 1;
+}
+
 // ------------------------------------------------------------------------------------------------ K12 pack
 // mode 0: fp32 -> fp16 with clamp to the fp16 range (the reference's wire format), mode 1: fp32 -> bf16
 __global__ void __launch_bounds__(256) rvn_pack_f32(const float* __restrict__ x, uint16_t* __restrict__ y, size_t n4, size_t n, int mode) {
@@ -224,6 +231,11 @@ extern "C" int rvn_dropout(const void* x, void* y, size_t n, const long long* rn
     if (n % 4 != 0) return -2;
     rvn::rvn_dropout_f32<<<stream_grid(n / 4, num_sms), 256, 0, stream>>>((const float*)x, (float*)y, n / 4, rng, p);
   }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+extern "C" int rvn_rng_next(long long* state, long long* snap, cudaStream_t stream) {
+  rvn::rvn_rng_next_kernel<<<1, 1, 0, stream>>>(state, snap);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -93,12 +93,36 @@ def test_bert_kwargs_split_routes_mask_to_both_stages():
           'token_type_ids': torch.zeros(2, 16, dtype=torch.long)}
     r = split_model(m, [0.5, 0.5], (), kw)
     assert r.model_input_names == ['input_ids', 'attention_mask', 'token_type_ids']
-    assert r.model_inputs_template[1]['target'] == ['submod_0', 'submod_1']        # attention mask relayed to the leaf
+    # the integer mask is turned into the additive key bias once, in the stage that holds the first encoder layer; what
+    # travels to the leaf is that fp32 bias (an extra output of submod_0), not the mask itself
+    assert r.model_inputs_template[1]['target'] == ['submod_0']
+    assert len(r.stages[0].outputs) == 2 and len(r.stages[1].inputs) == 2
     for s in r.stages:
         s.module.eval()
     a, b = r.run_local(kw['input_ids'], kw['attention_mask'], kw['token_type_ids'])
     ra, rb = m(**kw)
     assert torch.allclose(a, ra, atol=1e-5) and torch.allclose(b, rb, atol=1e-5)
+
+
+def test_model_input_used_by_two_stages_is_relayed():
+    class TwoUse(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = torch.nn.Linear(8, 8), torch.nn.Linear(8, 8), torch.nn.Linear(8, 4)
+
+        def forward(self, x, scale):
+            h = self.a(x) * scale
+            h = torch.relu(self.b(h))
+            return self.c(h) * scale
+
+    m = TwoUse().eval()
+    x, scale = torch.randn(3, 8), torch.rand(3, 1)
+    r = split_model(m, [0.5, 0.5], (x, scale))
+    assert r.model_input_names == ['x', 'scale']
+    assert r.model_inputs_template[1]['target'] == ['submod_0', 'submod_1']        # `scale` goes to the root AND the leaf
+    for s in r.stages:
+        s.module.eval()
+    assert torch.allclose(r.run_local(x, scale), m(x, scale), atol=1e-6)
 
 
 def test_genetic_algorithm_is_deterministic_and_feasible():
