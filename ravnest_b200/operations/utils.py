@@ -365,3 +365,24 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
     if verbose:
         print('Clusters formed:', clusters)
     return clusters
+
+
+# ---- reference names (operations/utils.py:200-263, pippy_utils.py:125) ---------------------------------------------------------
+def split_model_on_proportions(model, proportions, example_args=(), example_kwargs=None):
+    """``split_model`` under the reference's name: trace, cut at the parameter-share thresholds, return the per-stage modules."""
+    return split_model(model, proportions, example_args, example_kwargs or {}, check=False)
+
+
+def remake_proportions(proportions):
+    """The reference's retry policy when a split does not run: move 0.1 from the largest share to its neighbour."""
+    from .splitter import nudge_proportions
+    return nudge_proportions(list(proportions))
+
+
+def split_on_proportions(gm, proportions):
+    """Cut points for a traced graph module (the reference delegates this to pippy's size-threshold pass)."""
+    from .splitter import choose_split_points
+    return choose_split_points(gm, proportions)
+
+
+from .splitter import StageTracer as CustomTracer  # noqa: E402  (reference: operations/utils.py:200, unused by its current path)

@@ -87,3 +87,45 @@ def test_set_seed_and_memory_estimate():
     assert torch.equal(a, torch.rand(3))
     from ravnest_b200 import models
     assert rv.get_memory_reqs(models.CNN_Net(), input_size=(64, 1, 8, 8)) >= 1
+
+
+def test_reference_named_param_helpers_roundtrip():
+    """The reference's utils.py plumbing (optimizer over cloned parameters) works on plain modules with our helpers."""
+    import torch
+    from ravnest_b200 import utils
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    clones = list(utils.current_model_params_clone(model))
+    opt = torch.optim.SGD(clones, lr=0.5)
+    model(torch.randn(5, 4)).sum().backward()
+    before = [p.detach().clone() for p in model.parameters()]
+    utils.load_grads_into_optimizer(model, opt)
+    opt.step()
+    utils.load_optim_weights_into_model(model, opt)
+    for p, b, c in zip(model.parameters(), before, clones):
+        assert torch.allclose(p, b - 0.5 * p.grad) and p.data_ptr() == c.data_ptr()
+    assert utils.get_trainable_param_names(model) == ['0.weight', '0.bias', '1.weight', '1.bias']
+    stash = {n: p.detach().clone() * 0 for n, p in model.named_parameters()}
+    versions = [p._version for p in model.parameters()]
+    utils.load_state_dict_conserve_versions(model, stash)
+    assert all(float(p.abs().sum()) == 0 for p in model.parameters()) and versions == [p._version for p in model.parameters()]
+    chunks = utils.create_chunks({'w': torch.arange(24.).reshape(2, 12)}, 3)
+    assert chunks['w']['split_axis'] == 1 and [c.shape[1] for c in chunks['w']['data']] == [4, 4, 4]
+    oc = utils.create_chunks_optim({'w': {'step': torch.tensor(3.), 'exp_avg': torch.ones(6, 2)}}, 2)
+    assert oc['w']['step']['reshape'] and oc['w']['exp_avg']['split_axis'] == 0
+    adam = torch.optim.Adam(model.parameters())
+    state = {n: {'step': torch.tensor(7.), 'exp_avg': torch.zeros_like(p), 'exp_avg_sq': torch.ones_like(p)} for n, p in model.named_parameters()}
+    utils.load_optim_state(adam, state, model)
+    assert float(adam.state_dict()['state'][0]['step']) == 7.0
+    x = torch.tensor([1e9, -1e9, 1.5])
+    assert utils.compress_tensor_float16(x).dtype == torch.float16 and float(utils.compress_tensor_float16(x)[0]) == 65504.0
+    assert utils.extract_tensor_from_compression_float16(utils.compress_tensor_float16(x), torch.float32).dtype == torch.float32
+
+
+def test_planner_reference_aliases():
+    import torch
+    from ravnest_b200 import operations as ops_plan, models
+    res = ops_plan.split_model_on_proportions(models.CNN_Net(), [0.3, 0.3, 0.4], (torch.rand(4, 1, 8, 8),))
+    assert len(res.stages) == 3
+    assert ops_plan.remake_proportions([0.2, 0.6, 0.2]) == [0.2, 0.5, 0.3]
+    assert ops_plan.CustomTracer is ops_plan.StageTracer
