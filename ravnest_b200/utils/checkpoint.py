@@ -10,6 +10,13 @@ def _path(node, tag):
     return os.path.join(node.template_path, 'ckpt_{}.pt'.format(tag))
 
 
+def _philox_state(device):
+    if device.type != 'cuda':
+        return None
+    from ..ops import native
+    return native.rng_state(device).detach().to('cpu')
+
+
 def save_checkpoint(node, tag='latest'):
     cs = node.compute_session
     with cs.lock:
@@ -23,7 +30,8 @@ def save_checkpoint(node, tag='latest'):
                          'forward_pass_id': node.forward_pass_id, 'latest_backward_id': node.latest_backward_id,
                          'node_n_backwards': node.n_backwards, 'n_forwards': node.n_forwards},
             'rng': {'cpu': torch.get_rng_state(),
-                    'cuda': torch.cuda.get_rng_state(node.device) if node.device.type == 'cuda' else None},
+                    'cuda': torch.cuda.get_rng_state(node.device) if node.device.type == 'cuda' else None,
+                    'philox': _philox_state(node.device)},     # {seed, step} of the dropout kernels (ops/native.py rng_state)
         }
     path = _path(node, tag)
     tmp = path + '.tmp'
@@ -57,4 +65,7 @@ def load_checkpoint(node, tag='latest'):
         torch.set_rng_state(state['rng']['cpu'])
         if state['rng']['cuda'] is not None and node.device.type == 'cuda':
             torch.cuda.set_rng_state(state['rng']['cuda'], node.device)
+        if state['rng'].get('philox') is not None and node.device.type == 'cuda':
+            from ..ops import native
+            native.rng_state(node.device).copy_(state['rng']['philox'].to(node.device))
     return True

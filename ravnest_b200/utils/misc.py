@@ -10,8 +10,8 @@ from .serialization import load_submodel
 
 
 def set_seed(seed=42):
-    """Seed python / numpy / torch (CPU + every CUDA device) and ask for deterministic cuDNN
-    (reference utils.py:196-209)."""
+    """Seed python / numpy / torch (CPU + every CUDA device), reset the Philox state of the native dropout kernels and ask for
+    deterministic cuDNN (reference utils.py:196-209)."""
     random.seed(seed)
     np.random.seed(seed)
     torch.manual_seed(seed)
@@ -20,6 +20,12 @@ def set_seed(seed=42):
     torch.backends.cudnn.deterministic = True
     torch.backends.cudnn.benchmark = False
     os.environ['PYTHONHASHSEED'] = str(seed)
+    try:                                   # the dropout kernels' Philox {seed, step} is re-derived from the new torch seed
+        from ..ops import native
+        for state in native._RNG.values():         # in place: captured CUDA graphs keep pointing at these tensors
+            state.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+    except Exception:
+        pass
 
 
 def find_files_with_extension(root_folder, extension):
