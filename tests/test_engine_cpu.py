@@ -240,3 +240,114 @@ def test_two_cluster_ring_average_over_grpc(workdir, free_ports):
         assert n.compute_session.current_version() == 1
     for n in nodes:
         n.stop()
+
+
+def test_async_depth_two_matches_delayed_gradient_simulator():
+    """Two in-flight passes on a 2-stage pipeline: the engine must reproduce a plain-PyTorch simulator of the asynchronous
+    schedule — stage 0 differentiates pass k through the weights pass k's forward saw and applies that (stale) gradient to
+    whatever its current weights are; the leaf always runs forward + backward on its current weights."""
+    from torch.func import functional_call
+    torch.manual_seed(5)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+    xs = [torch.randn(8, 6) for _ in range(6)]
+    ys = [torch.randn(8, 3) for _ in range(6)]
+    lr = 0.1
+    for recompute in (True, False):
+        plans, engines = _stages(copy.deepcopy(model), [0.5, 0.5], xs[0], recompute=recompute)
+        s0, s1 = engines
+        # ---- simulator state: explicit copies of both stages' weights
+        m0, m1 = copy.deepcopy(s0.model), copy.deepcopy(s1.model)
+        w0 = {k: v.detach().clone() for k, v in m0.named_parameters()}
+        w1 = {k: v.detach().clone() for k, v in m1.named_parameters()}
+        seen = {}                                    # fpid -> stage-0 weights its forward used
+
+        def sim_forward(k):
+            seen[k] = {n: t.clone() for n, t in w0.items()}
+            with torch.no_grad():
+                return functional_call(m0, seen[k], (xs[k],))
+
+        def sim_leaf(k, act):
+            a = act.clone().requires_grad_(True)
+            p = {n: t.clone().requires_grad_(True) for n, t in w1.items()}
+            loss = torch.nn.functional.mse_loss(functional_call(m1, p, (a,)), ys[k])
+            loss.backward()
+            for n in w1:
+                w1[n] = w1[n] - lr * p[n].grad
+            return float(loss), a.grad
+
+        def sim_backward(k, gout):
+            p = {n: t.clone().requires_grad_(True) for n, t in seen.pop(k).items()}
+            functional_call(m0, p, (xs[k],)).backward(gout)
+            for n in w0:
+                w0[n] = w0[n] - lr * p[n].grad      # stale gradient, current weights
+
+        # ---- engine helpers (what Node does across processes)
+        acts, sim_acts, losses, sim_losses = {}, {}, [], []
+
+        def eng_forward(k):
+            out = s0.forward(k, [xs[k]], input_grads=False)
+            acts[k] = plans[0].root_payload(out, [xs[k]])
+
+        def eng_leaf(k):
+            loss, in_grads = s1.loss_step(plans[1].gather_args(acts.pop(k)), ys[k])
+            losses.append(float(loss))
+            return plans[1].add_input_grads({}, in_grads)
+
+        # ---- the asynchronous schedule with depth 2: F0 F1 | L0 B0 F2 | L1 B1 F3 | ...
+        for k in (0, 1):
+            eng_forward(k)
+            sim_acts[k] = sim_forward(k)
+        for k in range(len(xs)):
+            grads = eng_leaf(k)
+            loss, gout = sim_leaf(k, sim_acts.pop(k))
+            sim_losses.append(loss)
+            s0.backward(k, plans[0].take_output_grads(grads))
+            sim_backward(k, gout)
+            if k + 2 < len(xs):
+                eng_forward(k + 2)
+                sim_acts[k + 2] = sim_forward(k + 2)
+        assert losses == pytest.approx(sim_losses, rel=1e-5, abs=1e-7)
+        for n, p in zip(s0.store.names, s0.store.master_views):
+            assert torch.allclose(p, w0[n], atol=1e-6), n
+        for n, p in zip(s1.store.names, s1.store.master_views):
+            assert torch.allclose(p, w1[n], atol=1e-6), n
+        assert not s0.flights and all(s.refs == 0 for s in s0.store.slots)
+
+
+def test_restarted_replica_rejoins_with_latest_weights_over_grpc(workdir, free_ports):
+    """Failure-recovery path: a node that was killed and restarted from its initial artefacts calls
+    ``update_with_latest_weights`` and continues from its ring peer's current parameters (``get_latest_weights`` RPC)."""
+    rv.set_seed(2)
+    ports = free_ports(4)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+
+    def make(i):
+        return rv.Node(name='node_{}'.format(i), optimizer=torch.optim.SGD, optimizer_params={'lr': 0.1}, criterion=_loss_fn,
+                       labels=[(None, torch.zeros(1, 10))], device=torch.device('cpu'), transport='grpc', reset=False)
+
+    nodes = {i: make(i) for i in range(4)}
+    try:
+        # the surviving cluster (nodes 2, 3) has trained: its parameters moved away from the initial ones
+        with torch.no_grad():
+            for i in (2, 3):
+                nodes[i].compute_session.store.master.add_(0.25 * (i + 1))
+                nodes[i].compute_session.store.publish()
+        # node 0 dies (fault injection 'kill') and is restarted from node_data/: initial weights, version 0
+        nodes[0].stop()
+        time.sleep(0.3)
+        nodes[0] = make(0)
+        initial = nodes[0].compute_session.store.master.clone()
+        nodes[0].update_with_latest_weights()
+        peer = nodes[2].compute_session.store
+        mine = nodes[0].compute_session.store
+        for a, b in zip(mine.master_views, peer.master_views):
+            assert torch.allclose(a, b)
+        assert not torch.allclose(mine.master, initial)
+        # the adopted weights are what the next forward uses
+        for leaf, view in zip(mine.current.leaves, mine.master_views):
+            assert torch.allclose(leaf.detach().float(), view.float())
+    finally:
+        for n in nodes.values():
+            n.stop()
