@@ -1,7 +1,7 @@
 """Hot-op dispatch: hand-written sm_100a kernels on CUDA, plain PyTorch reference elsewhere.
 
 ``backend()`` is ``'native'`` by default: CUDA tensors go to the kernels in ``ops/csrc`` (loaded
-from the in-tree extension ``ravnest_b200/ops/_C*.so``) and a missing extension is a hard error —
+from the in-tree extension ``ravnest_b200/ops/rvn_C.so``) and a missing extension is a hard error —
 a GPU box must never fall back silently.  ``set_backend('torch')`` selects the stock
 cuBLAS/cuDNN/ATen path: that is the BASELINE TIER the product is measured against.
 
@@ -159,8 +159,9 @@ def cross_entropy(logits, target, ignore_index=-100):
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     """2-D convolution.  On CUDA (bf16, channels_last) pointwise convolutions run on the tcgen05 GEMM — in NHWC a 1x1
-    convolution IS ``[N*H*W, Cin] x [Cout, Cin]^T`` with zero data movement; other shapes use cuDNN (K4 implicit-GEMM
-    kernel is the next step)."""
+    convolution IS ``[N*H*W, Cin] x [Cout, Cin]^T`` with zero data movement — and square k x k convolutions (stride 1 / 2) on the
+    implicit-GEMM kernel (forward, stride-1 dgrad, split-K wgrad).  Remaining library cases (cuDNN): Cin % 8 != 0 (the RGB stem),
+    rectangular kernels, stride-2 data gradients, groups > 1 — counted in ``ops.native.fallbacks``."""
     if _native(x, weight):
         from . import native
         return native.conv2d(x, weight, bias, stride, padding, dilation, groups)

@@ -80,3 +80,21 @@ def check_gpu_usage(device=None):
     if not torch.cuda.is_available():
         return 0.0
     return torch.cuda.memory_allocated(device) / 1e6
+
+
+def compare_models(a, b, atol: float = 0.0, rtol: float = 0.0):
+    """Debug helper (reference compute.py:542-555): names of entries that differ between two modules / state dicts, with the
+    largest absolute difference of each.  Returns ``[]`` when they match."""
+    sa = a.state_dict() if hasattr(a, 'state_dict') else dict(a)
+    sb = b.state_dict() if hasattr(b, 'state_dict') else dict(b)
+    diffs = []
+    for key in sorted(set(sa) | set(sb)):
+        if key not in sa or key not in sb:
+            diffs.append((key, None))
+            continue
+        x, y = sa[key].detach().to('cpu'), sb[key].detach().to('cpu')
+        if x.shape != y.shape:
+            diffs.append((key, None))
+        elif not torch.allclose(x.double(), y.double(), atol=atol, rtol=rtol):
+            diffs.append((key, float((x.double() - y.double()).abs().max())))
+    return diffs
