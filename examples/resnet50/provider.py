@@ -11,14 +11,19 @@ from examples._gpu_common import launch  # noqa: E402
 from ravnest_b200 import Node, Trainer, set_seed  # noqa: E402
 
 set_seed(42)
-N = int(os.environ.get('SAMPLES', 2000))
-data = TensorDataset(torch.randn(N, 3, 224, 224), torch.randint(0, 200, (N,)))
+ROOT = os.environ.get('TINY_IMAGENET_ROOT')
+if ROOT:                                              # the real dataset when a copy is on disk
+    from examples.resnet50.TinyImageNet import TinyImageNet
+    data, val_data = TinyImageNet(ROOT, 'train'), TinyImageNet(ROOT, 'val')
+else:                                                 # no network in the build image: synthetic tensors of the same shape
+    N = int(os.environ.get('SAMPLES', 2000))
+    data = val_data = TensorDataset(torch.randn(N, 3, 224, 224), torch.randint(0, 200, (N,)))
 loss_fct = torch.nn.CrossEntropyLoss()
 
 
 def loaders():
     g = torch.Generator().manual_seed(42)
-    return DataLoader(data, batch_size=100, shuffle=True, generator=g, drop_last=True), DataLoader(data, batch_size=100)
+    return DataLoader(data, batch_size=100, shuffle=True, generator=g, drop_last=True), DataLoader(val_data, batch_size=100)
 
 
 def make_node(name, dev):
