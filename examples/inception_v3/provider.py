@@ -11,14 +11,22 @@ from examples._gpu_common import launch  # noqa: E402
 from ravnest_b200 import Node, Trainer, set_seed  # noqa: E402
 
 set_seed(42)
-N = int(os.environ.get('SAMPLES', 6400))
-data = TensorDataset(torch.randn(N, 3, 32, 32), torch.randint(0, 10, (N,)))
+ROOT = os.environ.get('CIFAR10_ROOT')
+if ROOT:                                              # torchvision's CIFAR-10 when a copy is on disk (no download offline)
+    import torchvision
+    import torchvision.transforms as T
+    tf = T.Compose([T.ToTensor(), T.Normalize((0.4914, 0.4822, 0.4465), (0.2470, 0.2435, 0.2616))])
+    data = torchvision.datasets.CIFAR10(ROOT, train=True, download=False, transform=tf)
+    val_data = torchvision.datasets.CIFAR10(ROOT, train=False, download=False, transform=tf)
+else:
+    N = int(os.environ.get('SAMPLES', 6400))
+    data = val_data = TensorDataset(torch.randn(N, 3, 32, 32), torch.randint(0, 10, (N,)))
 loss_fct = torch.nn.CrossEntropyLoss()
 
 
 def loaders():
     g = torch.Generator().manual_seed(42)
-    return DataLoader(data, batch_size=64, shuffle=True, generator=g, drop_last=True), DataLoader(data, batch_size=64)
+    return DataLoader(data, batch_size=64, shuffle=True, generator=g, drop_last=True), DataLoader(val_data, batch_size=64)
 
 
 def make_node(name, dev):
