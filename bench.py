@@ -186,7 +186,8 @@ class SyntheticImages:
 def main():
     args = parse()
     if args.impl == 'reference':
-        reference_unavailable()
+        if int(os.environ.get('RANK', '0')) == 0:        # one line per job, also under torchrun
+            reference_unavailable()
         return 0
     import torch
     import torch.distributed as dist
