@@ -60,10 +60,22 @@ class BertSelfOutput(nn.Module):
 
 
 class BertAttention(nn.Module):
+    """Attention half of an encoder block — one planner leaf, four fused kernels forward:
+    QKV GEMM(+bias) -> FMHA(+mask, +dropout) -> proj GEMM(+bias) -> LN(dropout(.) + residual)."""
+    _ravnest_leaf = True
+
     def __init__(self, cfg):
         super().__init__()
         self.self = rnn.SelfAttention(cfg.hidden_size, cfg.num_attention_heads, cfg.attention_probs_dropout_prob)
         self.output = BertSelfOutput(cfg)
+        self.hidden_dropout = cfg.hidden_dropout_prob
+
+    def forward(self, x, mask):
+        from .. import ops
+        p = self.hidden_dropout if self.training else 0.0
+        out = self.output
+        a = out.dense(self.self(x, mask))
+        return ops.layer_norm(a, out.LayerNorm.weight, out.LayerNorm.bias, out.LayerNorm.eps, x, p)
 
 
 class BertIntermediate(nn.Module):
@@ -73,37 +85,41 @@ class BertIntermediate(nn.Module):
 
 
 class BertOutput(nn.Module):
+    """Feed-forward half of an encoder block — the second planner leaf: FFN1 GEMM(+bias+GELU, act' side output) / FFN2
+    GEMM(+bias) as one fused MLP, then LN(dropout(.) + residual).  The FFN1 parameters keep their HF home
+    (``intermediate.dense``) and arrive as arguments, so state-dict keys are unchanged."""
+    _ravnest_leaf = True
+
     def __init__(self, cfg):
         super().__init__()
         self.dense = rnn.Linear(cfg.intermediate_size, cfg.hidden_size)
         self.LayerNorm = rnn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
         self.dropout = rnn.Dropout(cfg.hidden_dropout_prob)
+        self.hidden_dropout = cfg.hidden_dropout_prob
+        self.activation = 'gelu'
+
+    def forward(self, a, w1, b1):
+        from .. import ops
+        p = self.hidden_dropout if self.training else 0.0
+        h = ops.mlp(a, w1, b1, self.dense.weight, self.dense.bias, self.activation)
+        return ops.layer_norm(h, self.LayerNorm.weight, self.LayerNorm.bias, self.LayerNorm.eps, a, p)
 
 
 class BertLayer(nn.Module):
-    """One encoder block, a single FX leaf so the whole block runs as six fused kernels forward:
-    QKV GEMM(+bias) -> FMHA(+mask, +dropout) -> proj GEMM(+bias) -> LN(dropout(.)+residual) ->
-    FFN1 GEMM(+bias+GELU) / FFN2 GEMM(+bias) -> LN(dropout(.)+residual).
-    Sub-module / parameter names follow HF (attention.self / attention.output / intermediate / output)."""
-    _ravnest_leaf = True
+    """One encoder block = two planner leaves (attention half, feed-forward half), so a pipeline cut can fall in the middle of
+    a block: with 12 blocks + embeddings + MLM head on 2 stages, whole-block granularity left the stages 3.6-4.1 vs 4.5-5.1 ms
+    busy (profiles/RESULTS_r1.md).  Sub-module / parameter names follow HF (attention.self / attention.output /
+    intermediate / output)."""
 
     def __init__(self, cfg):
         super().__init__()
         self.attention = BertAttention(cfg)
         self.intermediate = BertIntermediate(cfg)
         self.output = BertOutput(cfg)
-        self.hidden_dropout = cfg.hidden_dropout_prob
 
     def forward(self, x, mask):
-        from .. import ops
-        p = self.hidden_dropout if self.training else 0.0
-        att, out = self.attention, self.output
-        ctx = att.self(x, mask)
-        a = att.output.dense(ctx)
-        a = ops.layer_norm(a, att.output.LayerNorm.weight, att.output.LayerNorm.bias, att.output.LayerNorm.eps, x, p)
-        inter = self.intermediate.dense
-        h = ops.mlp(a, inter.weight, inter.bias, out.dense.weight, out.dense.bias, inter.activation)
-        return ops.layer_norm(h, out.LayerNorm.weight, out.LayerNorm.bias, out.LayerNorm.eps, a, p)
+        a = self.attention(x, mask)
+        return self.output(a, self.intermediate.dense.weight, self.intermediate.dense.bias)
 
 
 class BertEncoder(nn.Module):

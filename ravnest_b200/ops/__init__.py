@@ -77,7 +77,7 @@ def reference_attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dro
         mask = torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
         att = att.masked_fill(~mask, float('-inf'))
     if key_padding_mask is not None:
-        if key_padding_mask.dtype == torch.float32:
+        if key_padding_mask.is_floating_point():
             att = att + key_padding_mask[:, None, None, :].to(att.dtype)
         else:
             att = att.masked_fill(~key_padding_mask.bool()[:, None, None, :], float('-inf'))
@@ -136,14 +136,15 @@ def dropout(x, p=0.5, training=True):
 
 
 def key_padding_bias(mask):
-    """Attention mask [B, S] (non-zero = attend) -> additive fp32 key bias (0 / -inf); an fp32 tensor is taken to be a bias already."""
-    if mask is None or mask.dtype == torch.float32:
-        return mask
-    return torch.zeros(mask.shape, dtype=torch.float32, device=mask.device).masked_fill_(~mask.bool(), float('-inf'))
+    """Attention mask [B, S] (any dtype, non-zero = attend — the HF convention) -> additive fp32 key bias (0 / -inf)."""
+    if mask is None:
+        return None
+    return torch.zeros(mask.shape, dtype=torch.float32, device=mask.device).masked_fill_(mask == 0, float('-inf'))
 
 
 def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
-    """``key_padding_mask``: [B, S] integer / bool mask (non-zero = attend) or the fp32 additive bias made by ``key_padding_bias``."""
+    """``key_padding_mask``: [B, S] integer / bool mask (non-zero = attend), or — any FLOATING dtype — the additive bias made by
+    ``key_padding_bias`` (0 = attend, -inf = padding; a relayed bias arrives in the next stage's compute dtype)."""
     if _native(qkv):
         from . import native
         return native.attention_qkv(qkv, heads, key_padding_mask, causal, dropout_p)

@@ -327,8 +327,8 @@ def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0
     if D == 64 and qkv.dtype == torch.bfloat16:
         kbias = None
         if key_padding_mask is not None:
-            if key_padding_mask.dtype == torch.float32:
-                kbias = key_padding_mask.contiguous()                     # already the additive bias (ops.key_padding_bias)
+            if key_padding_mask.is_floating_point():
+                kbias = key_padding_mask.float().contiguous()             # already the additive bias (ops.key_padding_bias), any precision
             else:
                 kbias = torch.zeros(B, S, dtype=torch.float32, device=qkv.device).masked_fill_(~key_padding_mask.bool(), float('-inf'))
         return _Attention.apply(qkv, heads, kbias, causal, float(dropout_p))
@@ -336,7 +336,7 @@ def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0
     q, k, v = qkv.view(B, S, 3, heads, D).permute(2, 0, 3, 1, 4)
     mask = None
     if key_padding_mask is not None:
-        mask = (key_padding_mask == 0 if key_padding_mask.dtype == torch.float32 else key_padding_mask.bool())[:, None, None, :]
+        mask = (key_padding_mask == 0 if key_padding_mask.is_floating_point() else key_padding_mask.bool())[:, None, None, :]
         if causal:
             mask = mask & torch.ones(S, S, dtype=torch.bool, device=qkv.device).tril()
     out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=dropout_p, is_causal=causal and mask is None)

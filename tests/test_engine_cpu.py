@@ -351,3 +351,37 @@ def test_restarted_replica_rejoins_with_latest_weights_over_grpc(workdir, free_p
     finally:
         for n in nodes.values():
             n.stop()
+
+
+@pytest.mark.parametrize('cut', [[0.45, 0.55], [0.3, 0.7]])
+def test_bert_pipeline_in_bf16_relays_the_key_bias(cut):
+    """BERT cut in the middle of the encoder, stages in bf16: the additive key bias made on the first stage is relayed to the
+    next one, where the engine casts every floating input to the compute dtype — padded keys must stay masked (the bias is
+    recognised by being floating point, not by being fp32) and a cut may fall between the two halves of an encoder block."""
+    torch.manual_seed(0)
+    cfg = models.BertConfig(vocab_size=128, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                            max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = models.BertForPreTraining(cfg)
+    mask = torch.ones(2, 16, dtype=torch.long)
+    mask[0, 9:] = 0
+    kw = {'input_ids': torch.randint(0, 128, (2, 16)), 'attention_mask': mask, 'token_type_ids': torch.zeros(2, 16, dtype=torch.long)}
+    labels, sop = torch.randint(0, 128, (2, 16)), torch.randint(0, 2, (2,))
+    r = split_model(m, cut, (), kw, balance='compute')
+    assert len(r.stages[1].inputs) == 2                                   # hidden state + relayed bias
+    crit = lambda out, tgt: models.bert_pretraining_loss(out, tgt[0], tgt[1])      # noqa: E731
+    plans, engines = [], []
+    for i, st in enumerate(r.stages):
+        plans.append(StagePlan(st.name, st.input_template(), st.output_template(), r.model_inputs_template if i == 0 else None))
+        engines.append(Compute(copy.deepcopy(st.module), optimizer_cls=torch.optim.SGD, optimizer_params={'lr': 0.05},
+                               criterion=crit if st.is_last else None, cluster_length=2, loss_filename=None, is_last=st.is_last,
+                               recompute=False, compute_dtype=torch.bfloat16))
+    flat = [kw['input_ids'], kw['attention_mask'], kw['token_type_ids']]
+    ins = [flat[src['out_idx']] for src in r.stages[0].inputs]
+    out = engines[0].forward(0, ins, input_grads=False)
+    args = plans[1].gather_args(plans[0].root_payload(out, ins))
+    loss, in_grads = engines[1].loss_step(args, (labels, sop))
+    ref = models.bert_pretraining_loss(m(**kw), labels, sop)
+    assert torch.isfinite(loss) and abs(float(loss) - float(ref)) < 0.08 * float(ref)       # bf16 vs fp32 on the same weights
+    # (a bias mistaken for a mask would mask every real key of the unpadded sample: softmax over -inf only -> NaN loss)
+    engines[0].backward(0, plans[0].take_output_grads(plans[1].add_input_grads({}, in_grads)))
+    assert all(torch.isfinite(e.store.master).all() for e in engines)
