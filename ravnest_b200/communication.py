@@ -65,6 +65,23 @@ class StagePlan:
         self.input_names = list(input_names or [])
 
     # ---- forward ---------------------------------------------------------------------------
+    def stage_args(self, model_inputs: Sequence[Any]) -> List[Any]:
+        """Root / solo stage: the model inputs (in the MODEL's signature order, which is how ``Node.forward_compute`` packs
+        positional and keyword inputs) re-ordered into this stage's placeholder order.  The splitter numbers a stage's
+        placeholders by first use, so e.g. BERT's root takes (input_ids, token_type_ids, attention_mask) while the model
+        signature is (input_ids, attention_mask, token_type_ids)."""
+        if not all(producer == 'model_inputs' for producer, _ in self.inputs):
+            raise ValueError('{} is not fed by model inputs only'.format(self.name))
+        return [model_inputs[idx] for _, idx in self.inputs]
+
+    def model_order(self, stage_inputs: Sequence[Any], model_inputs: Sequence[Any]) -> List[Any]:
+        """Inverse of ``stage_args`` for relaying: model-order list that prefers the stage's already prepared (device) tensors."""
+        merged = list(model_inputs)
+        for (producer, idx), value in zip(self.inputs, stage_inputs):
+            if producer == 'model_inputs' and idx < len(merged) and value is not None:
+                merged[idx] = value
+        return merged
+
     def gather_args(self, data: Dict[str, Dict[int, Dict[str, Any]]], consume: bool = True) -> List[Any]:
         """Pull this stage's positional args out of the relay dict; strike our name off each target
         list and drop entries nobody downstream needs (reference compute.py:329-407)."""

@@ -256,6 +256,7 @@ class Node:
         self.mailbox.put(FORWARD, msg)
 
     def _pack_inputs(self, tensors, kwargs) -> List[Any]:
+        """Positional + keyword inputs -> one list in the MODEL's signature order (``plan.stage_args`` maps it onto the stage)."""
         if tensors is None:
             positional = []
         elif isinstance(tensors, (list, tuple)):
@@ -280,7 +281,8 @@ class Node:
         """Inference pass through the pipeline (reference node.py:399-428).  ``output_type`` selects
         what the leaf does with the result: 'val_accuracy' | 'accuracy' | 'prediction'."""
         self._check()
-        args = self._pack_inputs(tensors, kwargs)
+        model_args = self._pack_inputs(tensors, kwargs)
+        args = self.plan.stage_args(model_args)
         ctx = torch.cuda.stream(self.compute_stream) if self.compute_stream is not None else _NullCtx()
         with ctx:       # same stream as the scheduler: ordered after every queued optimizer update
             if self.node_type == NodeTypes.SOLO:
@@ -288,7 +290,7 @@ class Node:
                 return self._consume_inference(out, output_type)
             self.status = NodeStatus.FORWARD
             out = self.compute_session.no_grad_forward(args)
-            data = self.plan.root_payload(out, args, self.compression)
+            data = self.plan.root_payload(out, model_args, self.compression)
             self.transport.send(FORWARD, make_message(ActionTypes.NO_GRAD_FORWARD, -1, data, output_type=output_type))
         self.status = NodeStatus.IDLE
         return None
@@ -305,14 +307,16 @@ class Node:
     # ------------------------------------------------------------------ action handlers
     def root_forward(self, msg) -> None:
         self.status = NodeStatus.FORWARD
-        fpid, args = msg['forward_pass_id'], msg['args']
+        fpid, model_args = msg['forward_pass_id'], msg['args']        # model signature order (see _pack_inputs)
+        args = self.plan.stage_args(model_args)                         # this stage's placeholder order
         if self.node_type == NodeTypes.SOLO:
             targets = self._next_labels()
             self.compute_session.loss_step(args, targets[0], input_grads=False)
             self._after_backward(fpid, epoch_change=targets[1])
             return
         out = self.compute_session.forward(fpid, args, input_grads=False)
-        inputs = self.compute_session.flights[fpid].inputs or args
+        prepared = self.compute_session.flights[fpid].inputs
+        inputs = self.plan.model_order(prepared, model_args) if prepared else model_args
         data = self.plan.root_payload(out, inputs, self.compression)
         self.transport.send(FORWARD, make_message(ActionTypes.FORWARD, fpid, data))
         self.metrics['forward'] += 1

@@ -48,3 +48,26 @@ def test_four_stage_pipeline_over_gloo(workdir, free_ports):
     assert all(r['n_backwards'] == 16 for r in res[:3])                  # 2 epochs x 8 batches, one replica
     losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_3.txt'))]
     assert len(losses) == 16 and losses[-1] < losses[0]
+
+
+@pytest.mark.slow
+def test_bert_three_stage_pipeline_over_gloo(workdir, free_ports):
+    """Keyword model inputs, dict targets, ragged padding masks whose additive bias is relayed root -> stem -> leaf, LAMB with
+    gradient accumulation: the BERT path of bench.py, on CPU."""
+    rv.set_seed(7)
+    cfg = models.BertConfig(vocab_size=128, hidden_size=64, num_hidden_layers=3, num_attention_heads=4, intermediate_size=128,
+                            max_position_embeddings=32)
+    kw = {'input_ids': torch.randint(0, 128, (4, 16)), 'attention_mask': torch.ones(4, 16, dtype=torch.long),
+          'token_type_ids': torch.zeros(4, 16, dtype=torch.long)}
+    rv.clusterize(models.BertForPreTraining(cfg), example_kwargs=kw, topology={'stages': 3, 'replicas': 1},
+                  node_configs=rv.default_gpu_configs(3), base_dir=str(workdir), balance='compute')
+    env = dict(os.environ, RAVNEST_HOME=str(workdir), OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '3', '--master-addr', '127.0.0.1',
+           '--master-port', str(29000 + free_ports(1)[0] % 900), os.path.join(HERE, 'dist_bert_worker.py')]
+    proc = subprocess.run(cmd, cwd=str(workdir), env=env, capture_output=True, text=True, timeout=420)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    res = [json.load(open(os.path.join(str(workdir), 'result.json.{}'.format(r)))) for r in range(3)]
+    assert [r['node_type'] for r in res] == ['root', 'stem', 'leaf']
+    assert all(r['finite'] for r in res) and all(r['n_backwards'] == 18 for r in res)        # 3 epochs x 6 batches
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_2.txt'))]
+    assert len(losses) == 9 and all(l == l for l in losses) and losses[-1] < losses[0]       # one line per optimizer update
