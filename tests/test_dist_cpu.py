@@ -71,3 +71,40 @@ def test_bert_three_stage_pipeline_over_gloo(workdir, free_ports):
     assert all(r['finite'] for r in res) and all(r['n_backwards'] == 18 for r in res)        # 3 epochs x 6 batches
     losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_2.txt'))]
     assert len(losses) == 9 and all(l == l for l in losses) and losses[-1] < losses[0]       # one line per optimizer update
+
+
+def _run_multi(workdir, port, world, model_args):
+    env = dict(os.environ, RAVNEST_HOME=str(workdir), OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(HERE, 'dist_multi_worker.py')] + model_args
+    proc = subprocess.run(cmd, cwd=str(workdir), env=env, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    return [json.load(open(os.path.join(str(workdir), 'result.json.{}'.format(r)))) for r in range(world)]
+
+
+@pytest.mark.slow
+def test_inception_three_stage_pipeline_over_gloo(workdir, free_ports):
+    """BASELINE.json config #4 on CPU: Inception-V3 (CIFAR variant) as a 3-stage pipeline, compute-balanced cuts that fall between
+    Inception blocks (branch concatenations stay inside a stage)."""
+    rv.set_seed(11)
+    rv.clusterize(models.Inception3(), example_args=(torch.rand(2, 3, 32, 32),), topology={'stages': 3, 'replicas': 1},
+                  node_configs=rv.default_gpu_configs(3), base_dir=str(workdir), balance='compute')
+    res = _run_multi(workdir, 29000 + free_ports(1)[0] % 900, 3, ['--model', 'inception', '--epochs', '2'])
+    assert [r['node_type'] for r in res] == ['root', 'stem', 'leaf']
+    assert all(r['finite'] and r['n_backwards'] == 6 for r in res)
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_2.txt'))]
+    assert len(losses) == 6 and all(l == l for l in losses)
+
+
+@pytest.mark.slow
+def test_sorter_eight_stage_pipeline_over_gloo(workdir, free_ports):
+    """BASELINE.json config #5 on CPU: the minGPT sorter as an 8-stage pure pipeline, one node per stage, tensor labels."""
+    rv.set_seed(11)
+    cfg = models.GPTConfig(model_type='gpt-nano', vocab_size=3, block_size=11, embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0)
+    rv.clusterize(models.GPT(cfg), example_args=(torch.randint(0, 3, (32, 11)),), topology={'stages': 8, 'replicas': 1},
+                  node_configs=rv.default_gpu_configs(8), base_dir=str(workdir), balance='compute')
+    res = _run_multi(workdir, 29000 + free_ports(1)[0] % 900, 8, ['--model', 'sorter', '--epochs', '6'])
+    assert [r['node_type'] for r in res] == ['root'] + ['stem'] * 6 + ['leaf']
+    assert all(r['finite'] and r['n_backwards'] == 24 for r in res)
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_7.txt'))]
+    assert len(losses) == 24 and losses[-1] < losses[0]
