@@ -380,6 +380,14 @@ def main():
         e2e_ms, e2e_wall = timed(args.steps, 'host', True)
         e2e = {'value': replicas * batch * args.steps / (max(e2e_ms, e2e_wall) / 1e3), 'unit': unit,
                'h2d_bytes_per_step': pool_host.input_bytes(), 'd2h_bytes_per_step': 4, 'ms_per_step': max(e2e_ms, e2e_wall) / args.steps}
+    # the loss every leaf / solo rank computed last (after the timed regions): evidence that the step trains, not just runs
+    cs = node.compute_session
+    mine = float(cs.last_loss.float()) if getattr(cs, 'last_loss', None) is not None else None
+    last_losses = [None] * world
+    if world > 1:
+        dist.all_gather_object(last_losses, mine, group=gloo)
+    else:
+        last_losses = [mine]
     launches = count_launches(node, feed, pool_dev, driver, sync, Labels) if rank == 0 or world > 1 else None
     if rank == 0:
         value = replicas * batch * args.steps / (dev_ms / 1e3)
@@ -398,6 +406,7 @@ def main():
             'gpu_launches': (launches or {}).get('ours_per_step', 0) * args.steps if isinstance(launches, dict) else 0,
             'gpu_launches_detail': launches, 'wall_ms_per_step': dev_wall / args.steps,
             'exposed_comm_ms_per_step': exposed_ms, 'stage_busy_ms_per_rank': busy_all,
+            'last_loss_per_rank': [None if v is None else round(v, 4) for v in last_losses],
         }
         if args.layers:
             result['invalid'] = 'debug run with --layers'
