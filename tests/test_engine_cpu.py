@@ -385,3 +385,33 @@ def test_bert_pipeline_in_bf16_relays_the_key_bias(cut):
     # (a bias mistaken for a mask would mask every real key of the unpadded sample: softmax over -inf only -> NaN loss)
     engines[0].backward(0, plans[0].take_output_grads(plans[1].add_input_grads({}, in_grads)))
     assert all(torch.isfinite(e.store.master).all() for e in engines)
+
+
+def test_solo_node_feeds_keyword_inputs_in_stage_order(workdir, free_ports):
+    """One-node cluster (the 1-GPU bench path): keyword inputs arrive in the model's signature order and must be mapped onto the
+    stage's placeholder order (BERT: ids, token types, mask) — the first loss must equal the unsplit model's loss."""
+    rv.set_seed(5)
+    cfg = models.BertConfig(vocab_size=128, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128,
+                            max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = models.BertForPreTraining(cfg)
+    mask = torch.ones(4, 16, dtype=torch.long)
+    mask[1, 10:] = 0
+    mask[3, 5:] = 0
+    batch = {'input_ids': torch.randint(1, 128, (4, 16)), 'attention_mask': mask, 'token_type_ids': torch.randint(0, 2, (4, 16))}
+    labels, sop = torch.randint(0, 128, (4, 16)), torch.randint(0, 2, (4,))
+    port = free_ports(1)[0]
+    rv.clusterize(model, example_kwargs=batch, topology={'stages': 1, 'replicas': 1},
+                  node_configs={'0': {'IP': '127.0.0.1:{}'.format(port), 'benchmarks': {'ram': 1, 'bandwidth': 10}}})
+    expected = float(models.bert_pretraining_loss(model(**batch), labels, sop))
+    node = rv.Node(name='node_0', optimizer=torch.optim.SGD, optimizer_params={'lr': 0.0}, device=torch.device('cpu'), transport='grpc',
+                   criterion=lambda out, tgt: models.bert_pretraining_loss(out, tgt[0], tgt[1]), labels=[(labels, sop)], reset=False)
+    try:
+        assert node.node_type == 'solo'
+        node.forward_compute(**batch)
+        node.wait_for_backwards()
+        assert float(node.compute_session.last_loss) == pytest.approx(expected, rel=1e-5)
+        # a swapped mask / token-type pair gives a different (here: non-finite or clearly different) loss
+        swapped = models.bert_pretraining_loss(model(batch['input_ids'], batch['token_type_ids'], batch['attention_mask']), labels, sop)
+        assert not torch.isfinite(swapped) or abs(float(swapped) - expected) > 1e-3
+    finally:
+        node.stop()
