@@ -240,14 +240,17 @@ def estimate_costs(gm: fx.GraphModule, inputs: Sequence[Any], scale: float = 1.0
 def measure_costs(gm: fx.GraphModule, inputs: Sequence[Any], device, dtype=torch.bfloat16, batch_scale: int = 1,
                   iters: int = 3) -> Dict[fx.Node, float]:
     """Profile-guided planning: run a copy of the traced model on ``device`` in the compute dtype with the REAL per-replica batch
-    (the example tiled ``batch_scale`` times along dim 0) and time every node's forward with CUDA events on the native kernels.
-    The step-time share of a node is taken as proportional to its forward time (backward ~ 2x forward for GEMM, conv, norm and
-    attention alike), which is what the split needs."""
+    (the example tiled ``batch_scale`` times along dim 0) and time every node's forward AND backward on the kernels the job
+    will run (CUDA events; wall clock on CPU).  Each node is differentiated on its own — inputs detached, gradient of ones —
+    so a node's cost includes its data and weight gradients; nodes that cannot be differentiated in isolation (in-place
+    updates of their input) fall back to 3 x forward."""
     import copy
+    import time
     dev = torch.device(device)
+    cuda = dev.type == 'cuda'
     twin = copy.deepcopy(gm).to(dev)
     for p in list(twin.parameters()) + list(twin.buffers()):
-        if p.is_floating_point():
+        if p.is_floating_point() and cuda:
             p.data = p.data.to(dtype)
     twin.train()
 
@@ -257,11 +260,52 @@ def measure_costs(gm: fx.GraphModule, inputs: Sequence[Any], device, dtype=torch
         if batch_scale > 1 and t.dim() >= 1:
             t = t.repeat(batch_scale, *([1] * (t.dim() - 1)))
         t = t.to(dev)
-        if t.is_floating_point():
+        if t.is_floating_point() and cuda:
             t = t.to(dtype)
             if t.dim() == 4:
                 t = t.contiguous(memory_format=torch.channels_last)
         return t
+
+    def mark():
+        if cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        return time.perf_counter()
+
+    def span(a, b):
+        return a.elapsed_time(b) * 1e-3 if cuda else b - a
+
+    def leafify(v):
+        if isinstance(v, torch.Tensor):
+            v = v.detach()
+            return v.requires_grad_(True) if v.is_floating_point() else v
+        if isinstance(v, (tuple, list)):
+            return type(v)(leafify(x) for x in v)
+        if isinstance(v, dict):
+            return {k: leafify(x) for k, x in v.items()}
+        return v
+
+    def detach_tree(v):
+        if isinstance(v, torch.Tensor):
+            return v.detach()
+        if isinstance(v, (tuple, list)):
+            return type(v)(detach_tree(x) for x in v)
+        if isinstance(v, dict):
+            return {k: detach_tree(x) for k, x in v.items()}
+        return v
+
+    def grad_roots(v, out):
+        if isinstance(v, torch.Tensor):
+            if v.is_floating_point() and v.requires_grad:
+                out.append(v)
+        elif isinstance(v, (tuple, list)):
+            for x in v:
+                grad_roots(x, out)
+        elif isinstance(v, dict):
+            for x in v.values():
+                grad_roots(x, out)
+        return out
 
     args = [stage(t) for t in inputs]
     samples: Dict[str, List[float]] = {}
@@ -270,24 +314,43 @@ def measure_costs(gm: fx.GraphModule, inputs: Sequence[Any], device, dtype=torch
         def run_node(self, n: fx.Node) -> Any:
             if n.op not in ('call_module', 'call_function', 'call_method'):
                 return super().run_node(n)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = super().run_node(n)
-            e1.record()
-            pending.append((n.name, e0, e1))
-            return out
+            a, kw = self.fetch_args_kwargs_from_env(n)
+            try:
+                la, lkw = leafify(a), leafify(kw)
+                with torch.enable_grad():
+                    t0 = mark()
+                    out = getattr(self, n.op)(n.target, la, lkw)
+                    t1 = mark()
+                    roots = grad_roots(out, [])
+                    seeds = [torch.ones_like(r) for r in roots]
+                    t2 = mark()
+                    if roots:
+                        torch.autograd.backward(roots, seeds)
+                    t3 = mark()
+                pending.append((n.name, (t0, t1), (t2, t3)))
+                return detach_tree(out)
+            except RuntimeError:                              # e.g. an in-place update of a (now leaf) input: forward only
+                with torch.no_grad():
+                    t0 = mark()
+                    out = getattr(self, n.op)(n.target, a, kw)
+                    t1 = mark()
+                pending.append((n.name, (t0, t1), None))
+                return out
 
-    with torch.no_grad():
-        for it in range(iters + 2):
-            pending: List[Tuple[str, Any, Any]] = []
+    for it in range(iters + 2):
+        pending: List[Tuple[str, Any, Any]] = []
+        with torch.no_grad():
             _Timed(twin).run(*args)
+        if cuda:
             torch.cuda.synchronize(dev)
-            if it >= 2:                                  # two warm-up passes (descriptor caches, cuDNN heuristics, allocator)
-                for name, e0, e1 in pending:
-                    samples.setdefault(name, []).append(e0.elapsed_time(e1) * 1e-3)
+        if it >= 2:                                          # two warm-up passes (descriptor caches, cuDNN heuristics, allocator)
+            for name, fwd, bwd in pending:
+                f = span(*fwd)
+                samples.setdefault(name, []).append(f + span(*bwd) if bwd is not None else 3.0 * f)
+        twin.zero_grad(set_to_none=True)
     del twin
     by_name = {k: sorted(v)[len(v) // 2] for k, v in samples.items()}
-    return {n: 3.0 * by_name.get(n.name, 0.0) for n in gm.graph.nodes}
+    return {n: by_name.get(n.name, 0.0) for n in gm.graph.nodes}
 
 
 def choose_split_points_by_cost(gm: fx.GraphModule, proportions: Sequence[float], costs: Dict[fx.Node, float]) -> List[fx.Node]:
@@ -498,8 +561,8 @@ def split_model(model: nn.Module, proportions: Sequence[float], example_args: Se
                 cost_scale: float = 1.0, device=None, dtype=torch.bfloat16) -> SplitResult:
     """Trace + split policy + carve.  ``balance='params'`` is the reference's parameter-share threshold policy;
     ``balance='compute'`` makes ``proportions`` shares of the estimated step time (``estimate_costs``); ``balance='measured'``
-    times every node on ``device`` with the native kernels at the real batch (``measure_costs``; falls back to the estimate
-    when no GPU is visible).  ``check`` runs the
+    times every node's forward + backward on ``device`` with the native kernels at the real batch (``measure_costs``; falls
+    back to the estimate when no GPU is visible and ``device`` is not explicitly the CPU).  ``check`` runs the
     chained stages once and compares against the traced module on the example inputs (the reference only checks "does not raise")."""
     assert balance in ('params', 'compute', 'measured')
     example_kwargs = dict(example_kwargs or {})
@@ -507,7 +570,7 @@ def split_model(model: nn.Module, proportions: Sequence[float], example_args: Se
     flat_inputs = list(example_args) + [example_kwargs[k] for k in input_names[len(example_args):]]
     propagate_meta(gm, flat_inputs)
     costs = None
-    if balance == 'measured' and torch.cuda.is_available():
+    if balance == 'measured' and (torch.cuda.is_available() or (device is not None and torch.device(device).type == 'cpu')):
         costs = measure_costs(gm, flat_inputs, device or torch.device('cuda', torch.cuda.current_device()), dtype,
                               batch_scale=max(1, int(round(cost_scale))))
     elif balance in ('compute', 'measured'):

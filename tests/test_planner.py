@@ -190,3 +190,25 @@ def test_compute_balanced_split_equalises_estimated_step_time():
             for st in plan.stages:
                 st.module.eval()
             assert torch.allclose(plan.run_local(x), ref, atol=1e-5)
+
+
+def test_measured_balance_times_forward_and_backward_per_node():
+    """Profile-guided planning mechanics on the CPU (wall clock instead of CUDA events): every traced node is run forward and
+    differentiated on its own; nodes with in-place updates of their input (torchvision's ``out += identity``) fall back to
+    forward-only timing; the resulting stages still compute the model."""
+    import torchvision
+    from ravnest_b200.operations.splitter import measure_costs, split_model, trace_model
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18(num_classes=10)
+    x = torch.randn(2, 3, 64, 64)
+    gm, _ = trace_model(model, (x,))
+    costs = measure_costs(gm, [x], 'cpu', iters=1)
+    timed = [n for n in gm.graph.nodes if n.op in ('call_module', 'call_function', 'call_method')]
+    assert all(costs[n] > 0 for n in timed)
+    plan = split_model(model, [0.5, 0.5], (x,), balance='measured', device='cpu')
+    assert len(plan.stage_costs) == 2 and max(plan.stage_costs) / min(plan.stage_costs) < 2.0
+    model.eval()
+    for st in plan.stages:
+        st.module.eval()
+    with torch.no_grad():
+        assert torch.allclose(plan.run_local(x), model(x), atol=1e-5)
