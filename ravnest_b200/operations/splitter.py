@@ -570,11 +570,18 @@ def split_model(model: nn.Module, proportions: Sequence[float], example_args: Se
     flat_inputs = list(example_args) + [example_kwargs[k] for k in input_names[len(example_args):]]
     propagate_meta(gm, flat_inputs)
     costs = None
-    if balance == 'measured' and (torch.cuda.is_available() or (device is not None and torch.device(device).type == 'cpu')):
-        costs = measure_costs(gm, flat_inputs, device or torch.device('cuda', torch.cuda.current_device()), dtype,
-                              batch_scale=max(1, int(round(cost_scale))))
-    elif balance in ('compute', 'measured'):
-        costs = estimate_costs(gm, flat_inputs, cost_scale)
+    if len(proportions) > 1 and balance in ('compute', 'measured'):          # a single stage needs no balancing
+        if balance == 'measured' and (torch.cuda.is_available() or (device is not None and torch.device(device).type == 'cpu')):
+            try:
+                costs = measure_costs(gm, flat_inputs, device or torch.device('cuda', torch.cuda.current_device()), dtype,
+                                      batch_scale=max(1, int(round(cost_scale))))
+            except Exception as err:      # planning must not take the job down: fall back to the analytic estimate
+                import warnings
+                warnings.warn('measured stage balancing failed ({!r}); using the estimated costs'.format(err))
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+        if costs is None:
+            costs = estimate_costs(gm, flat_inputs, cost_scale)
     attempt = list(proportions)
     last_err = None
     for _ in range(2):
