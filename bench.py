@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
     ap.add_argument('--balance', default='measured', choices=['measured', 'compute', 'params'], help='stage-balancing policy of the planner')
     ap.add_argument('--proportions', default=None, help='comma-separated parameter shares per stage (reference policy) instead of the compute-balanced plan')
+    ap.add_argument('--prefetch-h2d', action='store_true', help='start the H2D copy of a batch at submit time on a copy stream (experimental)')
     ap.add_argument('--no-graphs', action='store_true', help='disable CUDA-graph capture of the stage step')
     ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
     return ap.parse_args()
@@ -311,7 +312,7 @@ def main():
 
     node = rv.Node(name='node_{}'.format(rank), criterion=criterion, labels=Labels(), device=dev, base_dir=home,
                    reduce_factor=1 << 30, dp_mode='gradient', fused_optimizer=fused, loss_filename=None,
-                   recompute=False, use_cuda_graphs=not args.no_graphs, **node_kwargs)
+                   recompute=False, use_cuda_graphs=not args.no_graphs, prefetch_h2d=args.prefetch_h2d, **node_kwargs)
     driver = node.node_type in ('root', 'solo')
 
     def sync():

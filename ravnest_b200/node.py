@@ -64,6 +64,8 @@ class Node:
         self.loss_filename = os.path.join(self.base_dir, loss_filename) if loss_filename and not os.path.isabs(loss_filename) else loss_filename
         self.val_accuracy_file = os.path.join(self.base_dir, 'val_accuracies.txt')
         self.labels_to_device = kwargs.get('labels_to_device', False)
+        self.prefetch_h2d = bool(kwargs.get('prefetch_h2d', False))
+        self._h2d_stream = None
         self.status = NodeStatus.IDLE
         if kwargs.get('reset', True):
             self.reset()
@@ -214,7 +216,8 @@ class Node:
                 continue
             _lane, msg = item
             if '_ready_event' in msg:
-                self.transport.adopt(msg, self.device, self.tracer)
+                from .runtime.dist_transport import DistTransport
+                DistTransport.adopt(msg, self.device, self.tracer)
             action = msg['action']
             if self.faults.rules and self.faults.check(action, msg.get('forward_pass_id', -1)) == 'drop':
                 continue
@@ -251,9 +254,26 @@ class Node:
             self.wait_for_backwards()
         args = self._pack_inputs(tensors, kwargs)
         msg = make_message(ActionTypes.ROOT_FORWARD, self.forward_pass_id, {}, args=args)
+        if self.prefetch_h2d and self.device.type == 'cuda':
+            self._stage_inputs_async(msg)
         self.forward_pass_id += 1
         self.n_forwards += 1
         self.mailbox.put(FORWARD, msg)
+
+    def _stage_inputs_async(self, msg) -> None:
+        """Opt-in (``prefetch_h2d=True``): start the host-to-device copy of this batch NOW, on a dedicated copy stream, from the
+        submitting thread — it overlaps the compute of the passes already in flight instead of running at the head of this
+        pass on the compute stream (ResNet-50 batch 100: 60 MB, ~1.1 ms over PCIe 5).  The scheduler waits on the event."""
+        if self._h2d_stream is None:
+            self._h2d_stream = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(self._h2d_stream):
+            staged = [a.to(self.device, non_blocking=True) if isinstance(a, torch.Tensor) and a.device.type == 'cpu' else a
+                      for a in msg['args']]
+            ev = torch.cuda.Event()
+            ev.record(self._h2d_stream)
+        msg['args'] = staged
+        msg['_ready_event'] = ev
+        msg['_tensors'] = [t for t in staged if isinstance(t, torch.Tensor) and t.is_cuda]
 
     def _pack_inputs(self, tensors, kwargs) -> List[Any]:
         """Positional + keyword inputs -> one list in the MODEL's signature order (``plan.stage_args`` maps it onto the stage)."""
