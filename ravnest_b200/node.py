@@ -189,6 +189,11 @@ class Node:
         self.heartbeat.start()
         return self.heartbeat
 
+    def wait_until_stopped(self, timeout: Optional[float] = None) -> bool:
+        """Block until this node has been stopped — by ``stop()`` here or by the SHUTDOWN message a stopping root sends down
+        its pipeline.  Provider scripts of stem / leaf nodes end with this call."""
+        return self._stop.wait(timeout)
+
     def stop(self) -> None:
         if self.heartbeat is not None:
             self.heartbeat.stop()

@@ -223,28 +223,6 @@ def split_model_equal(model=None, num_splits=None, proportions=None, example_arg
     return result
 
 
-def _wire_chain(nodes: List[Node]) -> None:
-    for i, node in enumerate(nodes):
-        if i < len(nodes) - 1:
-            host, port = nodes[i + 1].address.split(':')
-            node.forward_target_host, node.forward_target_port = host, port
-        if i > 0:
-            host, port = nodes[i - 1].address.split(':')
-            node.backward_target_host, node.backward_target_port = host, port
-        node.stage_index = i
-
-
-def _node_type(node: Node) -> Optional[str]:
-    fwd, bwd = node.forward_target_host is not None, node.backward_target_host is not None
-    if fwd and not bwd:
-        return 'root'
-    if bwd and not fwd:
-        return 'leaf'
-    if fwd and bwd:
-        return 'stem'
-    return 'solo'
-
-
 def default_gpu_configs(n: int, base_port: int = 8080, host: str = '127.0.0.1') -> Dict[str, Dict]:
     """node_configs.json content for an n-GPU B200 box."""
     return {str(i): {'IP': '{}:{}'.format(host, base_port + i), 'gpu': i,
@@ -277,7 +255,7 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
     plans: Dict[Tuple, SplitResult] = {}           # identical chains (GPU grids) share one traced / measured plan
     for cluster in clusters:
         chain = cluster.ordered_nodes()
-        _wire_chain(chain)
+        cluster.wire()
         # reference policy: parameter shares (heterogeneous hosts are sized by RAM).  GPU grids are homogeneous, so unless the
         # caller pins ``proportions`` the stages are balanced by estimated step time instead (balance='compute').
         mode = balance or ('compute' if (topology is not None and proportions is None) else 'params')
@@ -353,7 +331,7 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
             'forward_target_port': int(node.forward_target_port) if node.forward_target_port is not None else None,
             'backward_target_host': node.backward_target_host,
             'backward_target_port': int(node.backward_target_port) if node.backward_target_port is not None else None,
-            'node_type': _node_type(node),
+            'node_type': node.role,
             # ---- B200 extensions -------------------------------------------------------------
             'gpu': node.gpu,
             'stage_index': node.stage_index,

@@ -19,7 +19,7 @@ import torch
 
 from ..endpoints import GrpcService, RingBuffers
 from ..protos import pb
-from ..strings import BufferStatus
+from ..strings import ActionTypes, BufferStatus
 from ..utils.streams import generate_data_stream, generate_stream, join_chunks
 from .mailbox import BACKWARD, FORWARD, Mailbox
 
@@ -72,7 +72,29 @@ class GrpcTransport:
             t.start()
             self._senders[lane] = t
 
+    def _announce_shutdown(self, deadline_s: float = 5.0) -> None:
+        """Best effort: tell the next stage that this node is leaving, so a stopping root takes its whole pipeline down (the
+        stem / leaf provider scripts return from ``Trainer.train()``).  Never blocks on a peer that is already gone."""
+        target = self.targets.get(FORWARD)
+        if target is None or not self.ping(target, timeout=0.5):
+            return
+        stub, probe = self._stub(target), pb.CheckBufferStatus(name=self.name, type=FORWARD)
+        message = {'action': ActionTypes.SHUTDOWN, 'forward_pass_id': -1, 'data': {}}
+        end = time.time() + deadline_s
+        try:
+            while time.time() < end:
+                if stub.buffer_status(probe, timeout=1.0).status == BufferStatus.SEND_BUFFER:
+                    stub.send_buffer(generate_stream(message, type=FORWARD), timeout=5.0)
+                    return
+                time.sleep(0.01)
+        except grpc.RpcError:
+            pass
+
     def stop(self) -> None:
+        if self._stop.is_set():
+            return
+        self.flush(timeout=5.0)                # payloads already queued go out first
+        self._announce_shutdown()
         self._stop.set()
         for q in self._queues.values():
             q.put(None)
