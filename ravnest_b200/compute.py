@@ -80,6 +80,7 @@ class Compute:
         self.n_updates = 0
         self._loss_acc: Optional[torch.Tensor] = None
         self._pending_losses: List[Any] = []
+        self._loss_lock = threading.Lock()
         self.last_loss: Optional[torch.Tensor] = None
         self.dp_group = dp_group
         self.lock = threading.RLock()
@@ -349,20 +350,23 @@ class Compute:
             self.flush_losses(block=False)
 
     def flush_losses(self, block: bool = True) -> None:
-        if self.loss_filename is None or not self._pending_losses:
+        """Write the loss lines whose device-to-host copies have landed.  Callable from any thread (scheduler, a stop() triggered
+        by a SHUTDOWN message, the user's main thread): the queue is drained under its own lock."""
+        if self.loss_filename is None:
             return
-        ready = []
-        while self._pending_losses:
-            host, ev = self._pending_losses[0]
-            if ev is not None and not ev.query():
-                if not block:
-                    break
-                ev.synchronize()
-            ready.append(round(float(host), 4))
-            self._pending_losses.pop(0)
-        if ready:
-            with open(self.loss_filename, 'a') as fh:
-                fh.write(''.join('{}\n'.format(v) for v in ready))
+        with self._loss_lock:
+            ready = []
+            while self._pending_losses:
+                host, ev = self._pending_losses[0]
+                if ev is not None and not ev.query():
+                    if not block:
+                        break
+                    ev.synchronize()
+                ready.append(round(float(host), 4))
+                self._pending_losses.pop(0)
+            if ready:
+                with open(self.loss_filename, 'a') as fh:
+                    fh.write(''.join('{}\n'.format(v) for v in ready))
 
     # ------------------------------------------------------------------ inference
     def no_grad_forward(self, args: Sequence[Any]):

@@ -65,6 +65,7 @@ class Node:
         self.val_accuracy_file = os.path.join(self.base_dir, 'val_accuracies.txt')
         self.labels_to_device = kwargs.get('labels_to_device', False)
         self.prefetch_h2d = bool(kwargs.get('prefetch_h2d', False))
+        self._stop_lock, self._stopping = threading.Lock(), False
         self._h2d_stream = None
         self.status = NodeStatus.IDLE
         if kwargs.get('reset', True):
@@ -195,6 +196,11 @@ class Node:
         return self._stop.wait(timeout)
 
     def stop(self) -> None:
+        """Idempotent and safe to call from several threads (user code, the SHUTDOWN handler)."""
+        with self._stop_lock:
+            if self._stopping:
+                return
+            self._stopping = True
         if self.heartbeat is not None:
             self.heartbeat.stop()
         self.tracer.dump()

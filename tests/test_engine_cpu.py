@@ -415,3 +415,34 @@ def test_solo_node_feeds_keyword_inputs_in_stage_order(workdir, free_ports):
         assert not torch.isfinite(swapped) or abs(float(swapped) - expected) > 1e-3
     finally:
         node.stop()
+
+
+@pytest.mark.parametrize('on_epoch', [True, False])
+def test_lr_schedulers_step_on_epoch_change_or_per_update(workdir, free_ports, on_epoch):
+    """Epoch-change propagation: the leaf notices its label loader wrapped, steps its scheduler and flags the
+    backward message; the root steps on receipt.  With ``lr_step_on_epoch_change=False`` schedulers step per optimizer update."""
+    rv.set_seed(9)
+    ports = free_ports(2)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 1},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+    x, y = torch.randn(24, 1, 8, 8), torch.nn.functional.one_hot(torch.randint(0, 10, (24,)), 10).float()
+    loader = DataLoader(list(zip(x, y)), batch_size=8, shuffle=False)           # 3 batches per epoch
+    nodes = [rv.Node(name='node_{}'.format(i), optimizer=torch.optim.SGD, optimizer_params={'lr': 1.0}, criterion=_loss_fn,
+                     lr_scheduler=torch.optim.lr_scheduler.StepLR, lr_scheduler_params={'step_size': 1, 'gamma': 0.5},
+                     lr_step_on_epoch_change=on_epoch, labels=loader, device=torch.device('cpu'), transport='grpc', reset=(i == 0))
+             for i in range(2)]
+    try:
+        trainer = rv.Trainer(node=nodes[0], train_loader=loader, epochs=2)
+        trainer.train()
+        nodes[0].wait_for_backwards()
+        time.sleep(0.3)
+        lrs = [n.compute_session.optimizer.param_groups[0]['lr'] for n in nodes]
+        # 2 epochs x 3 batches.  As in the reference (node.py:579-586) the leaf notices an epoch change lazily, when next() on its
+        # label iterator raises at the FIRST batch of the following epoch: one change so far; six optimizer updates otherwise.
+        expect = 0.5 ** 1 if on_epoch else 0.5 ** 6
+        assert lrs[1] == pytest.approx(expect)
+        assert lrs[0] == pytest.approx(expect)
+    finally:
+        for n in nodes:
+            n.stop()
