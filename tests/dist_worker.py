@@ -33,6 +33,7 @@ def main():
     ap.add_argument('--dp-mode', default='average')
     ap.add_argument('--recompute', type=int, default=1)
     ap.add_argument('--out', default='result.json')
+    ap.add_argument('--val', type=int, default=0)
     args = ap.parse_args()
     rank, world, dev = init_distributed()
     rv.set_seed(42)
@@ -45,7 +46,8 @@ def main():
     node = rv.Node(name='node_{}'.format(rank), optimizer=torch.optim.Adam, optimizer_params={'lr': 2e-3},
                    criterion=loss_fn, labels=loader, test_labels=loader, device=dev, reduce_factor=2,
                    dp_mode=args.dp_mode, recompute=bool(args.recompute), loss_filename='losses_{}.txt'.format(rank))
-    trainer = rv.Trainer(node=node, train_loader=loader, epochs=args.epochs, inputs_dtype=torch.float32)
+    trainer = rv.Trainer(node=node, train_loader=loader, val_loader=loader if args.val else None, val_freq=1, epochs=args.epochs,
+                         inputs_dtype=torch.float32)
     trainer.train()
     if trainer.is_driver:
         node.wait_for_backwards()

@@ -43,8 +43,12 @@ def test_two_by_two_grid_over_gloo(workdir, free_ports, dp_mode, recompute):
 @pytest.mark.slow
 def test_four_stage_pipeline_over_gloo(workdir, free_ports):
     """root -> stem -> stem -> leaf on the torch.distributed transport, stages balanced by the planner's step-time estimate."""
-    res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '2', '--recompute', '0'], stages=4, replicas=1, proportions=None)
+    res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '2', '--recompute', '0', '--val', '1'], stages=4, replicas=1,
+                  proportions=None)
     assert [r['node_type'] for r in res] == ['root', 'stem', 'stem', 'leaf']
+    # validation batches travel root -> stems -> leaf as NO_GRAD_FORWARD messages; the leaf scores them once per epoch
+    accs = [float(l) for l in open(os.path.join(str(workdir), 'val_accuracies.txt'))]
+    assert len(accs) == 2 and all(0.0 <= a <= 1.0 for a in accs)
     assert all(r['n_backwards'] == 16 for r in res[:3])                  # 2 epochs x 8 batches, one replica
     losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_3.txt'))]
     assert len(losses) == 16 and losses[-1] < losses[0]
