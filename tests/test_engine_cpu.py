@@ -202,6 +202,16 @@ def test_three_node_cnn_trains_over_grpc_and_fuses(workdir, free_ports):
     fused = torch.load(path)
     full = models.CNN_Net()
     assert not full.load_state_dict(fused).missing_keys
+    # inference through the pipeline: class predictions (`Trainer.pred` -> 'accuracy') and raw outputs ('prediction') arrive at
+    # the leaf and equal what the fused model computes
+    full.eval()
+    probe = x[:16]
+    with torch.no_grad():
+        expect = full(probe)
+    trainer.pred(probe)
+    assert torch.equal(leaf.pop_prediction(timeout=20), expect.argmax(dim=-1))
+    root.no_grad_forward_compute(tensors=probe, output_type='prediction')
+    assert torch.allclose(leaf.pop_prediction(timeout=20), expect, atol=1e-5)
     # heartbeat + latest-weights service answer on the control plane
     assert root.transport.ping(('127.0.0.1', ports[1]))
     got = root.transport.fetch_latest_weights(('127.0.0.1', ports[1]), 'dense_1.weight', 'dense_1.bias')
