@@ -65,6 +65,7 @@ class Node:
         self.val_accuracy_file = os.path.join(self.base_dir, 'val_accuracies.txt')
         self.labels_to_device = kwargs.get('labels_to_device', False)
         self.prefetch_h2d = bool(kwargs.get('prefetch_h2d', False))
+        self.checkpoint_every = int(kwargs.get('checkpoint_every', 0) or 0)      # backward passes between automatic checkpoints
         self._stop_lock, self._stopping = threading.Lock(), False
         self._h2d_stream = None
         self.status = NodeStatus.IDLE
@@ -163,7 +164,8 @@ class Node:
         self._prediction_cv = threading.Condition()
         self._saved = threading.Event()
         self._stop = threading.Event()
-        self.metrics = {'forward': 0, 'backward': 0, 'updates': 0, 'reduces': 0}
+        self.metrics = {'forward': 0, 'backward': 0, 'updates': 0, 'reduces': 0, 'checkpoints': 0}
+        self._resume_tag = kwargs.get('resume')           # e.g. 'auto': continue from this node's newest automatic checkpoint
         from .utils.tracing import StageTracer
         from .runtime.watchdog import FaultInjector
         self.tracer = StageTracer(name, self.device, enabled=kwargs.get('trace', True),
@@ -173,6 +175,8 @@ class Node:
         self.compute_stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
         if self.compute_stream is not None:
             self.compute_stream.wait_stream(torch.cuda.current_stream(self.device))   # init work is done
+        if self._resume_tag:
+            self.resumed = self.restore(self._resume_tag)      # False when this node has no such checkpoint (fresh start)
         self.start()
 
     # ------------------------------------------------------------------ lifecycle
@@ -396,6 +400,11 @@ class Node:
                 cs.lr_scheduler.step()
         self.n_backwards += 1
         self.metrics['backward'] += 1
+        if self.checkpoint_every and self.n_backwards % self.checkpoint_every == 0:
+            # periodic sharded checkpoint (new): every node writes its own shard after the same backward pass,
+            # so the set of 'auto' files of a cluster describes one consistent point of the asynchronous schedule per stage
+            self.checkpoint('auto')
+            self.metrics['checkpoints'] += 1
         if self.ring_size > 1 and self.dp_mode == 'average' and self.n_backwards % self.reduce_threshold == 0:
             self.status = NodeStatus.REDUCING
             self.comm_session.parallel_ring_reduce()

@@ -456,3 +456,47 @@ def test_lr_schedulers_step_on_epoch_change_or_per_update(workdir, free_ports, o
     finally:
         for n in nodes:
             n.stop()
+
+
+def test_periodic_checkpoints_and_resume(workdir, free_ports):
+    """``checkpoint_every=k``: every node writes its shard after every k-th backward pass; a node constructed with
+    ``resume='auto'`` continues from it (weights, optimizer state, counters), one without starts from the planned artefact."""
+    rv.set_seed(4)
+    ports = free_ports(2)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 1},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+    x, y = torch.randn(32, 1, 8, 8), torch.nn.functional.one_hot(torch.randint(0, 10, (32,)), 10).float()
+    loader = DataLoader(list(zip(x, y)), batch_size=8, shuffle=False)           # 4 batches per epoch
+
+    def make(i, **kw):
+        return rv.Node(name='node_{}'.format(i), optimizer=torch.optim.Adam, optimizer_params={'lr': 1e-2}, criterion=_loss_fn,
+                       labels=loader, device=torch.device('cpu'), transport='grpc', reset=False, checkpoint_every=3, **kw)
+
+    nodes = [make(0), make(1)]
+    try:
+        rv.Trainer(node=nodes[0], train_loader=loader, epochs=2).train()         # 8 backward passes -> checkpoints after 3 and 6
+        nodes[0].wait_for_backwards()
+        time.sleep(0.3)
+        assert [n.metrics['checkpoints'] for n in nodes] == [2, 2]
+        trained = [n.compute_session.store.master.clone() for n in nodes]
+    finally:
+        for n in nodes:
+            n.stop()
+    time.sleep(0.3)
+    fresh = make(1)                                   # restart WITHOUT resume: the planned initial weights
+    try:
+        assert not torch.allclose(fresh.compute_session.store.master, trained[1])
+    finally:
+        fresh.stop()
+    time.sleep(0.3)
+    resumed = make(1, resume='auto')                  # restart WITH resume: the state after backward pass 6
+    try:
+        assert resumed.resumed and resumed.n_backwards == 6
+        assert resumed.compute_session.optimizer.state_dict()['state']            # Adam moments came back
+        # two more Adam steps happened after the checkpoint, so it is close to but not equal to the final weights
+        d_final = float((resumed.compute_session.store.master - trained[1]).abs().max())
+        d_init = float((resumed.compute_session.store.master - fresh.compute_session.store.master).abs().max())
+        assert 0 < d_final < d_init
+    finally:
+        resumed.stop()
