@@ -500,3 +500,37 @@ def test_periodic_checkpoints_and_resume(workdir, free_ports):
         assert 0 < d_final < d_init
     finally:
         resumed.stop()
+
+
+def test_heterogeneous_clusters_average_ring_wise_over_grpc(workdir, free_ports):
+    """Clusters that cut the model differently (SURVEY §2.2 "heterogeneous rings"): the GA puts three small hosts into one
+    3-stage cluster and each big host into a cluster of its own; rings are defined by the largest cluster, a solo node takes part
+    in all three rings and maps parameter ranges to the right peers.  After ``parallel_ring_reduce`` every parameter equals the
+    mean over the three clusters."""
+    rv.set_seed(0)
+    ports = free_ports(5)
+    rams = [1, 1, 1, 3, 3]
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': r, 'bandwidth': 10}} for i, (p, r) in enumerate(zip(ports, rams))}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), node_configs=cfgs)
+    nodes = [rv.Node(name='node_{}'.format(i), optimizer=torch.optim.SGD, optimizer_params={'lr': 0.1}, criterion=_loss_fn,
+                     labels=[(None, torch.zeros(1, 10))], device=torch.device('cpu'), transport='grpc', reset=False) for i in range(5)]
+    try:
+        assert sorted(n.node_type for n in nodes) == ['leaf', 'root', 'solo', 'solo', 'stem']
+        assert all(n.ring_size == 3 for n in nodes)
+        value_of_cluster = {}
+        with torch.no_grad():
+            for n in nodes:
+                value_of_cluster.setdefault(n.rank, float(len(value_of_cluster) + 1) * 3.0)      # 3, 6, 9 -> mean 6
+                n.compute_session.store.master.fill_(value_of_cluster[n.rank])
+        threads = [threading.Thread(target=n.comm_session.parallel_ring_reduce) for n in nodes]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(90)
+        assert not any(t.is_alive() for t in threads), 'ring reduce did not finish'
+        for n in nodes:
+            real = torch.cat([v.reshape(-1) for v in n.compute_session.store.master_views])
+            assert torch.allclose(real, torch.full_like(real, 6.0)), (n.name, n.node_type, real.unique())
+    finally:
+        for n in nodes:
+            n.stop()
