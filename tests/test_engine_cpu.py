@@ -534,3 +534,41 @@ def test_heterogeneous_clusters_average_ring_wise_over_grpc(workdir, free_ports)
     finally:
         for n in nodes:
             n.stop()
+
+
+def test_ring_average_includes_optimizer_state_over_grpc(workdir, free_ports):
+    """``average_optim=True`` (reference communication.py:131-138): moment tensors shaped like their parameter ride the same
+    ring chunks as the parameter and come out averaged too."""
+    rv.set_seed(1)
+    ports = free_ports(4)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+    nodes = [rv.Node(name='node_{}'.format(i), optimizer=torch.optim.Adam, optimizer_params={'lr': 0.1}, criterion=_loss_fn,
+                     labels=[(None, torch.zeros(1, 10))], device=torch.device('cpu'), transport='grpc', reset=False,
+                     average_optim=True, fused_optimizer=False) for i in range(4)]
+    try:
+        with torch.no_grad():
+            for i, n in enumerate(nodes):
+                cs = n.compute_session
+                cs.store.master.fill_(float(i + 1))
+                for p in cs.store.master_params:                     # give Adam a state to average
+                    cs.optimizer.state[p] = {'step': torch.tensor(5.0), 'exp_avg': torch.full_like(p, 10.0 * (i + 1)),
+                                             'exp_avg_sq': torch.full_like(p, 100.0 * (i + 1))}
+        threads = [threading.Thread(target=n.comm_session.parallel_ring_reduce) for n in nodes]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(90)
+        expect = {0: 2.0, 2: 2.0, 1: 3.0, 3: 3.0}                    # mean of the two replicas of each stage
+        for i, n in enumerate(nodes):
+            cs = n.compute_session
+            for p in cs.store.master_params:
+                st = cs.optimizer.state[p]
+                assert torch.allclose(p, torch.full_like(p, expect[i]))
+                assert torch.allclose(st['exp_avg'], torch.full_like(p, 10.0 * expect[i]))
+                assert torch.allclose(st['exp_avg_sq'], torch.full_like(p, 100.0 * expect[i]))
+                assert float(st['step']) == 5.0
+    finally:
+        for n in nodes:
+            n.stop()
