@@ -572,3 +572,43 @@ def test_ring_average_includes_optimizer_state_over_grpc(workdir, free_ports):
     finally:
         for n in nodes:
             n.stop()
+
+
+def test_two_clusters_train_concurrently_with_periodic_averaging_and_fp16_wire(workdir, free_ports):
+    """The reference's data parallelism end to end over gRPC: two 2-stage clusters train on different shards, average their
+    parameters every ``update_frequency x reduce_factor`` backward passes and once more at the end; activations and gradients
+    travel as fp16 (``compression=True``).  Replicas of a stage must end identical, and the loss must go down."""
+    rv.set_seed(3)
+    ports = free_ports(4)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 2},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+    x, y = _digits()
+    shards = [(x[:128], y[:128]), (x[128:256], y[128:256])]
+    loaders = [DataLoader(list(zip(*s)), batch_size=32, shuffle=False) for s in shards]            # 4 batches per epoch and replica
+    nodes = []
+    for i in range(4):
+        replica = i // 2
+        nodes.append(rv.Node(name='node_{}'.format(i), optimizer=torch.optim.Adam, optimizer_params={'lr': 3e-3}, criterion=_loss_fn,
+                             labels=loaders[replica], device=torch.device('cpu'), transport='grpc', reset=(i == 0), compression=True,
+                             update_frequency=1, reduce_factor=2, loss_filename='losses_{}.txt'.format(i)))
+    try:
+        assert [n.node_type for n in nodes] == ['root', 'leaf', 'root', 'leaf'] and all(n.ring_size == 2 for n in nodes)
+        trainers = [rv.Trainer(node=nodes[r * 2], train_loader=loaders[r], epochs=6, inputs_dtype=torch.float32) for r in range(2)]
+        threads = [threading.Thread(target=t.train) for t in trainers]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(240)
+        assert not any(t.is_alive() for t in threads), 'training did not finish'
+        time.sleep(0.5)
+        for a, b in ((0, 2), (1, 3)):
+            assert torch.allclose(nodes[a].compute_session.store.master, nodes[b].compute_session.store.master, atol=1e-6)
+        assert nodes[0].metrics['reduces'] >= 24 // 2                     # 24 backward passes, averaging every 2nd
+        for leaf in (nodes[1], nodes[3]):
+            leaf.compute_session.flush_losses()
+        losses = [float(l) for l in open('losses_1.txt')]
+        assert len(losses) == 24 and sum(losses[-4:]) < sum(losses[:4])
+    finally:
+        for n in nodes:
+            n.stop()
