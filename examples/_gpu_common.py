@@ -18,11 +18,7 @@ def launch(make_node, make_trainer):
     node = make_node('node_{}'.format(rank), dev)
     trainer = make_trainer(node)
     trainer.train()
-    if trainer.is_driver:
-        node.wait_for_backwards()
-        time.sleep(0.2)
-        node.stop()
-    node._stop.wait(60)
+    trainer.finish(grace=0.2, timeout=60)           # root: drain and stop the pipeline; others: wait for the SHUTDOWN
     node.compute_session.flush_losses()
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()

@@ -12,7 +12,6 @@ import argparse
 import os
 import subprocess
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch  # noqa: E402
@@ -57,12 +56,7 @@ def run_node(name: str, epochs: int) -> None:
                               batch_size=BATCH, inputs_dtype=torch.float32, save=True)
     trainer.train()
     trainer.evaluate()
-    if trainer.is_driver:
-        node.wait_for_backwards()
-        time.sleep(1.0)                       # let the last validation batches reach the leaf
-        node.stop()                           # sends SHUTDOWN down the pipeline: stem and leaf providers exit too
-    else:
-        node.wait_until_stopped()
+    trainer.finish()                          # root: stop the pipeline (SHUTDOWN travels downstream); stem / leaf: wait for it
 
 
 def main() -> int:

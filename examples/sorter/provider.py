@@ -23,4 +23,6 @@ if __name__ == '__main__':
     data = SortDataset('train', n=int(os.environ.get('SAMPLES', 6400)))
     loader = DataLoader(data, shuffle=False, batch_size=64)
     node = Node(name=name, optimizer=torch.optim.Adam, criterion=sorter_criterion, labels=loader, device=torch.device('cpu'))
-    Trainer(node=node, train_loader=loader, save=True, epochs=1, batch_size=64).train()
+    trainer = Trainer(node=node, train_loader=loader, save=True, epochs=1, batch_size=64)
+    trainer.train()
+    trainer.finish()                # root: stop the pipeline; stem / leaf: return once the root has done so

@@ -66,7 +66,7 @@ class Node:
         self.labels_to_device = kwargs.get('labels_to_device', False)
         self.prefetch_h2d = bool(kwargs.get('prefetch_h2d', False))
         self.checkpoint_every = int(kwargs.get('checkpoint_every', 0) or 0)      # backward passes between automatic checkpoints
-        self._stop_lock, self._stopping = threading.Lock(), False
+        self._stop_lock, self._stopping, self._stopped = threading.Lock(), False, threading.Event()
         self._h2d_stream = None
         self.status = NodeStatus.IDLE
         if kwargs.get('reset', True):
@@ -197,7 +197,9 @@ class Node:
     def wait_until_stopped(self, timeout: Optional[float] = None) -> bool:
         """Block until this node has been stopped — by ``stop()`` here or by the SHUTDOWN message a stopping root sends down
         its pipeline.  Provider scripts of stem / leaf nodes end with this call."""
-        return self._stop.wait(timeout)
+        if not self._stop.wait(timeout):
+            return False
+        return self._stopped.wait(30.0 if timeout is None else timeout)      # the stopping thread finished its hand-offs
 
     def stop(self) -> None:
         """Idempotent and safe to call from several threads (user code, the SHUTDOWN handler)."""
@@ -213,7 +215,10 @@ class Node:
         try:
             self.compute_session.flush_losses()
         finally:
-            self.transport.stop()
+            try:
+                self.transport.stop()          # also tells the next stage that this node is leaving
+            finally:
+                self._stopped.set()
 
     def _scheduler_loop(self) -> None:
         """Reference ``check_load_forward_buffer`` (node.py:330-367): backward lane first, then

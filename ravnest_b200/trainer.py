@@ -42,7 +42,7 @@ class Trainer:
         """Stem / leaf providers park here while the scheduler thread serves the pipeline."""
         if self.is_driver:
             return True
-        self.node._stop.wait()
+        self.node.wait_until_stopped()
         return False
 
     def _as_input(self, x):
@@ -72,6 +72,17 @@ class Trainer:
         self.train_seconds = time.time() - t0
         if self.save:
             self.node.trigger_save_submodel()
+
+    def finish(self, grace: float = 1.0, timeout=None) -> None:
+        """End a provider script (new).  On the driving node (root / solo): wait for outstanding work, then stop the node — a
+        stopping root sends SHUTDOWN down its pipeline; on stem / leaf nodes: block until that SHUTDOWN arrives.  Without this
+        call providers keep serving forever, which is the reference's behaviour."""
+        if self.is_driver:
+            self.node.wait_for_backwards()
+            time.sleep(grace)                  # let trailing inference / save messages reach the leaf
+            self.node.stop()
+        else:
+            self.node.wait_until_stopped(timeout)
 
     def evaluate(self):
         if not self.is_driver or self.val_loader is None:
