@@ -98,3 +98,41 @@ def compare_models(a, b, atol: float = 0.0, rtol: float = 0.0):
         elif not torch.allclose(x.double(), y.double(), atol=atol, rtol=rtol):
             diffs.append((key, float((x.double() - y.double()).abs().max())))
     return diffs
+
+
+class ClusterPipeline(torch.nn.Module):
+    """The saved stages of one cluster chained in-process (no nodes, no transport): what the reference's
+    ``examples/sorter/sorter_inference.py`` does with its TorchScript sub-models.  Stages are loaded from
+    ``node_data/cluster_<c>/<host:port>/submod_<k>.pt`` (``submod.pt`` before training was saved) and wired with each stage's
+    ``plan.json``; call it with the model's inputs in signature order."""
+
+    def __init__(self, cluster_id: int = 0, base_dir=None, trained: bool = True):
+        super().__init__()
+        from .serialization import load_json, load_submodel
+        root = os.path.join(base_dir or os.environ.get('RAVNEST_HOME', '.'), 'node_data', 'cluster_{}'.format(cluster_id))
+        plans = []
+        for folder in sorted(os.listdir(root)):
+            plan_path = os.path.join(root, folder, 'plan.json')
+            if os.path.exists(plan_path):
+                plans.append((load_json(plan_path), os.path.join(root, folder)))
+        if not plans:
+            raise FileNotFoundError('no stage plans under {}'.format(root))
+        plans.sort(key=lambda item: item[0]['index'])
+        self.plans = [p for p, _ in plans]
+        modules = []
+        for plan, folder in plans:
+            saved = os.path.join(folder, '{}.pt'.format(plan['name']))
+            modules.append(load_submodel(saved if trained and os.path.exists(saved) else os.path.join(folder, 'submod.pt')))
+        self.stages = torch.nn.ModuleList(modules)
+
+    def forward(self, *model_inputs):
+        produced = {('model_inputs', i): v for i, v in enumerate(model_inputs)}
+        out = None
+        for plan, stage in zip(self.plans, self.stages):
+            out = stage(*[produced[(src['producer'], src['out_idx'])] for src in plan['inputs']])
+            if plan['is_last']:
+                return out
+            values = (out,) if len(plan['outputs']) == 1 else tuple(out)
+            for i, v in enumerate(values):
+                produced[(plan['name'], i)] = v
+        return out

@@ -52,6 +52,10 @@ def test_sorter_two_node_pipeline_trains_and_decodes(workdir, free_ports):
     assert set(missing.missing_keys) <= {'transformer.wte.weight', 'transformer.wpe.weight'}
     assert torch.equal(full.transformer.wte.weight, fused['transformer.emb.wte.weight'])
     full.eval()
+    # the saved stage modules chained in-process (examples/sorter/sorter_inference.py) compute what the fused model computes
+    chained = rv.ClusterPipeline(cluster_id=0).eval()
+    with torch.no_grad():
+        assert torch.allclose(chained(x[:8]), full(x[:8]), atol=1e-5)
     probe = torch.tensor([[2, 0, 1, 1, 0, 2]])
     out = full.generate(probe, 6)
     assert out.shape == (1, 12)
