@@ -34,6 +34,8 @@ def main():
     ap.add_argument('--recompute', type=int, default=1)
     ap.add_argument('--out', default='result.json')
     ap.add_argument('--val', type=int, default=0)
+    ap.add_argument('--optimizer', default='adam')
+    ap.add_argument('--dump', type=int, default=0, help='write the final master parameters to master.<rank>.pt')
     args = ap.parse_args()
     rank, world, dev = init_distributed()
     rv.set_seed(42)
@@ -43,7 +45,8 @@ def main():
     shard = slice(replica * 128, replica * 128 + 128) if cfg['ring_size'] > 1 else slice(0, 256)
     data = list(zip(x[shard], y[shard]))
     loader = DataLoader(data, batch_size=32, shuffle=False)
-    node = rv.Node(name='node_{}'.format(rank), optimizer=torch.optim.Adam, optimizer_params={'lr': 2e-3},
+    opt_cls, opt_params = (torch.optim.SGD, {'lr': 0.05}) if args.optimizer == 'sgd' else (torch.optim.Adam, {'lr': 2e-3})
+    node = rv.Node(name='node_{}'.format(rank), optimizer=opt_cls, optimizer_params=opt_params,
                    criterion=loss_fn, labels=loader, test_labels=loader, device=dev, reduce_factor=2,
                    dp_mode=args.dp_mode, recompute=bool(args.recompute), loss_filename='losses_{}.txt'.format(rank))
     trainer = rv.Trainer(node=node, train_loader=loader, val_loader=loader if args.val else None, val_freq=1, epochs=args.epochs,
@@ -56,6 +59,9 @@ def main():
     node._stop.wait(30)
     time.sleep(0.3)
     node.compute_session.flush_losses()
+    if args.dump:
+        torch.save({n: v.clone() for n, v in zip(node.compute_session.store.names, node.compute_session.store.master_views)},
+                   'master.{}.pt'.format(rank))
     summary = {'rank': rank, 'node_type': node.node_type, 'n_backwards': node.n_backwards,
                'version': node.compute_session.current_version(),
                'checksum': float(node.compute_session.store.master.double().sum())}

@@ -112,3 +112,39 @@ def test_sorter_eight_stage_pipeline_over_gloo(workdir, free_ports):
     assert all(r['finite'] and r['n_backwards'] == 24 for r in res)
     losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_7.txt'))]
     assert len(losses) == 24 and losses[-1] < losses[0]
+
+
+@pytest.mark.slow
+def test_gradient_mode_data_parallel_equals_large_batch_sgd(workdir, free_ports):
+    """Two solo replicas in ``dp_mode='gradient'`` (all-reduce of the gradient bucket inside every optimizer step), each on half
+    of every global batch, must follow exactly the trajectory of one process doing SGD on the full batches."""
+    import sys as _sys
+    _sys.path.insert(0, HERE)
+    from dist_worker import digits_like, loss_fn
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(64, 32), torch.nn.Tanh(), torch.nn.Linear(32, 10), torch.nn.Softmax(dim=-1))
+    rv.set_seed(42)
+    rv.clusterize(model, example_args=(torch.rand(32, 1, 8, 8),), topology={'stages': 1, 'replicas': 2},
+                  node_configs=rv.default_gpu_configs(2), base_dir=str(workdir))
+    env = dict(os.environ, RAVNEST_HOME=str(workdir), OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(29000 + free_ports(1)[0] % 900), os.path.join(HERE, 'dist_worker.py'), '--epochs', '2', '--dp-mode', 'gradient',
+           '--recompute', '0', '--optimizer', 'sgd', '--dump', '1']
+    proc = subprocess.run(cmd, cwd=str(workdir), env=env, capture_output=True, text=True, timeout=420)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    got = [torch.load(os.path.join(str(workdir), 'master.{}.pt'.format(r))) for r in range(2)]
+    # reference: same initial weights, global batch k = [replica 0 batch k ; replica 1 batch k], mean loss
+    import copy
+    ref = copy.deepcopy(model)
+    opt = torch.optim.SGD(ref.parameters(), lr=0.05)
+    x, y = digits_like()
+    for _epoch in range(2):
+        for k in range(4):
+            xb = torch.cat([x[k * 32:(k + 1) * 32], x[128 + k * 32:128 + (k + 1) * 32]])
+            yb = torch.cat([y[k * 32:(k + 1) * 32], y[128 + k * 32:128 + (k + 1) * 32]])
+            opt.zero_grad()
+            loss_fn(ref(xb), (None, yb)).backward()
+            opt.step()
+    for name, p in ref.named_parameters():
+        assert torch.allclose(got[0][name], got[1][name], atol=1e-7), name             # replicas identical
+        assert torch.allclose(got[0][name], p.detach(), atol=1e-5), name               # ... and equal to large-batch SGD
