@@ -612,3 +612,41 @@ def test_two_clusters_train_concurrently_with_periodic_averaging_and_fp16_wire(w
     finally:
         for n in nodes:
             n.stop()
+
+
+def test_bounded_staleness_holds_when_the_leaf_is_slow(workdir, free_ports):
+    """The root may run ahead of its last answered pass by at most ``cluster_length`` forwards (reference node.py:384); with a
+    leaf that stalls (fault injection: delay) the root must block in ``forward_compute`` instead of flooding the pipeline."""
+    rv.set_seed(6)
+    ports = free_ports(2)
+    cfgs = {str(i): {'IP': '127.0.0.1:{}'.format(p), 'benchmarks': {'ram': 1, 'bandwidth': 10}} for i, p in enumerate(ports)}
+    rv.clusterize(models.CNN_Net(), example_args=(torch.rand(8, 1, 8, 8),), topology={'stages': 2, 'replicas': 1},
+                  node_configs=cfgs, proportions=[0.5, 0.5])
+    x, y = torch.randn(64, 1, 8, 8), torch.nn.functional.one_hot(torch.randint(0, 10, (64,)), 10).float()
+    loader = DataLoader(list(zip(x, y)), batch_size=8, shuffle=False)            # 8 passes
+    root = rv.Node(name='node_0', optimizer=torch.optim.SGD, optimizer_params={'lr': 0.01}, criterion=_loss_fn, labels=loader,
+                   device=torch.device('cpu'), transport='grpc', reset=True)
+    leaf = rv.Node(name='node_1', optimizer=torch.optim.SGD, optimizer_params={'lr': 0.01}, criterion=_loss_fn, labels=loader,
+                   device=torch.device('cpu'), transport='grpc', reset=False,
+                   fault_spec='delay_forward:1:0.6,delay_forward:4:0.6')      # rules match the wire action (the leaf handles 'forward' as find_loss)
+    worst, stop = [0], threading.Event()
+
+    def watch():
+        while not stop.is_set():
+            worst[0] = max(worst[0], root.forward_pass_id - root.latest_backward_id)
+            time.sleep(0.002)
+
+    watcher = threading.Thread(target=watch, daemon=True)
+    watcher.start()
+    try:
+        rv.Trainer(node=root, train_loader=loader, epochs=1, inputs_dtype=torch.float32).train()
+        root.wait_for_backwards()
+        stop.set()
+        assert root.latest_backward_id == root.forward_pass_id == 8
+        assert leaf.faults.fired == [('delay_forward', 1), ('delay_forward', 4)]
+        # forward_pass_id is bumped right after the staleness check passed: at most cluster_length + 1 unanswered submissions
+        assert 2 <= worst[0] <= root.cluster_length + 1
+    finally:
+        stop.set()
+        for n in (root, leaf):
+            n.stop()
