@@ -514,7 +514,7 @@ class Node:
         self.compute_session.store.bind_module()
         self.compute_session.flush_losses()
         path = os.path.join(self.template_path, '{}.pt'.format(self.submod_file))
-        save_submodel(self.model.to('cpu') if False else self.model, path)
+        save_submodel(self.model, path)            # serialisation moves tensors to the CPU; the live module stays on its device
         shutil.copyfile(path, os.path.join(self.template_path, 'submod.pt'))
         self._saved.set()
         return path
