@@ -514,7 +514,7 @@ class Node:
         self.compute_session.store.bind_module()
         self.compute_session.flush_losses()
         path = os.path.join(self.template_path, '{}.pt'.format(self.submod_file))
-        save_submodel(self.model, path)            # serialisation moves tensors to the CPU; the live module stays on its device
+        save_submodel(self.model, path)            # tensors keep their device tag in the file; load_submodel maps them to the CPU
         shutil.copyfile(path, os.path.join(self.template_path, 'submod.pt'))
         self._saved.set()
         return path
