@@ -511,10 +511,21 @@ class Node:
     def _save_local(self) -> str:
         """Write ``<template_path>/<submod_k>.pt`` (reference node.py:692-724) and keep ``submod.pt``
         current so the node can restart."""
-        self.compute_session.store.bind_module()
-        self.compute_session.flush_losses()
+        cs = self.compute_session
+        cs.flush_losses()
         path = os.path.join(self.template_path, '{}.pt'.format(self.submod_file))
-        save_submodel(self.model, path)            # tensors keep their device tag in the file; load_submodel maps them to the CPU
+        with cs.lock:
+            # save the MASTER weights (fp32 even when the stage computes in bf16): point the module's parameters at copies of
+            # them for the duration of the pickle, then back at the live compute-dtype version (stage steps use their own
+            # parameter dicts, never the module's attributes, so nothing running is disturbed)
+            lookup = dict(self.model.named_parameters())
+            with torch.no_grad():
+                for name, master in cs.store.master_state().items():
+                    lookup[name].data = master.detach().clone()
+            try:
+                save_submodel(self.model, path)        # tensors keep their device tag; load_submodel maps them to the CPU
+            finally:
+                cs.store.bind_module()
         shutil.copyfile(path, os.path.join(self.template_path, 'submod.pt'))
         self._saved.set()
         return path

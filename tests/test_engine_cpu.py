@@ -689,3 +689,29 @@ def test_model_input_is_relayed_through_a_stem_over_grpc(workdir, free_ports):
     finally:
         for n in nodes:
             n.stop()
+
+
+def test_saved_submodel_holds_the_fp32_master_weights_of_a_bf16_stage(workdir, free_ports):
+    """A stage that computes in bf16 keeps fp32 master weights; ``save=True`` / ``trigger_save_submodel`` must write those, not
+    the rounded bf16 copy the kernels read."""
+    rv.set_seed(12)
+    port = free_ports(1)[0]
+    rv.clusterize(TinyMLP(), example_args=(torch.randn(4, 12),), topology={'stages': 1, 'replicas': 1},
+                  node_configs={'0': {'IP': '127.0.0.1:{}'.format(port), 'benchmarks': {'ram': 1, 'bandwidth': 10}}})
+    x, y = torch.randn(16, 12), torch.randn(16, 4)
+    loader = DataLoader(list(zip(x, y)), batch_size=4, shuffle=False)
+    node = rv.Node(name='node_0', optimizer=torch.optim.SGD, optimizer_params={'lr': 0.05}, device=torch.device('cpu'), transport='grpc',
+                   criterion=lambda out, tgt: torch.nn.functional.mse_loss(out.float(), tgt[1]), labels=loader, dtype=torch.bfloat16)
+    try:
+        rv.Trainer(node=node, train_loader=loader, epochs=2, save=True, inputs_dtype=torch.float32).train()
+        store = node.compute_session.store
+        assert store.compute_dtype == torch.bfloat16 and store.master.dtype == torch.float32
+        saved = torch.load(os.path.join(node.template_path, 'submod_0.pt'), weights_only=False)
+        for name, master in store.master_state().items():
+            p = dict(saved.named_parameters())[name]
+            assert p.dtype == torch.float32 and torch.equal(p, master)
+            assert not torch.equal(p, master.to(torch.bfloat16).float())          # i.e. more than bf16 precision survived
+        # the live module went back to the compute-dtype version
+        assert all(p.dtype == torch.bfloat16 for p in node.model.parameters())
+    finally:
+        node.stop()
