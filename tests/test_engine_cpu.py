@@ -715,3 +715,33 @@ def test_saved_submodel_holds_the_fp32_master_weights_of_a_bf16_stage(workdir, f
         assert all(p.dtype == torch.bfloat16 for p in node.model.parameters())
     finally:
         node.stop()
+
+
+def test_param_store_keeps_spatial_conv_weights_in_ohwi_order():
+    """Convolution weights with a spatial extent are laid out O-H-W-I inside every flat buffer (what the implicit-GEMM kernels
+    read K-major), while every view keeps the [O, I, H, W] shape and values; 1x1 / linear / vector parameters stay contiguous."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(4, 6, 3, bias=True), torch.nn.Conv2d(6, 8, 1, bias=False), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(8, 5))
+    ref = {n: p.detach().clone() for n, p in net.named_parameters()}
+    store = ParamStore(net, 'cpu', n_slots=2)
+    assert store.channels_last == [True, False, False, False, False]
+    for name, view, leaf, gview in zip(store.names, store.master_views, store.current.leaves, store.grad_views):
+        assert view.shape == ref[name].shape and torch.equal(view, ref[name]) and torch.equal(leaf.detach(), ref[name])
+        assert gview.shape == ref[name].shape and leaf.grad is gview
+    w = store.master_views[0]
+    assert w.permute(0, 2, 3, 1).is_contiguous() and not w.is_contiguous()
+    # the flat segment really is OHWI
+    seg = store.master[store.offsets[0]:store.offsets[0] + store.numels[0]]
+    assert torch.equal(seg.view(6, 3, 3, 4), ref['0.weight'].permute(0, 2, 3, 1))
+    # gradients written through a leaf land in the flat bucket, in the same physical order
+    x = torch.randn(2, 4, 5, 5)
+    from torch.func import functional_call
+    functional_call(net, store.current.param_dict, (x,)).sum().backward()
+    g = store.grad[store.offsets[0]:store.offsets[0] + store.numels[0]].view(6, 3, 3, 4)
+    net.zero_grad()
+    net(x).sum().backward()
+    assert torch.allclose(g, net[0].weight.grad.permute(0, 2, 3, 1), atol=1e-5)
+    # publishing a new version is still one flat cast-copy
+    store.master.add_(1.0)
+    store.publish()
+    assert torch.equal(store.current.leaves[0].detach(), ref['0.weight'] + 1.0)
