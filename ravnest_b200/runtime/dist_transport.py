@@ -77,6 +77,9 @@ def _load_chains(base_dir: str) -> Dict[int, List[int]]:
     return chains
 
 
+_FRAME = max(64, int(os.environ.get('RAVNEST_HEADER_FRAME', '4096')))    # bytes of the fixed header frame (8-byte length + pickled skeleton)
+
+
 class _Groups:
     """Every rank builds the same groups in the same order (``new_group`` is collective)."""
     _cache: Dict[str, '_Groups'] = {}
@@ -262,9 +265,16 @@ class DistTransport:
             try:
                 bag: List[torch.Tensor] = []
                 skeleton = _split_tensors(message, bag)
-                blob = torch.frombuffer(bytearray(pickle.dumps(skeleton, protocol=pickle.HIGHEST_PROTOCOL)), dtype=torch.uint8)
-                dist.send(torch.tensor([blob.numel()], dtype=torch.int64), dst=peer, group=hgroup, tag=_TAG[lane])
-                dist.send(blob, dst=peer, group=hgroup, tag=_TAG[lane])
+                raw = pickle.dumps(skeleton, protocol=pickle.HIGHEST_PROTOCOL)
+                # ONE fixed-size frame carries the length and (almost always) the whole pickled skeleton; only a header that
+                # does not fit is followed by a second message with the rest (was: a length message + a blob message per hop)
+                frame = torch.zeros(_FRAME, dtype=torch.uint8)
+                frame[:8] = torch.frombuffer(bytearray(len(raw).to_bytes(8, 'little')), dtype=torch.uint8)
+                head = min(len(raw), _FRAME - 8)
+                frame[8:8 + head] = torch.frombuffer(bytearray(raw[:head]), dtype=torch.uint8)
+                dist.send(frame, dst=peer, group=hgroup, tag=_TAG[lane])
+                if len(raw) > head:
+                    dist.send(torch.frombuffer(bytearray(raw[head:]), dtype=torch.uint8), dst=peer, group=hgroup, tag=_TAG[lane])
                 if bag:
                     if self.cuda:
                         stream = self.send_stream[lane]
@@ -296,16 +306,21 @@ class DistTransport:
         group = self.groups.pair[(peer, self.rank, lane)]
         hgroup = self.groups.header[(peer, self.rank, lane)]
         while not self._stop.is_set():
-            size = torch.zeros(1, dtype=torch.int64)
+            frame = torch.zeros(_FRAME, dtype=torch.uint8)
             try:
-                dist.recv(size, src=peer, group=hgroup, tag=_TAG[lane])
-                blob = torch.empty(int(size.item()), dtype=torch.uint8)
-                dist.recv(blob, src=peer, group=hgroup, tag=_TAG[lane])
+                dist.recv(frame, src=peer, group=hgroup, tag=_TAG[lane])
+                total = int.from_bytes(frame[:8].numpy().tobytes(), 'little')
+                head = min(total, _FRAME - 8)
+                raw = frame[8:8 + head].numpy().tobytes()
+                if total > head:
+                    rest = torch.empty(total - head, dtype=torch.uint8)
+                    dist.recv(rest, src=peer, group=hgroup, tag=_TAG[lane])
+                    raw += rest.numpy().tobytes()
             except RuntimeError:
                 if self._stop.is_set():
                     return
                 raise
-            skeleton = pickle.loads(blob.numpy().tobytes())
+            skeleton = pickle.loads(raw)
             specs: List[Tuple[Tuple[int, ...], torch.dtype]] = []
             _tensor_specs(skeleton, specs)
             bag: List[torch.Tensor] = []

@@ -43,8 +43,14 @@ def test_two_by_two_grid_over_gloo(workdir, free_ports, dp_mode, recompute):
 @pytest.mark.slow
 def test_four_stage_pipeline_over_gloo(workdir, free_ports):
     """root -> stem -> stem -> leaf on the torch.distributed transport, stages balanced by the planner's step-time estimate."""
-    res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '2', '--recompute', '0', '--val', '1'], stages=4, replicas=1,
-                  proportions=None)
+    # RAVNEST_HEADER_FRAME=64 forces every message header onto the two-part path (frame + remainder); the other tests in this
+    # file use the default 4 KiB frame that holds the whole header
+    os.environ['RAVNEST_HEADER_FRAME'] = '64'
+    try:
+        res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '2', '--recompute', '0', '--val', '1'], stages=4, replicas=1,
+                      proportions=None)
+    finally:
+        del os.environ['RAVNEST_HEADER_FRAME']
     assert [r['node_type'] for r in res] == ['root', 'stem', 'stem', 'leaf']
     # validation batches travel root -> stems -> leaf as NO_GRAD_FORWARD messages; the leaf scores them once per epoch
     accs = [float(l) for l in open(os.path.join(str(workdir), 'val_accuracies.txt'))]
