@@ -411,7 +411,8 @@ def main():
         }
         if args.layers:
             result['invalid'] = 'debug run with --layers'
-        print(json.dumps(result))
+        print(json.dumps(result), flush=True)
+    faulthandler.cancel_dump_traceback_later()          # measurements are out; teardown is not worth a stack dump
     sync()
     if driver:
         node.stop()
