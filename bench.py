@@ -412,7 +412,12 @@ def main():
         if args.layers:
             result['invalid'] = 'debug run with --layers'
         print(json.dumps(result), flush=True)
-    faulthandler.cancel_dump_traceback_later()          # measurements are out; teardown is not worth a stack dump
+    faulthandler.cancel_dump_traceback_later()
+    # the measurements are out: whatever happens during teardown (a peer that is already gone, a slow communicator destroy)
+    # must neither hang the box nor turn a finished run into a failure
+    killer = threading.Timer(90.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
     sync()
     if driver:
         node.stop()
