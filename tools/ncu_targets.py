@@ -1,5 +1,5 @@
 """Launch a few instances of one kernel family at the benchmark shapes (for `ncu -k regex:... python tools/ncu_targets.py <target>`).
-Targets: fmha, conv, bn, ln, ce, optim, pool, gemm_epi."""
+Targets: fmha, conv, bn, ln, ce, optim, pool, gemm_epi, embed."""
 import os
 import sys
 
@@ -58,6 +58,12 @@ for it in range(2):
         for p in (w1, b1, w2, b2):
             p.grad = torch.zeros_like(p)
         ops.mlp(x, w1, b1, w2, b2, 'gelu').backward(r(4096, 768))
+    elif target == 'embed':                                # BERT embeddings: gather, owner-computes backward, dropout
+        w = r(30522, 768, scale=0.02).requires_grad_(True)
+        w.grad = torch.zeros_like(w)
+        idx = torch.randint(0, 30522, (8, 512), device=dev)
+        y = ops.dropout(ops.embedding(idx, w, 0), 0.1, True)
+        y.backward(r(8, 512, 768))
     elif target == 'optim':
         from ravnest_b200.parallel.fused_optim import FusedFlatOptimizer
         from ravnest_b200.runtime.param_store import ParamStore
