@@ -34,6 +34,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--update-frequency', type=int, default=None)
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
+    ap.add_argument('--batch', type=int, default=0, help='per-replica batch override (sweeps; the result is marked as a non-headline config)')
     ap.add_argument('--balance', default='measured', choices=['measured', 'compute', 'params'], help='stage-balancing policy of the planner')
     ap.add_argument('--proportions', default=None, help='comma-separated parameter shares per stage (reference policy) instead of the compute-balanced plan')
     ap.add_argument('--prefetch-h2d', action='store_true', help='start the H2D copy of a batch at submit time on a copy stream (experimental)')
@@ -234,6 +235,8 @@ def main():
     home = os.environ.get('RAVNEST_HOME') or os.path.join(tempfile.gettempdir(), 'rvn_bench_{}'.format(os.environ.get('MASTER_PORT', '0')))
     os.environ['RAVNEST_HOME'] = home
     model, ex_args, ex_kwargs, batch = build_model(args)
+    if args.batch:
+        batch = args.batch
     if rank == 0:
         os.makedirs(home, exist_ok=True)
         # stages are balanced by the planner's step-time estimate (balance='compute'), not by parameter bytes
@@ -411,6 +414,8 @@ def main():
         }
         if args.layers:
             result['invalid'] = 'debug run with --layers'
+        if args.batch:
+            result['invalid'] = 'sweep run with --batch (not the BASELINE.json batch size)'
         print(json.dumps(result), flush=True)
     faulthandler.cancel_dump_traceback_later()
     # the measurements are out: whatever happens during teardown (a peer that is already gone, a slow communicator destroy)
