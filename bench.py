@@ -30,7 +30,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'baseline', 'reference'])
-    ap.add_argument('--model', default='bert', choices=['bert', 'resnet50', 'inception', 'sorter'])
+    ap.add_argument('--model', default='bert', choices=['bert', 'resnet50', 'inception', 'sorter', 'cnn'])
+    ap.add_argument('--ref-cpu', action='store_true', help='reference arm on CPU (plumbing check of the arm itself; not a benchmark)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--update-frequency', type=int, default=None)
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
@@ -43,11 +44,11 @@ def parse():
     return ap.parse_args()
 
 
-def reference_unavailable():
-    why = ("reference cannot be installed offline: setup.py pip-installs grpcio-tools==1.51.3 to compile protos and "
-           "ravnest/__init__ imports pippy (torchpippy==0.2.0) + torchinfo, none present in the image/wheelhouse; "
-           "it also has no NCCL/CUDA path (gRPC+pickle on CPU tensors)")
-    print(json.dumps({'impl': 'reference', 'unavailable': why}))
+def run_reference(args):
+    """The unmodified upstream package (baseline/_ref) through its own clusterize / Node / Trainer: baseline/ref_bench.py."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_bench
+    return ref_bench.run(args, (SyntheticBert, SyntheticImages), ClockSampler)
 
 
 class ClockSampler(threading.Thread):
@@ -188,9 +189,7 @@ class SyntheticImages:
 def main():
     args = parse()
     if args.impl == 'reference':
-        if int(os.environ.get('RANK', '0')) == 0:        # one line per job, also under torchrun
-            reference_unavailable()
-        return 0
+        return run_reference(args)
     import torch
     import torch.distributed as dist
     import ravnest_b200 as rv
