@@ -186,6 +186,7 @@ class Communication:
             for k in keys:
                 self.param_address_mapping[k] = (host, int(port))
         self.n_reduces = 0
+        self.stream_ctx = None        # set by Node: context that enters the stage's compute stream
 
     @staticmethod
     def _ranges(names: List[str], firsts: Dict[Any, str]) -> Dict[Any, List[str]]:
@@ -203,7 +204,9 @@ class Communication:
         cluster.  No-op for a single cluster (reference communication.py:126)."""
         if self.ring_size <= 1 or self.compute is None:
             return
-        with self.compute.lock:
+        import contextlib
+        ctx = self.stream_ctx() if self.stream_ctx is not None else contextlib.nullcontext()
+        with self.compute.lock, ctx:
             if self.dp_group is not None:
                 self._flat_average()
             else:
@@ -229,10 +232,10 @@ class Communication:
         import torch.distributed as dist
         store = self.compute.store
         fused = getattr(self.compute, '_fused', None)
-        if fused is not None and hasattr(fused, 'average_parameters'):
+        world = dist.get_world_size(self.dp_group)
+        if fused is not None and hasattr(fused, 'average_parameters') and fused.world == world:
             fused.average_parameters(include_state=self.average_optim)
             return
-        world = dist.get_world_size(self.dp_group)
         dist.all_reduce(store.master, group=self.dp_group)
         store.master.div_(world)
         if self.average_optim and self.compute.optimizer is not None:

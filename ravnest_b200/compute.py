@@ -97,6 +97,8 @@ class Compute:
         self._graph_failed = False
         self._stage_graphs = []
         self._max_stage_graphs = cluster_length + 2
+        self.run_next_step_eagerly = False  # one-shot: skip the CUDA graphs for the next stage step (K2 pull in flight)
+        self.after_next_step = None         # one-shot callback after the next forward / loss step
         self.loss_readback = False          # copy every step's loss to pinned host memory (async D2H)
         self._loss_host = None
         self.loss_history: List[Any] = []
@@ -108,8 +110,10 @@ class Compute:
     # ------------------------------------------------------------------ optimizer plumbing
     def _build_optimizer(self, optimizer_cls, params, fused, average_grads):
         from .optim import build_optimizer
+        # the DP group always reaches the fused optimizer (parameter averaging needs it too); the gradient all-reduce inside
+        # step() is switched on only in gradient-mode DP
         self.optimizer, self._fused = build_optimizer(optimizer_cls, params, self.store, dp_group=self.dp_group,
-                                                     fused=fused, average_grads=average_grads)
+                                                     fused=fused, average_grads=average_grads, sync_grads=average_grads)
 
     def optimizer_step(self) -> None:
         """Apply the accumulated gradient to the newest weights and publish a new version."""
@@ -170,17 +174,25 @@ class Compute:
                     out = self._call(slot, inputs)
                 self.flights[fpid] = Flight(fpid, slot, inputs, None, rng)
                 return out
-            if self.use_graphs and self.device.type == 'cuda':
+            eager_once, self.run_next_step_eagerly = self.run_next_step_eagerly, False
+            if self.use_graphs and self.device.type == 'cuda' and not eager_once:
                 gs = self._stage_graph_for(args, input_grads)
                 if gs is not None:
                     out = gs.run_forward(args)
                     self.flights[fpid] = Flight(fpid, slot, [], [], None, graph=gs)
+                    self._fire_after_step()
                     return out
             inputs = self._prepare_inputs(args, need_grad=input_grads)
             with torch.enable_grad():
                 out = self._call(slot, inputs)
             self.flights[fpid] = Flight(fpid, slot, inputs, _flatten_outputs(out), None)
+            self._fire_after_step()
             return _detach_tree(out)
+
+    def _fire_after_step(self) -> None:
+        hook, self.after_next_step = self.after_next_step, None
+        if hook is not None:
+            hook()
 
     def _stage_graph_for(self, args, input_grads):
         """A free GraphedStage for this input signature (captured lazily after the eager warm-up)."""
@@ -288,7 +300,8 @@ class Compute:
             self.model.train()
             slot = self.store.current
             det = in_grads = None
-            if self.use_graphs and self.device.type == 'cuda':
+            eager_once, self.run_next_step_eagerly = self.run_next_step_eagerly, False
+            if self.use_graphs and self.device.type == 'cuda' and not eager_once:
                 det, in_grads = self._graphed_loss_step(args, targets, input_grads, slot)
             if det is None:
                 inputs = self._prepare_inputs(args, need_grad=input_grads)
@@ -298,6 +311,7 @@ class Compute:
                 loss.backward()
                 in_grads = [a.grad if isinstance(a, torch.Tensor) and a.requires_grad else None for a in inputs]
                 det = loss.detach()
+            self._fire_after_step()
             self.last_loss = det
             if self.loss_readback and det.is_cuda:
                 if self._loss_host is None:

@@ -107,8 +107,16 @@ class Node:
                 n_labels = len(labels)
             except TypeError:
                 n_labels = None
-        if reduce_factor is None:
-            reduce_factor = n_labels if n_labels else 1
+        if reduce_factor is None and not n_labels:
+            # a node without labels (the typical root) cannot derive "once per epoch": no periodic averaging on this node's own
+            # clock — it still averages at the end of Trainer.train() — and, above all, no pipeline drain per update
+            if cfg['ring_size'] > 1 and kwargs.get('dp_mode', 'average') == 'average':
+                import warnings
+                warnings.warn('{}: reduce_factor not given and no labels to derive it from; pass the same reduce_factor to every node '
+                              'of the cluster to average periodically'.format(name))
+            reduce_factor = 1 << 40
+        elif reduce_factor is None:
+            reduce_factor = n_labels
         self.reduce_factor = reduce_factor
         self.reduce_threshold = self.update_frequency * max(1, int(reduce_factor))
 
@@ -141,7 +149,7 @@ class Node:
             criterion=self.criterion, device=self.device, update_frequency=self.update_frequency,
             cluster_length=self.cluster_length, recompute=recompute, compute_dtype=dtype,
             loss_filename=self.loss_filename if self.is_last else None, is_last=self.is_last,
-            dp_group=self.dp_group if self.dp_mode == 'gradient' else None,
+            dp_group=self.dp_group,
             fused_optimizer=kwargs.get('fused_optimizer'), lr_scheduler=lr_scheduler,
             lr_scheduler_params=lr_scheduler_params or {}, average_grads_over_dp=self.dp_mode == 'gradient',
             use_cuda_graphs=kwargs.get('use_cuda_graphs', self.device.type == 'cuda'), channels_last=self.channels_last)
@@ -175,6 +183,7 @@ class Node:
         self.compute_stream = torch.cuda.Stream(self.device) if self.device.type == 'cuda' else None
         if self.compute_stream is not None:
             self.compute_stream.wait_stream(torch.cuda.current_stream(self.device))   # init work is done
+        self.comm_session.stream_ctx = self.on_compute_stream     # collectives called from the user's thread join the compute stream
         if self._resume_tag:
             self.resumed = self.restore(self._resume_tag)      # False when this node has no such checkpoint (fresh start)
         self.start()
@@ -258,6 +267,11 @@ class Node:
                 raise
             self.status = NodeStatus.IDLE
 
+    def on_compute_stream(self):
+        """Context for main-thread entry points that touch the master weights / version slots: they run on the scheduler's compute
+        stream, i.e. ordered after every queued stage step and optimizer update (and before the next one)."""
+        return torch.cuda.stream(self.compute_stream) if self.compute_stream is not None else _NullCtx()
+
     def _check(self) -> None:
         if self._errors:
             raise RuntimeError('{} scheduler failed'.format(self.name)) from self._errors[0]
@@ -270,8 +284,9 @@ class Node:
         with self._cv:
             self._cv.wait_for(lambda: self.forward_pass_id - self.latest_backward_id <= self.cluster_length or self._errors)
         self._check()
-        if self.n_forwards and self.n_forwards % self.reduce_threshold == 0:
-            self.wait_for_backwards()
+        if (self.ring_size > 1 and self.dp_mode == 'average' and self.n_forwards
+                and self.n_forwards % self.reduce_threshold == 0):
+            self.wait_for_backwards()       # flush before a parameter-averaging point (reference node.py:387-388)
         args = self._pack_inputs(tensors, kwargs)
         msg = make_message(ActionTypes.ROOT_FORWARD, self.forward_pass_id, {}, args=args)
         if self.prefetch_h2d and self.device.type == 'cuda':
@@ -323,8 +338,7 @@ class Node:
         self._check()
         model_args = self._pack_inputs(tensors, kwargs)
         args = self.plan.stage_args(model_args)
-        ctx = torch.cuda.stream(self.compute_stream) if self.compute_stream is not None else _NullCtx()
-        with ctx:       # same stream as the scheduler: ordered after every queued optimizer update
+        with self.on_compute_stream():       # same stream as the scheduler: ordered after every queued optimizer update
             if self.node_type == NodeTypes.SOLO:
                 out = self.compute_session.no_grad_forward(args)
                 return self._consume_inference(out, output_type)
@@ -514,7 +528,7 @@ class Node:
         cs = self.compute_session
         cs.flush_losses()
         path = os.path.join(self.template_path, '{}.pt'.format(self.submod_file))
-        with cs.lock:
+        with cs.lock, self.on_compute_stream():
             # save the MASTER weights (fp32 even when the stage computes in bf16): point the module's parameters at copies of
             # them for the duration of the pickle, then back at the live compute-dtype version (stage steps use their own
             # parameter dicts, never the module's attributes, so nothing running is disturbed)
@@ -553,39 +567,51 @@ class Node:
         dist transport on CUDA: K2 — the DP-group leader publishes its weight bucket in symmetric memory and the
         next forward's GEMMs read their weight tiles straight from the leader's HBM over NVLink, landing them
         locally on the way (``parallel/broadcast.py``).  Collective: every replica of the stage must call it."""
-        if self.dp_group is not None and self.device.type == 'cuda' and self.compute_session.store.compute_dtype == torch.bfloat16:
+        cs = self.compute_session
+        if self.dp_group is not None and self.device.type == 'cuda' and cs.store.compute_dtype == torch.bfloat16:
             from .parallel.broadcast import WeightBroadcaster
             self.wait_for_backwards() if self.node_type in (NodeTypes.ROOT, NodeTypes.SOLO) else None
             if getattr(self, '_broadcaster', None) is None:
-                self._broadcaster = WeightBroadcaster(self.compute_session.store, self.dp_group, leader)
-            with self.compute_session.lock:
+                self._broadcaster = WeightBroadcaster(cs.store, self.dp_group, leader)
+            with cs.lock, self.on_compute_stream():
                 self._broadcaster.publish()
                 self._broadcaster.arm()
+                # the fp32 master travels exactly (NCCL, behind the armed bf16 pull): the follower's next optimizer step starts
+                # from the leader's master, not from a bf16-rounded copy of it
+                torch.distributed.broadcast(cs.store.master, src=torch.distributed.get_global_rank(self.dp_group, leader),
+                                            group=self.dp_group)
                 self._pending_pull = True
+                # the pull completes by itself: the next stage step runs eagerly (the armed GEMMs land the weights), then
+                # whatever was not consumed is copied and the pull is closed — no second user call
+                cs.run_next_step_eagerly = True
+                cs.after_next_step = self.finish_weight_pull
             return
         if self.dp_group is not None:
-            with self.compute_session.lock:
-                torch.distributed.broadcast(self.compute_session.store.master, src=torch.distributed.get_global_rank(self.dp_group, leader),
+            with cs.lock, self.on_compute_stream():
+                torch.distributed.broadcast(cs.store.master, src=torch.distributed.get_global_rank(self.dp_group, leader),
                                             group=self.dp_group)
-                self.compute_session.store.publish()
+                cs.store.publish()
             return
         weights = self.comm_session.get_latest_weights()
         self.compute_session.load_weights(weights)
 
     def finish_weight_pull(self) -> None:
-        """Complete a K2 pull after the first forward has consumed (and landed) the GEMM weights."""
+        """Complete a K2 pull after the first forward has consumed (and landed) the GEMM weights.  Called automatically after the
+        first stage step that follows ``update_with_latest_weights``; calling it by hand is harmless."""
         if getattr(self, '_pending_pull', False):
-            with self.compute_session.lock:
-                self._broadcaster.finish()
             self._pending_pull = False
+            with self.compute_session.lock, self.on_compute_stream():
+                self._broadcaster.finish()
 
     def checkpoint(self, tag: str = 'latest') -> str:
         from .utils.checkpoint import save_checkpoint
-        return save_checkpoint(self, tag)
+        with self.on_compute_stream():
+            return save_checkpoint(self, tag)
 
     def restore(self, tag: str = 'latest') -> bool:
         from .utils.checkpoint import load_checkpoint
-        return load_checkpoint(self, tag)
+        with self.on_compute_stream():
+            return load_checkpoint(self, tag)
 
     def reset(self) -> None:
         """Clear run outputs of a previous job (reference node.py:732-746)."""

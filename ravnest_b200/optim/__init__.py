@@ -14,23 +14,27 @@ __all__ = ['Lamb', 'build_optimizer']
 
 
 def _kind_of(optimizer_cls):
-    name = getattr(optimizer_cls, '__name__', '').lower()
-    if optimizer_cls is torch.optim.SGD or name == 'sgd':
-        return 'sgd'
-    if optimizer_cls is torch.optim.AdamW or name == 'adamw':
-        return 'adamw'
-    if optimizer_cls is torch.optim.Adam or name == 'adam':
-        return 'adam'
-    if optimizer_cls is Lamb or name == 'lamb':
+    """Only classes we KNOW are lowered onto the fused kernels (identity / subclass of torch's, our Lamb, or the
+    ``torch_optimizer.Lamb`` the reference's BERT example uses) — a user class that merely shares a name is left alone."""
+    if not isinstance(optimizer_cls, type):
+        return None
+    for cls, kind in ((torch.optim.SGD, 'sgd'), (torch.optim.AdamW, 'adamw'), (torch.optim.Adam, 'adam'), (Lamb, 'lamb')):
+        if optimizer_cls is cls or (issubclass(optimizer_cls, cls) and optimizer_cls.step is cls.step):
+            return kind
+    if optimizer_cls.__name__ == 'Lamb' and optimizer_cls.__module__.split('.')[0] == 'torch_optimizer':
         return 'lamb'
     return None
 
 
-def build_optimizer(optimizer_cls, params, store, dp_group=None, fused=None, average_grads=False):
+def build_optimizer(optimizer_cls, params, store, dp_group=None, fused=None, average_grads=False, sync_grads=None):
     kind = _kind_of(optimizer_cls)
     want_fused = fused if fused is not None else (store.device.type == 'cuda' and kind is not None)
     if want_fused and kind is not None and store.device.type == 'cuda':
         from ..parallel.fused_optim import FusedFlatOptimizer
-        opt = FusedFlatOptimizer(store, kind, params, dp_group=dp_group, average_grads=average_grads)
-        return opt, opt
+        try:
+            opt = FusedFlatOptimizer(store, kind, params, dp_group=dp_group, average_grads=average_grads, sync_grads=sync_grads)
+            return opt, opt
+        except TypeError as err:            # amsgrad / maximize / unknown kwargs: the stock optimizer has them, the kernel does not
+            import warnings
+            warnings.warn('fused optimizer not used: {}'.format(err))
     return optimizer_cls(store.master_params, **params), None

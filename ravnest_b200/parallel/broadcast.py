@@ -55,9 +55,10 @@ class WeightBroadcaster:
         return n
 
     def finish(self) -> None:
-        """Anything still armed (weights the forward never touched) is copied the plain way; then refresh the master copy."""
+        """Anything still armed (weights the forward never touched) is copied the plain way.  The fp32 master is NOT rebuilt from
+        the bf16 weights (that would round it): ``Node.update_with_latest_weights`` broadcasts it exactly.  The version counter
+        moves so pass-private weight copies (``GraphedStage.wbuf``) refresh."""
         for leaf, src in native.drain_peer_weights():
             leaf.detach().copy_(src)
-        with torch.no_grad():
-            self.store.master.copy_(self.store.current.flat)
-        dist.barrier(group=self.group)
+        self.store.version += 1
+        self.store.current.version = self.store.version

@@ -23,7 +23,11 @@ _CHUNK = 16384          # elements per LAMB chunk (never straddles a parameter)
 
 
 class FusedFlatOptimizer(torch.optim.Optimizer):
-    def __init__(self, store, kind: str, params: dict, dp_group=None, average_grads: bool = False):
+    def __init__(self, store, kind: str, params: dict, dp_group=None, average_grads: bool = False,
+                 sync_grads: Optional[bool] = None):
+        """``dp_group``: the stage's replicas.  ``sync_grads`` (default: ``average_grads``): all-reduce the gradient bucket inside
+        ``step()`` (gradient-mode DP).  With ``sync_grads=False`` the group is only used by ``average_parameters()`` — the reference's
+        periodic parameter averaging — and ``step()`` is a purely local update."""
         self.kind = kind
         self.store = store
         p = dict(params)
@@ -39,7 +43,10 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
                             adam=p.pop('adam', False), debias=p.pop('debias', False))
         else:
             raise ValueError(kind)
-        for k in ('foreach', 'fused', 'capturable', 'maximize', 'differentiable', 'amsgrad'):
+        for k in ('maximize', 'differentiable', 'amsgrad'):
+            if p.pop(k, False):          # different numerics: refuse instead of silently ignoring (the caller falls back to torch's optimizer)
+                raise TypeError('fused {} does not implement {}=True'.format(kind, k))
+        for k in ('foreach', 'fused', 'capturable'):
             p.pop(k, None)
         if p:
             raise TypeError('unsupported optimizer arguments for fused {}: {}'.format(kind, sorted(p)))
@@ -53,14 +60,16 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
         self.epoch = 0
         self.dp_group = dp_group
         self.average_grads = average_grads
+        self.sync_grads = bool(average_grads if sync_grads is None else sync_grads)
         self.grad_sym = self.sig_sym = self.avg_sym = None
         self.rank, self.world = 0, 1
         if dp_group is not None and dist.get_world_size(dp_group) > 1:
             from .symmetric import SymmetricBuffer
-            self.grad_sym = SymmetricBuffer(n, store.compute_dtype, dev, dp_group)
             self.sig_sym = SymmetricBuffer(64, torch.int32, dev, dp_group)
-            store.rebind_grad(self.grad_sym.tensor)
-            self.rank, self.world = self.grad_sym.rank, self.grad_sym.world
+            self.rank, self.world = self.sig_sym.rank, self.sig_sym.world
+            if self.sync_grads:
+                self.grad_sym = SymmetricBuffer(n, store.compute_dtype, dev, dp_group)
+                store.rebind_grad(self.grad_sym.tensor)
         if kind == 'lamb':
             self._build_chunks()
         self._C = _ext.load()
@@ -95,7 +104,7 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
             c1, c2 = 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t)
         if kind == 'lamb' and group['debias']:
             lr = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
-        scale = (1.0 / self.world) if (self.average_grads and self.world > 1) else 1.0
+        scale = (1.0 / self.world) if (self.average_grads and self.grad_sym is not None and self.world > 1) else 1.0
         f = [lr, b1, b2, group.get('eps', 0.0), group['weight_decay'], group.get('momentum', 0.0), group.get('dampening', 0.0),
              scale, c1, c2, group.get('clamp_value', 0.0)]
         flags = [int(group.get('nesterov', False)), int(t == 1), int(kind == 'adamw'), int(group.get('adam', False))]
@@ -156,6 +165,7 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
         return sd
 
     def load_state_dict(self, sd):
+        sd = dict(sd)                       # never mutate the caller's dict
         flat = sd.pop('flat', None)
         super().load_state_dict(sd)
         if flat is not None:

@@ -17,14 +17,26 @@ def _philox_state(device):
     return native.rng_state(device).detach().to('cpu')
 
 
+def _snapshot(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().to('cpu', copy=True)
+    if isinstance(obj, dict):
+        return {k: _snapshot(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_snapshot(v) for v in obj)
+    return obj
+
+
 def save_checkpoint(node, tag='latest'):
     cs = node.compute_session
     with cs.lock:
+        # everything is COPIED under the lock (``.to('cpu')`` aliases CPU tensors, ``optimizer.state_dict()`` returns live references):
+        # the scheduler may update the stage while torch.save serialises
         state = {
-            'master': cs.store.master.detach().to('cpu'),
-            'names': cs.store.names,
-            'buffers': {k: v.detach().to('cpu') for k, v in node.model.named_buffers()},
-            'optimizer': cs.optimizer.state_dict() if cs.optimizer is not None else None,
+            'master': cs.store.master.detach().to('cpu', copy=True),
+            'names': list(cs.store.names),
+            'buffers': {k: v.detach().to('cpu', copy=True) for k, v in node.model.named_buffers()},
+            'optimizer': _snapshot(cs.optimizer.state_dict()) if cs.optimizer is not None else None,
             'lr_scheduler': cs.lr_scheduler.state_dict() if cs.lr_scheduler is not None else None,
             'counters': {'n_backwards': cs.n_backwards, 'n_updates': cs.n_updates, 'version': cs.store.version,
                          'forward_pass_id': node.forward_pass_id, 'latest_backward_id': node.latest_backward_id,
