@@ -73,7 +73,13 @@ def _build_model(model_name, device):
     if model_name == 'bert':
         from transformers import BertConfig, BertForPreTraining
         config = BertConfig()
+        if os.environ.get('RVN_REF_TINY') == '1':      # plumbing check on CPU only; the result is marked invalid
+            config = BertConfig(num_hidden_layers=4, hidden_size=128, num_attention_heads=2, intermediate_size=256, vocab_size=1000)
         config.return_dict = False
+        # the explicit matmul-softmax attention of the transformers release the reference was written against: its additive
+        # float mask is what crosses the stage cut (the reference calls requires_grad_() on every received tensor,
+        # ravnest/compute.py:436, which a boolean SDPA mask cannot take)
+        config._attn_implementation = 'eager'
         model = BertForPreTraining(config)
         batch, seq = 8, 512
         g = torch.Generator().manual_seed(0)
@@ -198,8 +204,10 @@ def run(args, datasets, ClockSampler):
             unavailable('no CUDA device visible')
         return 0
     device = torch.device('cuda') if use_cuda else torch.device('cpu')
-    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{}'.format(master_port + 1 if n_gpus == 1 else master_port + 7),
-                            rank=rank, world_size=n_nodes)
+    if n_gpus == 1:       # two providers on one GPU, launched by us
+        dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{}'.format(master_port + 1), rank=rank, world_size=n_nodes)
+    else:                 # torchrun: its agent store
+        dist.init_process_group('gloo')
     # ----- everything the reference prints goes to a log file; stdout carries the one JSON line -------------------
     log_path = os.path.join(workdir, 'provider_{}.log'.format(rank))
     real_stdout = os.dup(1)
@@ -218,23 +226,36 @@ def run(args, datasets, ClockSampler):
         import traceback
         traceback.print_exception(hook_args.exc_type, hook_args.exc_value, hook_args.exc_traceback, file=log)
         log.flush()
-        if rank == 0:
-            emit({'impl': 'reference', 'unavailable': 'a reference thread died: {!r} (log: {})'.format(hook_args.exc_value, log_path)})
-        if helper is not None:
-            helper.kill()
-        os._exit(0)
+        with open(os.path.join(workdir, 'FAILED_{}'.format(rank)), 'w') as fh:
+            fh.write('provider {}: {!r}'.format(rank, hook_args.exc_value))
 
+    def watchdog():                                    # any provider's failure ends every provider (rank 0 reports it)
+        import glob
+        limit = time.time() + float(os.environ.get('RVN_REF_TIMEOUT', '1500'))
+        while True:
+            time.sleep(0.5)
+            marks = glob.glob(os.path.join(workdir, 'FAILED_*'))
+            if marks or time.time() > limit:
+                why = open(marks[0]).read() if marks else 'no result within RVN_REF_TIMEOUT'
+                if rank == 0:
+                    emit({'impl': 'reference', 'unavailable': 'reference run failed: {} (logs: {})'.format(why, workdir)})
+                if helper is not None:
+                    helper.kill()
+                os._exit(0)
+
+    for stale in [f for f in os.listdir(workdir) if f.startswith('FAILED_')] if rank == 0 else []:
+        os.remove(os.path.join(workdir, stale))
     threading.excepthook = thread_died
+    threading.Thread(target=watchdog, daemon=True).start()
     try:
         result = _provider(args, datasets, ClockSampler, rank, local_rank, n_nodes, stages, replicas, master_port, device, log)
     except BaseException as err:                       # a crashed provider must not hang its peers
         import traceback
         traceback.print_exc(file=log)
         log.flush()
-        if rank == 0:
-            emit({'impl': 'reference', 'unavailable': 'reference run failed: {!r} (log: {})'.format(err, log_path)})
-        if helper is not None:
-            helper.kill()
+        with open(os.path.join(workdir, 'FAILED_{}'.format(rank)), 'w') as fh:
+            fh.write('provider {}: {!r}'.format(rank, err))
+        time.sleep(5)                                  # the watchdog reports and exits
         os._exit(0)
     if rank == 0 and result is not None:
         emit(result)
@@ -272,14 +293,15 @@ def _provider(args, datasets, ClockSampler, rank, local_rank, n_nodes, stages, r
     if args.model == 'bert':
         from torch_optimizer import Lamb
         from bert_trainer import BERT_Trainer           # the reference's own custom trainer (examples/bert/bert_trainer.py)
-        pool = SyntheticBert(4, 8, 512, 30522, device=None, seed=replica).items
+        vocab = 1000 if os.environ.get('RVN_REF_TINY') == '1' else 30522
+        pool = SyntheticBert(4, 8, 512, vocab, device=None, seed=replica).items
         batch = 8
         loss_fct = torch.nn.CrossEntropyLoss()
 
         def loss_fn(y_pred, targets):
             labels = targets['labels'].to(device)
             sentence_order_label = targets['sentence_order_label'].to(device)
-            masked_lm_loss = loss_fct(y_pred[0].view(-1, 30522), labels.view(-1))
+            masked_lm_loss = loss_fct(y_pred[0].view(-1, vocab), labels.view(-1))
             sentence_order_loss = loss_fct(y_pred[1].view(-1, 2), sentence_order_label.view(-1))
             total_loss = masked_lm_loss + sentence_order_loss
             total_loss.div_(upd)
@@ -400,6 +422,7 @@ def _provider(args, datasets, ClockSampler, rank, local_rank, n_nodes, stages, r
                 'note': 'the reference path is end to end by construction: host loader -> .to(device) every step, loss.item() every step; '
                         'activations additionally cross PCIe twice per hop'},
         'gpu_launches': 0,
+        **({'invalid': 'RVN_REF_TINY plumbing run'} if os.environ.get('RVN_REF_TINY') == '1' else {}),
         'wall_ms_per_step': max(t[1] for t in times) / steps,
         'per_provider_ms': [{'node': i, 'type': t[2], 'replica': t[3], 'device_ms': round(t[0], 2)} for i, t in enumerate(times)],
         'last_loss_per_rank': losses,
