@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--prefetch-h2d', action='store_true', help='start the H2D copy of a batch at submit time on a copy stream (experimental)')
     ap.add_argument('--no-graphs', action='store_true', help='disable CUDA-graph capture of the stage step')
     ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
+    ap.add_argument('--diagnose', type=int, default=0, help='after the timed regions: profile this many steady-state steps on every rank and '
+                    'write gpurun_out/diag_<model>_n<N>_rank<r>.txt (per-stream busy time, gaps, top kernels, native call counters)')
     return ap.parse_args()
 
 
@@ -392,6 +394,8 @@ def main():
     else:
         last_losses = [mine]
     launches = count_launches(node, feed, pool_dev, driver, sync, Labels) if rank == 0 or world > 1 else None
+    if args.diagnose:
+        diagnose(args, node, feed, pool_dev, driver, sync, Labels, rank, world)
     if rank == 0:
         value = replicas * batch * args.steps / (dev_ms / 1e3)
         result = {
@@ -431,6 +435,57 @@ def main():
         dist.barrier(group=gloo)
         dist.destroy_process_group()
     return 0
+
+
+def diagnose(args, node, feed, pool, driver, sync, Labels, rank, world):
+    """Steady-state timeline summary of this rank: where the step's device time goes and where the stream sits idle."""
+    import torch
+    from collections import defaultdict
+    from torch.profiler import ProfilerActivity, profile
+    from ravnest_b200.ops import native
+    Labels.mode = 'dev'
+    steps = args.diagnose
+    src = iter(pool)
+    sync()
+    before = dict(native.calls)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        if driver:
+            for _ in range(steps):
+                feed(node, next(src))
+            node.wait_for_backwards()
+        sync()
+    after = dict(native.calls)
+    per_stream = defaultdict(list)
+    by_name = defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        t0 = ev.time_range.start
+        t1 = ev.time_range.end
+        stream = getattr(ev, 'stream', None)
+        per_stream[stream if stream is not None else -1].append((t0, t1, ev.name))
+        by_name[ev.name][0] += 1
+        by_name[ev.name][1] += (t1 - t0)
+    lines = ['rank {} of {}  node_type {}  steps {}'.format(rank, world, node.node_type, steps)]
+    for stream, evs in sorted(per_stream.items(), key=lambda kv: -sum(b - a for a, b, _ in kv[1])):
+        evs.sort()
+        busy = sum(b - a for a, b, _ in evs)
+        span = evs[-1][1] - evs[0][0]
+        gaps = sorted(((evs[i + 1][0] - evs[i][1], evs[i][2][:60], evs[i + 1][2][:60]) for i in range(len(evs) - 1)), reverse=True)
+        big = [g for g in gaps if g[0] > 20]
+        lines.append('stream {}: {} kernels, busy {:.3f} ms/step, span {:.3f} ms/step, idle {:.3f} ms/step in {} gaps > 20 us'.format(
+            stream, len(evs), busy / 1e3 / steps, span / 1e3 / steps, sum(g[0] for g in big) / 1e3 / steps, len(big)))
+        for g in big[:12]:
+            lines.append('    gap {:8.1f} us  after {}  before {}'.format(g[0], g[1], g[2]))
+    lines.append('top kernels (count/step, us/step):')
+    for name, (n, t) in sorted(by_name.items(), key=lambda kv: -kv[1][1])[:45]:
+        lines.append('  {:7.1f} {:9.1f}  {}'.format(n / steps, t / steps, name[:110]))
+    lines.append('native calls per step: ' + json.dumps({k: round((after.get(k, 0) - before.get(k, 0)) / steps, 2) for k in after
+                                                         if after.get(k, 0) != before.get(k, 0)}))
+    lines.append('native fallbacks: ' + json.dumps(dict(getattr(native, 'fallbacks', {}))))
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'diag_{}_n{}_rank{}.txt'.format(args.model, world, rank)), 'w') as fh:
+        fh.write('\n'.join(lines) + '\n')
 
 
 def count_launches(node, feed, pool, driver, sync, Labels):
