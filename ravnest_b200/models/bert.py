@@ -218,6 +218,28 @@ class BertForPreTraining(nn.Module):
         return prediction_logits, seq_relationship_logits
 
 
+def to_hf_state_dict(model: BertForPreTraining):
+    """State dict under HuggingFace's exact key set (``transformers.BertForPreTraining.load_state_dict`` accepts it strictly):
+    the fused ``attention.self.qkv`` parameter is split back into ``query`` / ``key`` / ``value`` and the tied decoder bias is
+    listed under both of HF's names.  The inverse direction needs no helper: ``load_state_dict`` merges q/k/v on the fly."""
+    out = {}
+    for k, v in model.state_dict().items():
+        if '.attention.self.qkv.' in k:
+            prefix, kind = k.split('.attention.self.qkv.')
+            H = v.shape[0] // 3
+            for i, n in enumerate(('query', 'key', 'value')):
+                out['{}.attention.self.{}.{}'.format(prefix, n, kind)] = v[i * H:(i + 1) * H]
+        else:
+            out[k] = v
+    if 'cls.predictions.decoder.bias' in out:
+        out.setdefault('cls.predictions.bias', out['cls.predictions.decoder.bias'])
+    if 'cls.predictions.bias' in out:
+        out.setdefault('cls.predictions.decoder.bias', out['cls.predictions.bias'])
+    if 'cls.predictions.decoder.weight' not in out and 'bert.embeddings.word_embeddings.weight' in out:
+        out['cls.predictions.decoder.weight'] = out['bert.embeddings.word_embeddings.weight']
+    return out
+
+
 def bert_pretraining_loss(outputs, labels, sentence_order_label, ignore_index=-100):
     """MLM + SOP loss of the reference's BERT provider (examples/bert/provider.py:30-40)."""
     from .. import ops

@@ -23,12 +23,16 @@ def _pair(layers=2, hidden=64, heads=4, inter=128, vocab=512, maxpos=64):
 
 
 def test_state_dict_keys_match_hf():
+    """Our only structural difference is the fused [3H, H] QKV parameter; ``to_hf_state_dict`` undoes it, and HF loads the result
+    strictly.  The other direction (HF -> ours) goes through ``load_state_dict`` directly (next test)."""
     hf, ours = _pair()
+    exported = models.to_hf_state_dict(ours)
     hf_keys = {k for k in hf.state_dict() if not k.endswith('position_ids') and not k.endswith('token_type_ids')}
-    our_keys = {k for k in ours.state_dict()}
-    # HF registers the tied decoder bias twice (cls.predictions.bias and cls.predictions.decoder.bias); both spellings are accepted
-    assert hf_keys - our_keys <= {'cls.predictions.decoder.bias', 'cls.predictions.bias'}, sorted(hf_keys - our_keys)
-    assert our_keys - hf_keys <= {'cls.predictions.decoder.bias', 'cls.predictions.bias'}, sorted(our_keys - hf_keys)
+    assert set(exported) == hf_keys, (sorted(set(exported) ^ hf_keys))
+    hf.load_state_dict(exported, strict=False)
+    for k, v in hf.state_dict().items():
+        if k in exported:
+            assert torch.equal(v, exported[k]), k
 
 
 def test_default_config_matches_hf_bert_base():
