@@ -457,15 +457,16 @@ def diagnose(args, node, feed, pool, driver, sync, Labels, rank, world):
     after = dict(native.calls)
     per_stream = defaultdict(list)
     by_name = defaultdict(lambda: [0, 0.0])
-    for ev in prof.events():
-        if ev.device_type != torch.autograd.DeviceType.CUDA:
-            continue
-        t0 = ev.time_range.start
-        t1 = ev.time_range.end
-        stream = getattr(ev, 'stream', None)
-        per_stream[stream if stream is not None else -1].append((t0, t1, ev.name))
-        by_name[ev.name][0] += 1
-        by_name[ev.name][1] += (t1 - t0)
+    try:            # kineto events carry the stream id (FunctionEvent does not)
+        raw = [(e.device_resource_id(), e.start_ns() / 1e3, (e.start_ns() + e.duration_ns()) / 1e3, e.name())
+               for e in prof.profiler.kineto_results.events()
+               if str(e.device_type()).endswith('CUDA') and e.duration_ns() > 0]
+    except Exception:
+        raw = [(-1, ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA]
+    for stream, t0, t1, name in raw:
+        per_stream[stream].append((t0, t1, name))
+        by_name[name][0] += 1
+        by_name[name][1] += (t1 - t0)
     lines = ['rank {} of {}  node_type {}  steps {}'.format(rank, world, node.node_type, steps)]
     for stream, evs in sorted(per_stream.items(), key=lambda kv: -sum(b - a for a, b, _ in kv[1])):
         evs.sort()

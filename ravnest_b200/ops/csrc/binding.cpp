@@ -4,6 +4,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <cuda_runtime.h>
 #include <torch/extension.h>
+#include <cstdlib>
 
 #include <map>
 #include <mutex>
@@ -12,7 +13,8 @@
 extern "C" {
 int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
                   const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out, int ld_preact,
-                  int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int num_sms,
+                  int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int split_k,
+                  int reduce_out, int num_sms,
                   cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
@@ -98,6 +100,42 @@ int ld_of(const torch::Tensor& t) {
   return static_cast<int>(t.stride(0));
 }
 
+// Tile shape (128 x BN, BN in {128, 192, 256}) and split-K factor from a wave model of the persistent kernel: one CTA per SM runs
+// ceil(units / SMs) work units back to back; a unit costs (k-blocks / split) * BN / eff(BN) plus one exposed epilogue.  eff = achieved
+// fraction of the tensor peak per tile shape (128-wide tiles are shared-memory-bandwidth bound: A + B = 128 B/clk).  Explicit
+// block_n / split_k > 0 (or RVN_GEMM_BN / RVN_GEMM_SPLITK) override the model.
+static void choose_tiling(int M, int N, int K, bool can_split, int sms, int64_t* block_n, int64_t* split_k) {
+  static const int env_bn = getenv("RVN_GEMM_BN") ? atoi(getenv("RVN_GEMM_BN")) : 0;
+  static const int env_sk = getenv("RVN_GEMM_SPLITK") ? atoi(getenv("RVN_GEMM_SPLITK")) : 0;
+  if (*block_n <= 0 && env_bn > 0) *block_n = env_bn;
+  if (*split_k <= 0 && env_sk > 0) *split_k = env_sk;
+  if (!can_split) *split_k = 1;
+  const int mb = (M + 127) / 128, nkb = (K + 63) / 64;
+  const int bns[3] = {128, 192, 256};
+  const double eff[3] = {0.76, 0.86, 0.92};
+  const int splits[6] = {1, 2, 3, 4, 6, 8};
+  double best = 1e30;
+  int best_bn = 128, best_s = 1;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = bns[i];
+    if (*block_n > 0 && bn != *block_n) continue;
+    if (bn > 128 && N < bn) continue;
+    const int nb = (N + bn - 1) / bn;
+    for (int j = 0; j < 6; ++j) {
+      const int s = splits[j];
+      if (*split_k > 0 && s != *split_k) continue;
+      if (s > 1 && (!can_split || nkb / s < 8)) continue;
+      const long units = static_cast<long>(mb) * nb * s;
+      const long waves = (units + sms - 1) / sms;
+      const double unit_cost = (static_cast<double>(nkb) / s + 1.5) * bn / eff[i];     // + pipeline fill / barrier turn-around per unit
+      const double cost = waves * unit_cost + 5.0 * bn + (s > 1 ? 2.0 * bn : 0.0);    // + one exposed epilogue (+ L2 reduce traffic)
+      if (cost < best) { best = cost; best_bn = bn; best_s = s; }
+    }
+  }
+  if (*block_n <= 0 || (*block_n != 128 && *block_n != 192 && *block_n != 256)) *block_n = best_bn;
+  if (*split_k <= 0) *split_k = best_s;
+}
+
 // D[M,N] = epi(op(A) * op(B)^T).  A: [M,K] (a_mn=false) or [K,M] (a_mn=true); B: [N,K] (b_mn=false) or [K,N] (b_mn=true).
 // store_preact: 0 none, 1 also return the pre-activation z, 2 also return act'(z).  aux_mode (with dact_in): 1 D = acc * act'(aux),
 // 2 D = acc + aux, 3 D = acc * aux.  Returns {D} or {D, preact}.  D is allocated with a row stride rounded up to 8 elements; a narrowed view is returned.
@@ -106,7 +144,7 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
                                 const c10::optional<torch::Tensor>& dact_in, int64_t store_preact, int64_t block_n,
                                 int64_t aux_mode, const c10::optional<torch::Tensor>& out,
                                 const c10::optional<torch::Tensor>& b_copy_dst, const c10::optional<torch::Tensor>& bcopy_flags,
-                                int64_t bcopy_epoch) {
+                                int64_t bcopy_epoch, int64_t split_k) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16,
               "gemm expects CUDA bf16 operands");
   c10::cuda::CUDAGuard guard(A.device());
@@ -143,11 +181,12 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
     P = torch::empty({M, (N + 7) / 8 * 8}, A.options());
     preact_ptr = P.data_ptr();
   }
-  if (block_n <= 0) {
-    // tile-shape heuristic: 128x256 tiles halve smem traffic per FLOP; take them when they still fill the machine
-    const int64_t tiles256 = static_cast<int64_t>((M + 127) / 128) * ((N + 255) / 256);
-    block_n = (N >= 256 && tiles256 >= sm_count()) ? 256 : 128;
-  }
+  // gradient accumulation D += A*B (aux_mode 2 with the aux tile being D itself): done by TMA reduce-add, D is never read and the
+  // K range may be split over several CTAs (wgrad shapes have few output tiles and a long K)
+  const bool reduce_out = dact_ptr != nullptr && aux_mode == 2 && out.has_value() && out->defined() &&
+                          dact_ptr == out->data_ptr() && ld_dact == ldd && !store_preact && !(bias.has_value() && bias->defined()) && act == 0;
+  if (reduce_out) dact_ptr = nullptr;
+  choose_tiling(M, N, K, reduce_out, sm_count(), &block_n, &split_k);
   void* bcopy_ptr = nullptr;
   int ld_bcopy = 0;
   if (b_copy_dst.has_value() && b_copy_dst->defined()) {   // K2: B lives in a peer's HBM; land it locally while multiplying
@@ -160,7 +199,8 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   unsigned* flags_ptr = bcopy_ptr != nullptr ? reinterpret_cast<unsigned*>(bcopy_flags->data_ptr<int>()) : nullptr;
   check(rvn_gemm_bf16(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
                       dact_ptr, ld_dact, static_cast<int>(aux_mode), preact_ptr, store_preact ? static_cast<int>(P.stride(0)) : ldd,
-                      static_cast<int>(store_preact), bcopy_ptr, ld_bcopy, flags_ptr, static_cast<unsigned>(bcopy_epoch), static_cast<int>(block_n), sm_count(),
+                      static_cast<int>(store_preact), bcopy_ptr, ld_bcopy, flags_ptr, static_cast<unsigned>(bcopy_epoch), static_cast<int>(block_n),
+                      static_cast<int>(split_k), reduce_out ? 1 : 0, sm_count(),
                       cur_stream()),
         "gemm_bf16");
   std::vector<torch::Tensor> res;
@@ -659,7 +699,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "bf16 tcgen05 GEMM with fused epilogue", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("aux_in") = py::none(), py::arg("store_preact") = false,
         py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none(),
-        py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0);
+        py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0, py::arg("split_k") = 0);
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("gamma"), py::arg("mean"), py::arg("rstd"), py::arg("rng"),
         py::arg("dropout_p"), py::arg("grad_gamma") = py::none(), py::arg("grad_beta") = py::none());

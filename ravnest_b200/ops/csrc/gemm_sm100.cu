@@ -45,6 +45,9 @@ struct GemmParams {
   unsigned* bcopy_flags;
   unsigned bcopy_epoch;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  int split_k;                    // >1: work unit = (tile, k-slice); only with reduce_out (partials are summed by the L2)
+  int reduce_out;                 // D += acc through TMA reduce-add (cp.reduce.async.bulk.tensor .add on the bf16 map) instead of
+                                  // store: gradient accumulation into the flat bucket without reading it, and split-K safe
 };
 
 template <int BN>
@@ -52,7 +55,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int OPERAND_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = 2 * SLAB_BYTES;
   static constexpr int BAR_OFFSET = OPERAND_BYTES + STAGING_BYTES;
@@ -118,7 +121,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
                       const __grid_constant__ CUtensorMap map_bcopy, const GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;                 // two accumulator stages (256 or 512 columns)
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);   // two accumulator stages, power of two
   constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BN, A_MN, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -133,6 +136,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_units = num_tiles * p.split_k;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_a);
@@ -166,7 +170,10 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles;
+        const int ks = unit / num_tiles;
+        const int kb_begin = ks * p.num_k_blocks / p.split_k, kb_end = (ks + 1) * p.num_k_blocks / p.split_k;
         const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
         const int n0 = (tile / p.num_m_blocks) * BN;
         if (!B_MN && p.b_copy) {
@@ -182,7 +189,7 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
           }
           asm volatile("fence.proxy.async;" ::: "memory");
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
@@ -216,11 +223,13 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int ks = unit / num_tiles;
+      const int kb_begin = ks * p.num_k_blocks / p.split_k, kb_end = (ks + 1) * p.num_k_blocks / p.split_k;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -235,10 +244,10 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
                                      : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
-            umma_bf16(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da, db, IDESC, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);                       // frees the smem stage when these MMAs retire
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb_end - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -276,13 +285,14 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (et == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.bcopy_flags + t), "r"(p.bcopy_epoch) : "memory");
       }
     }
-    const bool has_aux_in = p.dact_in != nullptr;
+    const bool has_aux_in = p.dact_in != nullptr;           // never together with reduce_out / split_k (host guarantees it)
     const bool one_buffer = p.store_preact || has_aux_in;     // staging[1] is taken by the aux slab (in or out)
     if (has_aux_in && issuer && static_cast<int>(blockIdx.x) < num_tiles) {   // aux tile of the very first slab: overlaps the mainloop
       mbar_expect_tx(aux_bar, SLAB_BYTES);
       tma_load_2d(staging + SLAB_BYTES, &map_aux, aux_bar, (blockIdx.x / p.num_m_blocks) * BN, (blockIdx.x % p.num_m_blocks) * BLOCK_M);
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int tile = unit % num_tiles;
       const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
       const int n0 = (tile / p.num_m_blocks) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -387,14 +397,14 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_THREADS);
         if (issuer) {
-          tma_store_2d(&map_d, buf_main, col0, m0);
+          if (p.reduce_out) tma_reduce_add_2d(&map_d, buf_main, col0, m0); else tma_store_2d(&map_d, buf_main, col0, m0);
           if (p.store_preact) tma_store_2d(&map_aux, buf_aux, col0, m0);
           tma_store_commit();
           if (has_aux_in) {
             // every thread has consumed buf_aux (it passed the barrier above): prefetch the NEXT slab's aux tile now,
             // either the next slab of this tile or the first slab of this CTA's next tile
             int nt = tile, ns = slab + 1;
-            if (ns == BN / SLAB_N || n0 + ns * SLAB_N >= p.N) { nt = tile + gridDim.x; ns = 0; }
+            if (ns == BN / SLAB_N || n0 + ns * SLAB_N >= p.N) { nt = tile + gridDim.x; ns = 0; }     // split_k == 1 here: unit == tile
             if (nt < num_tiles) {
               mbar_expect_tx(aux_bar, SLAB_BYTES);
               tma_load_2d(buf_aux, &map_aux, aux_bar, (nt / p.num_m_blocks) * BN + ns * SLAB_N, (nt % p.num_m_blocks) * BLOCK_M);
@@ -457,6 +467,10 @@ template <int BN, bool A_MN, bool B_MN>
 static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, void* aux_out, int ld_auxout,
                   void* b_copy_dst, int ld_bcopy, GemmParams p, int num_sms, cudaStream_t stream) {
   if (p.bcopy_flags == nullptr) b_copy_dst = nullptr;
+  if (p.reduce_out) {                    // the accumulated-into tensor is never read: no aux slab
+    p.dact_in = nullptr;
+    p.aux_mode = 0;
+  }
   if (p.dact_in != nullptr) {            // aux INPUT tile (mutually exclusive with the pre-activation output)
     aux_out = const_cast<__nv_bfloat16*>(p.dact_in);
     ld_auxout = p.ld_aux;
@@ -487,7 +501,9 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
     if (ce != cudaSuccess) return 2000 + static_cast<int>(ce);
     configured = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  if (p.split_k < 1 || !p.reduce_out) p.split_k = 1;
+  if (p.split_k > p.num_k_blocks) p.split_k = p.num_k_blocks;
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(ma, mb, md, mx, mc, p);
   cudaError_t le = cudaGetLastError();
@@ -500,7 +516,7 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
                              int K, const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out,
                              int ld_preact, int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n,
-                             int num_sms, cudaStream_t stream) {
+                             int split_k, int reduce_out, int num_sms, cudaStream_t stream) {
   rvn::GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -511,12 +527,15 @@ extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   p.store_preact = preact_out != nullptr ? (preact_mode == 2 ? 2 : 1) : 0;
   p.bcopy_flags = bcopy_flags;
   p.bcopy_epoch = bcopy_epoch;
+  p.split_k = split_k;
+  p.reduce_out = reduce_out;
 #define RVN_DISPATCH(BN_)                                                                                              \
   if (!a_mn && !b_mn) return rvn::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream); \
   if (!a_mn && b_mn) return rvn::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);   \
   if (a_mn && b_mn) return rvn::launch<BN_, true, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);     \
   return rvn::launch<BN_, true, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);
   if (block_n == 256) { RVN_DISPATCH(256) }
+  if (block_n == 192) { RVN_DISPATCH(192) }
   RVN_DISPATCH(128)
 #undef RVN_DISPATCH
 }

@@ -205,6 +205,7 @@ class DistTransport:
         self.recv_stream = {FORWARD: None, BACKWARD: None}
         self.bytes_out = 0
         self.rings = None
+        self.just_in_time = os.environ.get('RAVNEST_P2P_JIT', '1') != '0'
 
     # ------------------------------------------------------------------ lifecycle
     def start(self) -> None:
@@ -241,7 +242,9 @@ class DistTransport:
     def send(self, lane: str, message: Dict[str, Any]) -> None:
         ev = None
         if self.cuda:
-            ev = torch.cuda.Event()
+            # blocking-sync event: the lane's sender thread SLEEPS on it until the producing kernels have finished (see
+            # _sender_loop: NCCL kernels are only launched once the payload exists)
+            ev = torch.cuda.Event(blocking=True)
             ev.record(torch.cuda.current_stream(self.device))
         with self._pending_cv:
             self._pending += 1
@@ -265,6 +268,14 @@ class DistTransport:
             try:
                 bag: List[torch.Tensor] = []
                 skeleton = _split_tensors(message, bag)
+                if bag and ev is not None and self.just_in_time:
+                    # Just-in-time rendezvous.  The host runs far ahead of the GPU (a whole stage step is one graph launch), so a
+                    # header sent at enqueue time makes the receiver launch its ncclRecv kernel milliseconds before the data exists:
+                    # that kernel then sits on the peer's SMs spinning (measured: 3.6 - 4.6 ms of resident ncclDevKernel_SendRecv per
+                    # 5 ms BERT step, 10 ms per 12.7 ms ResNet step, and every concurrent GEMM / BN kernel 20 - 28 % slower).  Waiting
+                    # for the producer's event HERE (this thread sleeps, the scheduler thread is not involved) keeps both NCCL
+                    # kernels down to the transfer itself.
+                    ev.synchronize()
                 raw = pickle.dumps(skeleton, protocol=pickle.HIGHEST_PROTOCOL)
                 # ONE fixed-size frame carries the length and (almost always) the whole pickled skeleton; only a header that
                 # does not fit is followed by a second message with the rest (was: a length message + a blob message per hop)

@@ -32,7 +32,7 @@ def _rand(*shape, scale=1.0):
 # ----------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 256, 128), (4096, 768, 768), (4096, 2304, 768), (300, 200, 72),
                                    (4096, 768, 3072), (1000, 30522, 768)])
-@pytest.mark.parametrize('block_n', [128, 256])
+@pytest.mark.parametrize('block_n', [128, 192, 256])
 def test_gemm_nt(M, N, K, block_n):
     torch.manual_seed(0)
     a, b = _rand(M, K), _rand(N, K, scale=0.05)
@@ -58,6 +58,25 @@ def test_gemm_wgrad_layout(M, N, K):
     a, b = _rand(K, M, scale=0.1), _rand(K, N, scale=0.1)
     out = _C().gemm(a, True, b, True, None, 0, None, False, 0)[0]
     assert _rel_err(out, a.float().t() @ b.float()) < 1e-2
+
+
+@pytest.mark.parametrize('M,N,K', [(768, 768, 4096), (2304, 768, 4096), (264, 200, 1032), (128, 3072, 512)])
+@pytest.mark.parametrize('block_n,split_k', [(0, 0), (128, 1), (128, 4), (192, 2), (256, 3), (128, 8)])
+def test_gemm_wgrad_accumulate_split_k(M, N, K, block_n, split_k):
+    """G += A^T B through the TMA reduce-add epilogue (gradient accumulation into the flat bucket), with the K range split over CTAs."""
+    torch.manual_seed(5)
+    a, b = _rand(K, M, scale=0.1), _rand(K, N, scale=0.1)
+    g0 = _rand(M, N, scale=2.0)
+    g = g0.clone()
+    _C().gemm(a, True, b, True, None, 0, g, False, block_n, 2, g, None, None, 0, split_k)
+    ref = g0.float() + a.float().t() @ b.float()
+    assert _rel_err(g, ref) < 1.5e-2
+    # a strided view of a wider buffer (bucket rows) accumulates in place too
+    wide = torch.zeros(M, N + 64, dtype=torch.bfloat16, device=DEV)
+    view = wide[:, 8:8 + N]
+    _C().gemm(a, True, b, True, None, 0, view, False, block_n, 2, view, None, None, 0, split_k)
+    assert _rel_err(view, a.float().t() @ b.float()) < 1.5e-2
+    assert float(wide[:, :8].abs().sum()) == 0 and float(wide[:, 8 + N:].abs().sum()) == 0
 
 
 @pytest.mark.parametrize('act,name', [(1, 'gelu'), (2, 'gelu_tanh'), (3, 'relu')])
