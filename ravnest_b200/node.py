@@ -66,6 +66,7 @@ class Node:
         self.labels_to_device = kwargs.get('labels_to_device', False)
         self.prefetch_h2d = bool(kwargs.get('prefetch_h2d', False))
         self.checkpoint_every = int(kwargs.get('checkpoint_every', 0) or 0)      # backward passes between automatic checkpoints
+        self.inference_timeout = float(kwargs.get('inference_timeout', 120.0))
         self._stop_lock, self._stopping, self._stopped = threading.Lock(), False, threading.Event()
         self._h2d_stream = None
         self.status = NodeStatus.IDLE
@@ -347,6 +348,9 @@ class Node:
             data = self.plan.root_payload(out, model_args, self.compression)
             self.transport.send(FORWARD, make_message(ActionTypes.NO_GRAD_FORWARD, -1, data, output_type=output_type))
         self.status = NodeStatus.IDLE
+        if output_type in (ActionTypes.ACCURACY, ActionTypes.PREDICTION):
+            # the leaf sends its result back up the backward lane (the reference's Trainer.pred returns None, trainer.py:113)
+            return self.pop_prediction(timeout=self.inference_timeout)
         return None
 
     def wait_for_backwards(self, timeout: Optional[float] = None) -> None:
@@ -504,16 +508,28 @@ class Node:
         self._score_validation(self._leaf_inference(msg))
 
     def accuracy(self, msg) -> None:
-        with self._prediction_cv:
-            self._predictions.append(self._score_accuracy(self._leaf_inference(msg)))
-            self._prediction_cv.notify_all()
+        self._publish_inference(self._score_accuracy(self._leaf_inference(msg)))
 
     def prediction(self, msg) -> None:
-        """Store raw outputs of an inference pass (the reference's handler is broken, node.py:683-690)."""
-        out = self._leaf_inference(msg)
+        """Raw outputs of an inference pass (the reference's handler is broken, node.py:683-690)."""
+        self._publish_inference(_to_device(self._leaf_inference(msg), 'cpu'))
+
+    def _publish_inference(self, result) -> None:
+        """Leaf: keep the result (``pop_prediction``) and send it to the root, which is where ``Trainer.pred`` waits for it."""
         with self._prediction_cv:
-            self._predictions.append(_to_device(out, 'cpu'))
+            self._predictions.append(result)
             self._prediction_cv.notify_all()
+        if self.node_type == NodeTypes.LEAF:
+            self.transport.send(BACKWARD, make_message(ActionTypes.INFERENCE_RESULT, -1, {'result': result}))
+
+    def inference_result(self, msg) -> None:
+        """Backward-lane relay of an inference result: stems pass it on, the root hands it to the waiting caller."""
+        if self.node_type == NodeTypes.ROOT:
+            with self._prediction_cv:
+                self._predictions.append(msg['data']['result'])
+                self._prediction_cv.notify_all()
+        else:
+            self.transport.send(BACKWARD, make_message(ActionTypes.INFERENCE_RESULT, -1, msg['data']))
 
     def pop_prediction(self, timeout: Optional[float] = None):
         with self._prediction_cv:

@@ -52,7 +52,7 @@ struct FwdSmem {
   static constexpr int P_OFF = 3 * FM_TILE_BYTES;
   static constexpr int BAR_OFF = 5 * FM_TILE_BYTES;
   static constexpr int XCHG_OFF = BAR_OFF + 128;
-  static constexpr int TOTAL = XCHG_OFF + 2048 + 1024;
+  static constexpr int TOTAL = XCHG_OFF + 2048 + 64 + 1024;
 };
 
 constexpr int FM_SOFTMAX_THREADS = 256;      // 8 warps: thread = (query row, key half); warp w -> TMEM lanes 32*(w%4), half w/4
@@ -78,6 +78,7 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float* xchg = reinterpret_cast<float*>(smem + FwdSmem::XCHG_OFF);      // [2][128] per-half row maxima / sums
   float* kb_s = xchg + 256;                                               // [2][128] additive key bias (log2 domain) of tile j / j+1
+  int* kb_any = reinterpret_cast<int*>(kb_s + 256);                       // [2][4] "this tile has a non-zero bias", one word per staging warp
 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * FM_BLOCK;
@@ -175,10 +176,15 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
     // dropout groups: 8 consecutive keys of one (batch, head, query) row
     const unsigned long long drow = (static_cast<unsigned long long>(blockIdx.y) * p.S + q) * ((p.S + 7) / 8);
     // additive key bias of a tile, staged in smem once per tile: user padding bias (log2 domain) and -inf for keys >= S
+    // ... and a per-tile flag: tiles whose keys all carry a zero bias (no padding in them — with padding at the end of the sequence
+    // that is every tile but the last one or two) take the bias-free fast path of the softmax
     auto stage_bias = [&](int tile) {
       if (half == 0) {
         const int k = tile * FM_BLOCK + r;
-        kb_s[(tile & 1) * 128 + r] = k >= p.S ? -INFINITY : (kb != nullptr ? kb[k] * LOG2E : 0.f);
+        const float v = k >= p.S ? -INFINITY : (kb != nullptr ? kb[k] * LOG2E : 0.f);
+        kb_s[(tile & 1) * 128 + r] = v;
+        const int any = __any_sync(0xffffffffu, v != 0.f);
+        if (lane_id() == 0) kb_any[(tile & 1) * 4 + (warp & 3)] = any;
       }
     };
     stage_bias(0);
@@ -186,7 +192,8 @@ rvn_fmha_fwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const FmhaPara
     for (int j = 0; j < n_tiles; ++j) {
       const uint32_t ph = j & 1;
       const int kbase = j * FM_BLOCK + half * 64;    // first key handled by this thread
-      const bool biased = kb != nullptr || (j * FM_BLOCK + FM_BLOCK > p.S);
+      const int* anyp = kb_any + (j & 1) * 4;
+      const bool biased = (anyp[0] | anyp[1] | anyp[2] | anyp[3]) != 0;
       const bool diag = p.causal && (j * FM_BLOCK + FM_BLOCK - 1 > q0);
       const bool edge = biased || diag;
       const float* kbt = kb_s + (j & 1) * 128 + half * 64;
@@ -359,7 +366,7 @@ struct BwdSmem {
   static constexpr int DS_OFF = 6 * FM_TILE_BYTES;
   static constexpr int DQ_OFF = 8 * FM_TILE_BYTES;
   static constexpr int BAR_OFF = 10 * FM_TILE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 512 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 128 + 512 + 64 + 1024;
 };
 
 __global__ void __launch_bounds__(FM_THREADS, 1)
@@ -468,13 +475,17 @@ rvn_fmha_bwd_tcgen05(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     if (use_drop) drng.init(p.rng, p.dropout_p);
     const int kbase = k0 + half * 64;
     float* kb_s = reinterpret_cast<float*>(smem + BwdSmem::BAR_OFF + 128);      // [128] key bias of this CTA's kv tile
+    int* kb_any = reinterpret_cast<int*>(kb_s + 128);                           // [4] non-zero bias seen by staging warp w
     if (half == 0) {
       const int k = k0 + r;
-      kb_s[r] = k >= p.S ? -INFINITY : (kb != nullptr ? kb[k] * LOG2E : 0.f);
+      const float v = k >= p.S ? -INFINITY : (kb != nullptr ? kb[k] * LOG2E : 0.f);
+      kb_s[r] = v;
+      const int any = __any_sync(0xffffffffu, v != 0.f);
+      if (lane_id() == 0) kb_any[warp & 3] = any;
     }
     named_bar_sync(1, FM_SOFTMAX_THREADS);
     const float* kbt = kb_s + half * 64;
-    const bool biased = kb != nullptr || (k0 + FM_BLOCK > p.S);
+    const bool biased = (kb_any[0] | kb_any[1] | kb_any[2] | kb_any[3]) != 0;     // no padded key in this kv tile: bias-free fast path
     int it = 0;
     for (int i = i_first; i < n_q_tiles; ++i, ++it) {
       const uint32_t ph = it & 1;

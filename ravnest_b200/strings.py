@@ -30,6 +30,7 @@ class ActionTypes(object):
     # control-plane extensions (never seen by reference peers)
     SHUTDOWN = "shutdown"
     CHECKPOINT = "checkpoint"
+    INFERENCE_RESULT = "inference_result"      # leaf -> root on the backward lane: what ``Trainer.pred`` returns
 
 
 class BufferStatus(object):
@@ -58,5 +59,6 @@ ACTION_CODES = {
     ActionTypes.SHUTDOWN: 9,
     ActionTypes.CHECKPOINT: 10,
     ActionTypes.ROOT_FORWARD: 11,
+    ActionTypes.INFERENCE_RESULT: 12,
 }
 CODE_ACTIONS = {v: k for k, v in ACTION_CODES.items()}

@@ -8,7 +8,8 @@ Deliberate differences:
   * ``prelim_checks`` on stem/leaf blocks on an event and RETURNS ``False`` when the pipeline has
     been shut down, instead of spinning forever in ``while True: time.sleep(0)`` (:54-57);
   * the dtype handling of non-tensor batches is fixed (the reference's branch is inverted, :79-83);
-  * ``pred`` returns the prediction (the reference returns ``None``, :113).
+  * ``pred`` returns the prediction on the root — the leaf's result travels back up the backward lane
+    (``ActionTypes.INFERENCE_RESULT``); the reference returns ``None`` (:113).
 """
 import time
 

@@ -208,9 +208,11 @@ def test_three_node_cnn_trains_over_grpc_and_fuses(workdir, free_ports):
     probe = x[:16]
     with torch.no_grad():
         expect = full(probe)
-    trainer.pred(probe)
+    got = trainer.pred(probe)                       # the root gets the leaf's answer back (the reference returns None here)
+    assert torch.equal(got, expect.argmax(dim=-1))
     assert torch.equal(leaf.pop_prediction(timeout=20), expect.argmax(dim=-1))
-    root.no_grad_forward_compute(tensors=probe, output_type='prediction')
+    raw = root.no_grad_forward_compute(tensors=probe, output_type='prediction')
+    assert torch.allclose(raw, expect, atol=1e-5)
     assert torch.allclose(leaf.pop_prediction(timeout=20), expect, atol=1e-5)
     # heartbeat + latest-weights service answer on the control plane
     assert root.transport.ping(('127.0.0.1', ports[1]))
