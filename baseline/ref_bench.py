@@ -33,6 +33,26 @@ REF = os.path.join(HERE, '_ref')
 SHIMS = os.path.join(HERE, 'shims')
 
 
+def _reap():
+    """The reference spawns a Manager process and a gRPC server process per node as daemons and never joins them; this harness leaves
+    through os._exit (daemon threads of the reference spin forever), which skips multiprocessing's atexit cleanup — so kill every
+    descendant explicitly, or they outlive the benchmark holding the GPU and the stdout pipe."""
+    try:
+        import psutil
+        for child in psutil.Process().children(recursive=True):
+            try:
+                child.kill()
+            except psutil.Error:
+                pass
+    except Exception:
+        pass
+
+
+def _leave(code=0):
+    _reap()
+    os._exit(code)
+
+
 def unavailable(why):
     print(json.dumps({'impl': 'reference', 'unavailable': why}), flush=True)
     return 0
@@ -239,9 +259,7 @@ def run(args, datasets, ClockSampler):
                 why = open(marks[0]).read() if marks else 'no result within RVN_REF_TIMEOUT'
                 if rank == 0:
                     emit({'impl': 'reference', 'unavailable': 'reference run failed: {} (logs: {})'.format(why, workdir)})
-                if helper is not None:
-                    helper.kill()
-                os._exit(0)
+                _leave(0)
 
     for stale in [f for f in os.listdir(workdir) if f.startswith('FAILED_')] if rank == 0 else []:
         os.remove(os.path.join(workdir, stale))
@@ -256,7 +274,7 @@ def run(args, datasets, ClockSampler):
         with open(os.path.join(workdir, 'FAILED_{}'.format(rank)), 'w') as fh:
             fh.write('provider {}: {!r}'.format(rank, err))
         time.sleep(5)                                  # the watchdog reports and exits
-        os._exit(0)
+        _leave(0)
     if rank == 0 and result is not None:
         emit(result)
     if helper is not None:
@@ -265,7 +283,7 @@ def run(args, datasets, ClockSampler):
         except subprocess.TimeoutExpired:
             helper.kill()
     # the reference spawns a Manager and a gRPC server process per node and never joins them
-    os._exit(0)
+    _leave(0)
 
 
 def _provider(args, datasets, ClockSampler, rank, local_rank, n_nodes, stages, replicas, master_port, device, log):
