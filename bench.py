@@ -33,6 +33,8 @@ def parse():
     ap.add_argument('--model', default='bert', choices=['bert', 'resnet50', 'inception', 'sorter', 'cnn'])
     ap.add_argument('--ref-cpu', action='store_true', help='reference arm on CPU (plumbing check of the arm itself; not a benchmark)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--also', default=None, help='comma-separated further models timed after --model in the same job; their results are nested '
+                    'under "also" (default: resnet50 next to bert — the two halves of the BASELINE.json headline; "" for none)')
     ap.add_argument('--update-frequency', type=int, default=None)
     ap.add_argument('--topology', default=None, help='SxR override (stages x replicas), e.g. 1x2 to exercise pure DP')
     ap.add_argument('--batch', type=int, default=0, help='per-replica batch override (sweeps; the result is marked as a non-headline config)')
@@ -190,6 +192,9 @@ class SyntheticImages:
 
 def main():
     args = parse()
+    if args.also is None:
+        args.also = 'resnet50' if (args.model == 'bert' and args.impl != 'reference' and not args.layers and not args.batch
+                                   and not args.topology and not args.diagnose) else ''
     if args.impl == 'reference':
         return run_reference(args)
     import torch
@@ -229,11 +234,47 @@ def main():
     torch.backends.cudnn.deterministic = False
     torch.backends.cudnn.benchmark = True
 
+    results = {}
+    models_to_run = [args.model] + [m for m in (args.also.split(',') if args.also else []) if m and m != args.model]
+    for i, name in enumerate(models_to_run):
+        sub = argparse.Namespace(**vars(args))
+        sub.model = name
+        if i > 0:                       # secondary models: same K / W, no per-model overrides
+            sub.update_frequency = None
+            sub.topology = sub.proportions = None
+            sub.batch = 0
+            sub.diagnose = 0
+        results[name] = bench_one(sub, rank, world, dev, gloo, milestone)
+    if rank == 0:
+        result = results[args.model]
+        extra = {k: v for k, v in results.items() if k != args.model and v is not None}
+        if extra:
+            result['also'] = extra      # the other half of the headline metric (BASELINE.json: ResNet-50 images/s AND BERT samples/s)
+        print(json.dumps(result), flush=True)
+    faulthandler.cancel_dump_traceback_later()
+    # the measurements are out: whatever happens during teardown (a peer that is already gone, a slow communicator destroy)
+    # must neither hang the box nor turn a finished run into a failure
+    killer = threading.Timer(90.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    if world > 1:
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=gloo)
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_one(args, rank, world, dev, gloo, milestone):
+    """Plan, build and time ONE model on the already initialised process group; returns the result dict on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import ravnest_b200 as rv
+    fused = args.impl == 'native'
     stages, replicas = topology_for(args.model, world)
     if args.topology:
         stages, replicas = (int(v) for v in args.topology.lower().split('x'))
         assert stages * replicas == world
-    home = os.environ.get('RAVNEST_HOME') or os.path.join(tempfile.gettempdir(), 'rvn_bench_{}'.format(os.environ.get('MASTER_PORT', '0')))
+    home = os.path.join(os.environ.get('RAVNEST_BENCH_HOME') or os.path.join(tempfile.gettempdir(), 'rvn_bench_{}'.format(os.environ.get('MASTER_PORT', '0'))), args.model)
     os.environ['RAVNEST_HOME'] = home
     model, ex_args, ex_kwargs, batch = build_model(args)
     if args.batch:
@@ -363,7 +404,9 @@ def main():
     node.tracer.resolve(block=True)
     exposed0 = node.tracer.totals_ms.get('exposed_comm', 0.0)
     busy0 = sum(v for k, v in node.tracer.totals_ms.items() if k != 'exposed_comm')
+    updates0 = node.compute_session.n_updates
     dev_ms, dev_wall = timed(args.steps, 'dev', False)
+    updates_in_window = node.compute_session.n_updates - updates0
     clocks = sampler.summary()
     node.tracer.resolve(block=True)
     own_exposed = (node.tracer.totals_ms.get('exposed_comm', 0.0) - exposed0) / args.steps
@@ -393,6 +436,20 @@ def main():
         dist.all_gather_object(last_losses, mine, group=gloo)
     else:
         last_losses = [mine]
+    # data-parallel replicas of a stage must hold identical master weights after the timed steps: proof that the fused all-reduce +
+    # optimizer kernel (K1) did its job on every replica (max |w_i - w_j| over the stage's DP group, worst stage reported)
+    replica_diff = None
+    if node.dp_group is not None:
+        with node.on_compute_stream():
+            m = cs.store.master
+            hi, lo = m.clone(), m.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=node.dp_group)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=node.dp_group)
+            worst = torch.stack([(hi - lo).abs().max(), m.abs().max()])
+        torch.cuda.synchronize(dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        replica_diff = {'max_abs_diff': float(worst[0]), 'max_abs_weight': float(worst[1]), 'updates_checked': cs.n_updates}
+        del hi, lo
     launches = count_launches(node, feed, pool_dev, driver, sync, Labels) if rank == 0 or world > 1 else None
     if args.diagnose:
         diagnose(args, node, feed, pool_dev, driver, sync, Labels, rank, world)
@@ -414,18 +471,14 @@ def main():
             'gpu_launches_detail': launches, 'wall_ms_per_step': dev_wall / args.steps,
             'exposed_comm_ms_per_step': exposed_ms, 'stage_busy_ms_per_rank': busy_all,
             'last_loss_per_rank': [None if v is None else round(v, 4) for v in last_losses],
+            'optimizer_updates_in_window': updates_in_window, 'replica_weights': replica_diff,
         }
+        if replica_diff is not None and replica_diff['max_abs_diff'] > 1e-6 * max(1.0, replica_diff['max_abs_weight']):
+            result['invalid'] = 'data-parallel replicas diverged: {}'.format(replica_diff)
         if args.layers:
             result['invalid'] = 'debug run with --layers'
         if args.batch:
             result['invalid'] = 'sweep run with --batch (not the BASELINE.json batch size)'
-        print(json.dumps(result), flush=True)
-    faulthandler.cancel_dump_traceback_later()
-    # the measurements are out: whatever happens during teardown (a peer that is already gone, a slow communicator destroy)
-    # must neither hang the box nor turn a finished run into a failure
-    killer = threading.Timer(90.0, lambda: os._exit(0))
-    killer.daemon = True
-    killer.start()
     sync()
     if driver:
         node.stop()
@@ -433,8 +486,7 @@ def main():
     time.sleep(0.2)
     if world > 1:
         dist.barrier(group=gloo)
-        dist.destroy_process_group()
-    return 0
+    return result
 
 
 def diagnose(args, node, feed, pool, driver, sync, Labels, rank, world):
