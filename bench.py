@@ -441,6 +441,7 @@ def bench_one(args, rank, world, dev, gloo, milestone):
     replica_diff = None
     if node.dp_group is not None:
         with node.on_compute_stream():
+            cs.sync_master()                    # two-shot K1 keeps the fp32 master sharded over the replicas
             m = cs.store.master
             hi, lo = m.clone(), m.clone()
             dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=node.dp_group)

@@ -130,6 +130,12 @@ class Compute:
                 self.store.zero_grad()
         self.n_updates += 1
 
+    def sync_master(self) -> None:
+        """Make the WHOLE fp32 master (and optimizer moments) current on this rank.  No-op except with the two-shot fused optimizer,
+        which keeps them sharded over the stage's data-parallel replicas (``parallel/fused_optim.py``)."""
+        if self._fused is not None and hasattr(self._fused, 'sync_master'):
+            self._fused.sync_master()
+
     # ------------------------------------------------------------------ RNG replay
     def _rng_capture(self):
         cpu = torch.get_rng_state()
@@ -405,6 +411,7 @@ class Compute:
 
     def latest_weights(self, first: Optional[str] = None, last: Optional[str] = None) -> Dict[str, torch.Tensor]:
         """Master copy of parameters ``first..last`` (served by get_latest_weights, endpoints.py:145)."""
+        self.sync_master()
         names = self.store.names
         i = names.index(first) if first in names else 0
         j = names.index(last) if last in names else len(names) - 1

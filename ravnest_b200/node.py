@@ -545,6 +545,7 @@ class Node:
         cs.flush_losses()
         path = os.path.join(self.template_path, '{}.pt'.format(self.submod_file))
         with cs.lock, self.on_compute_stream():
+            cs.sync_master()
             # save the MASTER weights (fp32 even when the stage computes in bf16): point the module's parameters at copies of
             # them for the duration of the pickle, then back at the live compute-dtype version (stage steps use their own
             # parameter dicts, never the module's attributes, so nothing running is disturbed)

@@ -75,6 +75,14 @@ int rvn_fused_update(const PeerPtrs* pp, const OptArgs* a, int kind, float* mast
 int rvn_fused_lamb(const PeerPtrs* pp, const OptArgs* a, float* master, float* m, float* v, void* w_out, int grad_is_bf16,
                    int out_is_bf16, const int* chunk_param, const long long* chunk_start, const long long* chunk_end, int n_chunks,
                    float* norms, int n_params, uint32_t epoch, uint32_t* done_counter, cudaStream_t stream);
+struct WeightPeers { void* w[8]; };
+struct NormPeers { const float* norms[8]; };
+int rvn_fused_twoshot_update(const PeerPtrs* pp, const WeightPeers* wp, const OptArgs* a, int kind, float* master, float* m, float* v,
+                             int grad_is_bf16, int out_is_bf16, size_t shard_begin, size_t shard_end, uint32_t epoch, uint32_t* done_counter,
+                             int num_sms, cudaStream_t stream);
+int rvn_fused_twoshot_lamb(const PeerPtrs* pp, const WeightPeers* wp, const NormPeers* np, const OptArgs* a, float* master, float* m, float* v,
+                           int grad_is_bf16, int out_is_bf16, const int* chunk_param, const long long* chunk_start, const long long* chunk_end,
+                           int n_chunks, float* norms, int n_params, uint32_t epoch, uint32_t* done_counter, cudaStream_t stream);
 int rvn_fused_param_average(const PeerPtrs* pp, float* master_out, void* w_out, int out_is_bf16, size_t n, uint32_t epoch,
                             uint32_t* done_counter, int num_sms, cudaStream_t stream);
 }
@@ -683,6 +691,50 @@ void fused_lamb(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t
         "fused_lamb");
 }
 
+// K1 v2 (two-shot): this rank reduces + updates only [shard_begin, shard_end) and pushes the new weights into every rank's landing buffer
+void fused_twoshot_update(int64_t kind, const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs,
+                          const std::vector<int64_t>& landing_ptrs, int64_t rank, const std::vector<double>& f,
+                          const std::vector<int64_t>& flags, torch::Tensor master, torch::Tensor m, torch::Tensor v, bool grad_is_bf16,
+                          bool out_is_bf16, int64_t shard_begin, int64_t shard_end, int64_t epoch, torch::Tensor done_counter) {
+  c10::cuda::CUDAGuard guard(master.device());
+  PeerPtrs pp = make_peers(grad_ptrs, signal_ptrs, rank);
+  TORCH_CHECK(landing_ptrs.size() == grad_ptrs.size() && landing_ptrs.size() <= 8, "one landing buffer per DP rank (<= 8)");
+  WeightPeers wp{};
+  for (size_t i = 0; i < landing_ptrs.size(); ++i) wp.w[i] = reinterpret_cast<void*>(landing_ptrs[i]);
+  OptArgs a = make_args(f, flags);
+  check(rvn_fused_twoshot_update(&pp, &wp, &a, static_cast<int>(kind), master.data_ptr<float>(),
+                                 m.defined() && m.numel() ? m.data_ptr<float>() : nullptr, v.defined() && v.numel() ? v.data_ptr<float>() : nullptr,
+                                 grad_is_bf16, out_is_bf16, static_cast<size_t>(shard_begin), static_cast<size_t>(shard_end),
+                                 static_cast<uint32_t>(epoch), reinterpret_cast<uint32_t*>(done_counter.data_ptr()), sm_count(), cur_stream()),
+        "fused_twoshot_update");
+}
+
+void fused_twoshot_lamb(const std::vector<int64_t>& grad_ptrs, const std::vector<int64_t>& signal_ptrs,
+                        const std::vector<int64_t>& landing_ptrs, const std::vector<int64_t>& norm_ptrs, int64_t rank,
+                        const std::vector<double>& f, const std::vector<int64_t>& flags, torch::Tensor master, torch::Tensor m,
+                        torch::Tensor v, bool grad_is_bf16, bool out_is_bf16, torch::Tensor chunk_param, torch::Tensor chunk_start,
+                        torch::Tensor chunk_end, int64_t first_chunk, int64_t n_chunks, torch::Tensor norms, int64_t epoch,
+                        torch::Tensor done_counter) {
+  c10::cuda::CUDAGuard guard(master.device());
+  PeerPtrs pp = make_peers(grad_ptrs, signal_ptrs, rank);
+  TORCH_CHECK(landing_ptrs.size() == grad_ptrs.size() && norm_ptrs.size() == grad_ptrs.size() && grad_ptrs.size() <= 8, "bad peer lists");
+  WeightPeers wp{};
+  NormPeers np{};
+  for (size_t i = 0; i < landing_ptrs.size(); ++i) {
+    wp.w[i] = reinterpret_cast<void*>(landing_ptrs[i]);
+    np.norms[i] = reinterpret_cast<const float*>(norm_ptrs[i]);
+  }
+  OptArgs a = make_args(f, flags);
+  TORCH_CHECK(first_chunk >= 0 && first_chunk + n_chunks <= chunk_param.numel(), "chunk range out of bounds");
+  check(rvn_fused_twoshot_lamb(&pp, &wp, &np, &a, master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), grad_is_bf16, out_is_bf16,
+                               chunk_param.data_ptr<int>() + first_chunk,
+                               reinterpret_cast<const long long*>(chunk_start.data_ptr<int64_t>()) + first_chunk,
+                               reinterpret_cast<const long long*>(chunk_end.data_ptr<int64_t>()) + first_chunk, static_cast<int>(n_chunks),
+                               norms.data_ptr<float>(), static_cast<int>(norms.numel() / 2), static_cast<uint32_t>(epoch),
+                               reinterpret_cast<uint32_t*>(done_counter.data_ptr()), cur_stream()),
+        "fused_twoshot_lamb");
+}
+
 void fused_param_average(const std::vector<int64_t>& src_ptrs, const std::vector<int64_t>& signal_ptrs, int64_t rank, torch::Tensor master_out,
                          torch::Tensor w_out, int64_t epoch, torch::Tensor done_counter) {
   c10::cuda::CUDAGuard guard(master_out.device());
@@ -722,5 +774,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("fmha_bwd", &fmha_bwd);
   m.def("fused_update", &fused_update);
   m.def("fused_lamb", &fused_lamb);
+  m.def("fused_twoshot_update", &fused_twoshot_update);
+  m.def("fused_twoshot_lamb", &fused_twoshot_lamb);
   m.def("fused_param_average", &fused_param_average);
 }

@@ -96,6 +96,8 @@ __device__ __forceinline__ void exit_barrier(const PeerPtrs& pp, int base, uint3
   }
 }
 
+__device__ __forceinline__ void exit_barrier_sys(const PeerPtrs& pp, int base, uint32_t epoch, uint32_t* done_counter);
+
 // ------------------------------------------------------------------------------------------------ gradient fetch
 template <typename G>
 __device__ __forceinline__ void load4(const G* p, size_t i, float (&f)[4]);
@@ -145,7 +147,7 @@ __device__ __forceinline__ void reduced_grad4(const PeerPtrs& pp, size_t i, floa
 // U vectors of 4 elements per thread (idx = i0 + u * step), ALL of one peer's loads issued before any is consumed: peer memory
 // is ~2.5 us away and is not cached in the local L2, so link bandwidth = bytes in flight / latency.  Measured on 2 GPUs with one
 // 8-byte load per thread per peer: 172 GB/s; U = 4 puts 148 x 512 x 32 B = 2.4 MB in flight per peer.
-constexpr int GRAD_U = 4;
+constexpr int GRAD_U = 8;
 template <typename G>
 __device__ __forceinline__ void reduced_grad_tile(const PeerPtrs& pp, size_t i0, size_t step, size_t end, float scale,
                                                   float (&g)[GRAD_U][4]) {
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(512) rvn_fused_allreduce_lamb1(PeerPtrs pp, Op
     atomicAdd(&norms[2 * param], a0);
     atomicAdd(&norms[2 * param + 1], a1);
   }
-  exit_barrier(pp, MAX_PEERS + 1, epoch, done_counter);
+  exit_barrier_sys(pp, MAX_PEERS + 1, epoch, done_counter);   // system scope: in two-shot mode the peers read these norms next
 }
 
 template <typename W>
@@ -332,6 +334,143 @@ __global__ void __launch_bounds__(512) rvn_fused_lamb2(OptArgs a, float* __restr
     store4<float>(master, i, w);
     store4<W>(w_out, i, w);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ two-shot variants (K1 v2)
+// One-shot (above): every rank pulls every peer's WHOLE gradient bucket ((N-1) x bucket over its links) and every rank redoes the
+// full optimizer update (whole master / m / v through HBM).  Two-shot: rank r owns the contiguous shard r of the flat bucket;
+//   shot 1 (reduce-scatter): pull only shard r of every peer's gradients,
+//   update only shard r of master / m / v (1/N of the optimizer's HBM traffic),
+//   shot 2 (all-gather): PUSH the new compute-dtype weights of shard r into every peer's landing buffer with posted P2P stores.
+// Per rank (N-1)/N x bucket crosses the link in each direction — at 8 replicas 8x less than one-shot — and the kernel is still ONE
+// launch with the same device-side barriers (entry: gradients complete everywhere; exit: every peer has finished reading my
+// gradients AND writing its shard into my landing buffer).
+struct WeightPeers {
+  void* w[MAX_PEERS];              // landing buffer (compute dtype, whole bucket) of every DP rank
+};
+
+// like exit_barrier, but every CTA publishes its P2P stores at system scope before it counts itself done
+__device__ __forceinline__ void exit_barrier_sys(const PeerPtrs& pp, int base, uint32_t epoch, uint32_t* done_counter) {
+  if (pp.n <= 1) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const uint32_t prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *done_counter = 0;
+      __threadfence_system();
+      for (int p = 0; p < pp.n; ++p) st_release_sys(pp.signal[p] + base + pp.rank, epoch);
+      for (int p = 0; p < pp.n; ++p)
+        while (ld_acquire_sys(pp.signal[pp.rank] + base + p) < epoch) {
+        }
+    }
+  }
+}
+
+template <typename G, typename W, int KIND>
+__global__ void __launch_bounds__(512) rvn_fused_twoshot_update(PeerPtrs pp, WeightPeers wp, OptArgs a, float* __restrict__ master,
+                                                                float* __restrict__ m, float* __restrict__ v, size_t shard_begin,
+                                                                size_t shard_end, uint32_t epoch, uint32_t* done_counter) {
+  cross_gpu_barrier(pp, 0, epoch);
+  const size_t step = static_cast<size_t>(blockDim.x) * 4;
+  const size_t tile = step * GRAD_U;
+  for (size_t base = shard_begin + static_cast<size_t>(blockIdx.x) * tile; base < shard_end; base += static_cast<size_t>(gridDim.x) * tile) {
+    const size_t i0 = base + threadIdx.x * 4;
+    float gt[GRAD_U][4];
+    reduced_grad_tile<G>(pp, i0, step, shard_end, a.grad_scale, gt);
+#pragma unroll
+    for (int u = 0; u < GRAD_U; ++u) {
+      const size_t i = i0 + u * step;
+      if (i >= shard_end) break;
+      float g[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = gt[u][j];
+      load4<float>(master, i, w);
+      if (KIND == 0) {
+        float mom[4];
+        if (a.momentum != 0.f) load4<float>(m, i, mom);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d = g[j] + a.weight_decay * w[j];
+          if (a.momentum != 0.f) {
+            mom[j] = a.first_step ? d : a.momentum * mom[j] + (1.f - a.dampening) * d;
+            d = a.nesterov ? d + a.momentum * mom[j] : mom[j];
+          }
+          w[j] -= a.lr * d;
+        }
+        if (a.momentum != 0.f) store4<float>(m, i, mom);
+      } else {
+        float m1[4], v1[4];
+        load4<float>(m, i, m1);
+        load4<float>(v, i, v1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float gj = g[j];
+          if (!a.decoupled_wd) gj += a.weight_decay * w[j];
+          else w[j] *= 1.f - a.lr * a.weight_decay;
+          m1[j] = a.beta1 * m1[j] + (1.f - a.beta1) * gj;
+          v1[j] = a.beta2 * v1[j] + (1.f - a.beta2) * gj * gj;
+          const float denom = sqrtf(v1[j]) / a.bias_c2 + a.eps;
+          w[j] -= (a.lr / a.bias_c1) * m1[j] / denom;
+        }
+        store4<float>(m, i, m1);
+        store4<float>(v, i, v1);
+      }
+      store4<float>(master, i, w);
+      for (int q = 0; q < pp.n; ++q) {                     // all-gather by posted stores, own copy first, then rank+1, ...
+        int t = pp.rank + q;
+        if (t >= pp.n) t -= pp.n;
+        store4<W>(static_cast<W*>(wp.w[t]), i, w);
+      }
+    }
+  }
+  exit_barrier_sys(pp, MAX_PEERS + 1, epoch, done_counter);
+}
+
+// LAMB two-shot, phase 1: like rvn_fused_allreduce_lamb1 but only over the chunks of this rank's shard (chunk arrays are passed
+// already offset); the partial squared norms of the shard land in THIS rank's symmetric norm buffer.
+// phase 2: trust ratio from the sum of every rank's partial norms (P2P loads of 2 floats per parameter), update of the shard,
+// push of the new weights into every peer's landing buffer.
+struct NormPeers {
+  const float* norms[MAX_PEERS];
+};
+
+template <typename W>
+__global__ void __launch_bounds__(512) rvn_fused_twoshot_lamb2(PeerPtrs pp, WeightPeers wp, NormPeers np, OptArgs a,
+                                                               float* __restrict__ master, const float* __restrict__ m,
+                                                               const float* __restrict__ v, const int* __restrict__ chunk_param,
+                                                               const long long* __restrict__ chunk_start,
+                                                               const long long* __restrict__ chunk_end, uint32_t epoch,
+                                                               uint32_t* done_counter) {
+  const int param = chunk_param[blockIdx.x];
+  const size_t s = chunk_start[blockIdx.x], e = chunk_end[blockIdx.x];
+  float wsq = 0.f, usq = 0.f;
+  for (int q = 0; q < pp.n; ++q) {
+    wsq += np.norms[q][2 * param];
+    usq += np.norms[q][2 * param + 1];
+  }
+  const float wn = fminf(sqrtf(wsq), a.clamp_value);
+  const float un = sqrtf(usq);
+  const float trust = (a.lamb_adam_mode || wn == 0.f || un == 0.f) ? 1.f : wn / un;
+  for (size_t i = s + threadIdx.x * 4; i < e; i += blockDim.x * 4) {
+    float w[4], m1[4], v1[4];
+    load4<float>(master, i, w);
+    load4<float>(m, i, m1);
+    load4<float>(v, i, v1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float u = m1[j] / (sqrtf(v1[j]) + a.eps) + a.weight_decay * w[j];
+      w[j] -= a.lr * trust * u;
+    }
+    store4<float>(master, i, w);
+    for (int q = 0; q < pp.n; ++q) {
+      int t = pp.rank + q;
+      if (t >= pp.n) t -= pp.n;
+      store4<W>(static_cast<W*>(wp.w[t]), i, w);
+    }
+  }
+  exit_barrier_sys(pp, 2 * MAX_PEERS + 2, epoch, done_counter);
 }
 
 // parameter averaging (reference semantics of parallel_ring_reduce): master = mean over replicas of master_peer
@@ -409,6 +548,56 @@ extern "C" int rvn_fused_lamb(const PeerPtrs* pp, const OptArgs* a, float* maste
   else
     rvn::rvn_fused_lamb2<float><<<n_chunks, 512, 0, stream>>>(*a, master, m, v, static_cast<float*>(w_out), chunk_param, chunk_start,
                                                             chunk_end, norms);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+
+using rvn::NormPeers;
+using rvn::WeightPeers;
+
+// two-shot SGD / Adam(W): rank owns [shard_begin, shard_end) of the flat bucket; wp = landing buffers (compute dtype) of all ranks
+extern "C" int rvn_fused_twoshot_update(const PeerPtrs* pp, const WeightPeers* wp, const OptArgs* a, int kind, float* master, float* m,
+                                        float* v, int grad_is_bf16, int out_is_bf16, size_t shard_begin, size_t shard_end, uint32_t epoch,
+                                        uint32_t* done_counter, int num_sms, cudaStream_t stream) {
+  int grid = grid_for(shard_end - shard_begin, num_sms);
+  if (grid > num_sms) grid = num_sms;
+#define RVN_LAUNCH2(G, W, K)                                                                                           \
+  rvn::rvn_fused_twoshot_update<G, W, K><<<grid, 512, 0, stream>>>(*pp, *wp, *a, master, m, v, shard_begin, shard_end, epoch, done_counter)
+  if (kind == 0) {
+    if (grad_is_bf16 && out_is_bf16) RVN_LAUNCH2(__nv_bfloat16, __nv_bfloat16, 0);
+    else if (!grad_is_bf16 && !out_is_bf16) RVN_LAUNCH2(float, float, 0);
+    else if (grad_is_bf16) RVN_LAUNCH2(__nv_bfloat16, float, 0);
+    else RVN_LAUNCH2(float, __nv_bfloat16, 0);
+  } else {
+    if (grad_is_bf16 && out_is_bf16) RVN_LAUNCH2(__nv_bfloat16, __nv_bfloat16, 1);
+    else if (!grad_is_bf16 && !out_is_bf16) RVN_LAUNCH2(float, float, 1);
+    else if (grad_is_bf16) RVN_LAUNCH2(__nv_bfloat16, float, 1);
+    else RVN_LAUNCH2(float, __nv_bfloat16, 1);
+  }
+#undef RVN_LAUNCH2
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// two-shot LAMB over the n_chunks chunks of this rank's shard (chunk arrays already offset to the shard's first chunk);
+// norms = this rank's symmetric partial-norm buffer (zeroed here), np = every rank's
+extern "C" int rvn_fused_twoshot_lamb(const PeerPtrs* pp, const WeightPeers* wp, const NormPeers* np, const OptArgs* a, float* master,
+                                      float* m, float* v, int grad_is_bf16, int out_is_bf16, const int* chunk_param,
+                                      const long long* chunk_start, const long long* chunk_end, int n_chunks, float* norms, int n_params,
+                                      uint32_t epoch, uint32_t* done_counter, cudaStream_t stream) {
+  cudaMemsetAsync(norms, 0, sizeof(float) * 2 * n_params, stream);
+  if (n_chunks <= 0) return 2;
+  if (grad_is_bf16)
+    rvn::rvn_fused_allreduce_lamb1<__nv_bfloat16><<<n_chunks, 512, 0, stream>>>(*pp, *a, master, m, v, chunk_param, chunk_start,
+                                                                              chunk_end, norms, epoch, done_counter);
+  else
+    rvn::rvn_fused_allreduce_lamb1<float><<<n_chunks, 512, 0, stream>>>(*pp, *a, master, m, v, chunk_param, chunk_start, chunk_end,
+                                                                      norms, epoch, done_counter);
+  if (out_is_bf16)
+    rvn::rvn_fused_twoshot_lamb2<__nv_bfloat16><<<n_chunks, 512, 0, stream>>>(*pp, *wp, *np, *a, master, m, v, chunk_param, chunk_start,
+                                                                            chunk_end, epoch, done_counter);
+  else
+    rvn::rvn_fused_twoshot_lamb2<float><<<n_chunks, 512, 0, stream>>>(*pp, *wp, *np, *a, master, m, v, chunk_param, chunk_start,
+                                                                    chunk_end, epoch, done_counter);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

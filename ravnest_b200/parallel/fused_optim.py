@@ -12,6 +12,7 @@ device-side flag barrier replaces NCCL.  ``average_parameters`` is the same tric
 periodic parameter averaging (``parallel_ring_reduce``).
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -50,18 +51,16 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
             p.pop(k, None)
         if p:
             raise TypeError('unsupported optimizer arguments for fused {}: {}'.format(kind, sorted(p)))
-        super().__init__(store.master_params, defaults)
         dev = store.device
         n = store.total
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev) if kind != 'sgd' or defaults['momentum'] != 0 else torch.zeros(0, device=dev)
-        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev) if kind != 'sgd' else torch.zeros(0, device=dev)
         self.steps = 0
-        self.done_counter = torch.zeros(4, dtype=torch.int32, device=dev)
         self.epoch = 0
         self.dp_group = dp_group
         self.average_grads = average_grads
         self.sync_grads = bool(average_grads if sync_grads is None else sync_grads)
-        self.grad_sym = self.sig_sym = self.avg_sym = None
+        self.grad_sym = self.sig_sym = self.avg_sym = self.land_sym = self.norm_sym = self.master_sym = None
+        self.two_shot = False
+        self._master_stale = False
         self.rank, self.world = 0, 1
         if dp_group is not None and dist.get_world_size(dp_group) > 1:
             from .symmetric import SymmetricBuffer
@@ -70,8 +69,57 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
             if self.sync_grads:
                 self.grad_sym = SymmetricBuffer(n, store.compute_dtype, dev, dp_group)
                 store.rebind_grad(self.grad_sym.tensor)
+                # K1 v2, two-shot: each rank reduces / updates only its shard and pushes the new weights to everybody's landing
+                # buffer — (N-1)/N of the bucket per direction instead of (N-1) x bucket inbound, and 1/N of the optimizer's HBM
+                # traffic.  Default from 3 replicas up (at 2 the link traffic is the same and one-shot has one barrier less);
+                # RAVNEST_K1_TWOSHOT=0/1 overrides.  The fp32 master lives in symmetric memory so that any rank can refresh the
+                # shards it does not own with one-sided peer copies (``sync_master``: checkpoints, saves, parameter averaging).
+                want = os.environ.get('RAVNEST_K1_TWOSHOT')
+                self.two_shot = (self.world >= 3) if want is None else (want == '1')
+                if self.two_shot:
+                    self.land_sym = SymmetricBuffer(n, store.compute_dtype, dev, dp_group)
+                    self.master_sym = SymmetricBuffer(n, torch.float32, dev, dp_group, zero=False)
+                    store.rebind_master(self.master_sym.tensor)
+                    dist.barrier(group=dp_group)
+                    per = (n // self.world + 63) // 64 * 64
+                    self.shards = [(min(n, r * per), min(n, (r + 1) * per)) for r in range(self.world)]
+                    self.shard = self.shards[self.rank]
+        super().__init__(store.master_params, defaults)
+        need_m = kind != 'sgd' or defaults['momentum'] != 0
+        need_v = kind != 'sgd'
+        self.m_sym = self.v_sym = None
+        if self.two_shot:                  # sharded moments are peer-readable too (state_dict gathers them one-sidedly)
+            from .symmetric import SymmetricBuffer
+            self.m_sym = SymmetricBuffer(n, torch.float32, dev, dp_group) if need_m else None
+            self.v_sym = SymmetricBuffer(n, torch.float32, dev, dp_group) if need_v else None
+        self.exp_avg = (self.m_sym.tensor if self.m_sym is not None else torch.zeros(n, dtype=torch.float32, device=dev)) if need_m else torch.zeros(0, device=dev)
+        self.exp_avg_sq = (self.v_sym.tensor if self.v_sym is not None else torch.zeros(n, dtype=torch.float32, device=dev)) if need_v else torch.zeros(0, device=dev)
+        self.done_counter = torch.zeros(4, dtype=torch.int32, device=dev)
         if kind == 'lamb':
             self._build_chunks()
+            if self.two_shot:
+                # shards follow chunk boundaries (chunks never straddle a parameter): contiguous chunk ranges of ~equal element count
+                from .symmetric import SymmetricBuffer
+                ends = self.chunk_end.cpu().tolist()
+                n_chunks = len(ends)
+                cut = [0]
+                for r in range(1, self.world):
+                    target = n * r // self.world
+                    cut.append(next((i for i, e in enumerate(ends) if e >= target), n_chunks - 1) + 1)
+                cut.append(n_chunks)
+                cut = [min(max(c, 0), n_chunks) for c in cut]
+                for i in range(1, len(cut)):
+                    cut[i] = max(cut[i], cut[i - 1])
+                self.chunk_range = (cut[self.rank], cut[self.rank + 1])
+                starts = self.chunk_start.cpu().tolist()
+                edge = [starts[c] if c < n_chunks else n for c in cut]
+                edge[0] = 0
+                self.shards = [(edge[r], edge[r + 1]) for r in range(self.world)]
+                self.shard = self.shards[self.rank]
+                self.norm_sym = SymmetricBuffer(2 * len(store.numels), torch.float32, dev, dp_group)
+                self.norms = self.norm_sym.tensor
+                if any(self.shards[r][1] <= self.shards[r][0] or cut[r + 1] <= cut[r] for r in range(self.world)):
+                    self.two_shot = False          # fewer chunks than replicas (toy models): every rank takes the same decision
         self._C = _ext.load()
 
     # ------------------------------------------------------------------ helpers
@@ -122,6 +170,22 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
         bf16_grad = st.grad.dtype == torch.bfloat16
 
         def writer(slot):
+            if self.two_shot:
+                out_bf16 = slot.flat.dtype == torch.bfloat16
+                if self.kind == 'lamb':
+                    c0, c1 = self.chunk_range
+                    self._C.fused_twoshot_lamb(grads, sigs, self.land_sym.ptrs, self.norm_sym.ptrs, rank, f, flags, st.master, self.exp_avg,
+                                               self.exp_avg_sq, bf16_grad, out_bf16, self.chunk_param, self.chunk_start, self.chunk_end,
+                                               c0, c1 - c0, self.norms, self.epoch, self.done_counter)
+                else:
+                    self._C.fused_twoshot_update(0 if self.kind == 'sgd' else 1, grads, sigs, self.land_sym.ptrs, rank, f, flags, st.master,
+                                                 self.exp_avg, self.exp_avg_sq, bf16_grad, out_bf16, self.shard[0], self.shard[1],
+                                                 self.epoch, self.done_counter)
+                # every rank's shard has landed (the kernel's exit barrier): adopt the gathered weights as the new version.  The
+                # fp32 master outside the own shard is refreshed from them lazily (``sync_master``) — nothing on the step path reads it
+                slot.flat.copy_(self.land_sym.tensor)
+                self._master_stale = True
+                return
             if self.kind == 'lamb':
                 self._C.fused_lamb(grads, sigs, rank, f, flags, st.master, self.exp_avg, self.exp_avg_sq, slot.flat, bf16_grad,
                                    self.chunk_param, self.chunk_start, self.chunk_end, self.norms, self.epoch, self.done_counter)
@@ -133,10 +197,27 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
         st.zero_grad()
 
     @torch.no_grad()
+    def sync_master(self):
+        """Two-shot mode keeps the fp32 master (and moments) sharded: a rank only updates its own shard.  Refresh the shards owned
+        by the peers with one-sided copies out of their symmetric master (race-free between two steps: the step kernel's exit
+        barrier means every peer has finished its update, and nobody starts the next one before this rank arrives at the entry
+        barrier).  Call on the stage's compute stream before anything reads the WHOLE master: checkpoint, save, averaging."""
+        if not (self.two_shot and self._master_stale):
+            return
+        for r, (s0, e0) in enumerate(self.shards):
+            if r != self.rank and e0 > s0:
+                self.store.master[s0:e0].copy_(self.master_sym.peer_tensor(r)[s0:e0])
+                for sym, buf in ((self.m_sym, self.exp_avg), (self.v_sym, self.exp_avg_sq)):
+                    if sym is not None:
+                        buf[s0:e0].copy_(sym.peer_tensor(r)[s0:e0])
+        self._master_stale = False
+
+    @torch.no_grad()
     def average_parameters(self, include_state: bool = False):
         """Parameter averaging across the DP group in one kernel (reference parallel_ring_reduce)."""
         if self.world <= 1:
             return
+        self.sync_master()
         from .symmetric import SymmetricBuffer
         st = self.store
         if self.avg_sym is None:
@@ -160,6 +241,7 @@ class FusedFlatOptimizer(torch.optim.Optimizer):
 
     # state_dict / load_state_dict keep the flat moments (checkpoint/resume)
     def state_dict(self):
+        self.sync_master()
         sd = super().state_dict()
         sd['flat'] = {'exp_avg': self.exp_avg.cpu(), 'exp_avg_sq': self.exp_avg_sq.cpu(), 'steps': self.steps}
         return sd

@@ -159,6 +159,16 @@ class ParamStore:
                 leaf.grad = g
         self._master_grad = None
 
+    def rebind_master(self, new_flat: torch.Tensor) -> None:
+        """Move the fp32 master into externally allocated (symmetric / peer-mapped) memory.  Must happen before an optimizer is
+        built over ``master_params``."""
+        assert new_flat.numel() == self.total and new_flat.dtype == self.master.dtype
+        with torch.no_grad():
+            new_flat.copy_(self.master)
+        self.master = new_flat
+        self.master_views = self.views_of(self.master)
+        self.master_params = [torch.nn.Parameter(v, requires_grad=True) for v in self.master_views]
+
     def zero_grad(self) -> None:
         self.grad.zero_()
 

@@ -30,6 +30,7 @@ def _snapshot(obj):
 def save_checkpoint(node, tag='latest'):
     cs = node.compute_session
     with cs.lock:
+        cs.sync_master()
         # everything is COPIED under the lock (``.to('cpu')`` aliases CPU tensors, ``optimizer.state_dict()`` returns live references):
         # the scheduler may update the stage while torch.save serialises
         state = {

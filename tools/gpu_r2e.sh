@@ -3,9 +3,9 @@
 N=${1:-4}
 mkdir -p gpurun_out
 export RVN_REF_TIMEOUT=600
-tr() { timeout -k 10 ${TMO:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 300)) "$@"; }
+trun() { timeout -k 10 ${TMO:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 300)) "$@"; }
 if [ "$2" = "tests" ]; then echo "== pytest gpu"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3; fi
-echo "== native n$N"; tr bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/e_native_n$N.log 2>&1; grep '^{"metric"' gpurun_out/e_native_n$N.log | tail -1 > gpurun_out/e_native_n$N.json
+echo "== native n$N"; trun bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/e_native_n$N.log 2>&1; grep '^{"metric"' gpurun_out/e_native_n$N.log | tail -1 > gpurun_out/e_native_n$N.json
 python - <<PY
 import json
 try:
@@ -17,5 +17,5 @@ except Exception as e:
     print('no json', e)
 PY
 grep -E "Error|Traceback|error" gpurun_out/e_native_n$N.log | head -5
-echo "== reference n$N"; tr bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/e_ref_n$N.log 2>&1; grep '"impl": "reference"' gpurun_out/e_ref_n$N.log | tail -1 > gpurun_out/e_ref_n$N.json; tail -c 700 gpurun_out/e_ref_n$N.json
+echo "== reference n$N"; trun bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/e_ref_n$N.log 2>&1; grep '"impl": "reference"' gpurun_out/e_ref_n$N.log | tail -1 > gpurun_out/e_ref_n$N.json; tail -c 700 gpurun_out/e_ref_n$N.json
 echo; nvidia-smi --query-gpu=memory.used --format=csv | tr '\n' ' '

@@ -67,9 +67,17 @@ def main():
             state = {'sgd': 1, 'adamw': 2, 'lamb': 2}[kind]
             hbm_bytes = n * (2 + 4 * 2 + state * 4 * 2 + 2 + (12 if kind == 'lamb' else 0))   # grad in, master rw, state rw, bf16 out (+ LAMB phase 2 re-read)
             nvl_bytes = n * 2 * (world - 1)                           # every peer bucket crosses the link once per GPU
+            two_shot = bool(getattr(fused, 'two_shot', False))
+            if two_shot:                # shard of the gradients in, shard of the weights out; optimizer traffic only for the own shard
+                nvl_bytes = n * 2 * (world - 1) / world
+                hbm_bytes = hbm_bytes / world + n * 2 * 2          # + landing buffer -> version slot copy
             roof_ms = max(hbm_bytes / HBM_GBS, nvl_bytes / NVL_GBS) / 1e6
-            row = dict(kernel='rvn_fused_allreduce_' + ('lamb1+lamb2' if kind == 'lamb' else 'update'), optimizer=kind, n_gpus=world, params=n, fused_ms=round(t_fused, 4), nccl_plus_torch_ms=round(t_lib, 4),
+            # the ALGORITHMIC floor whatever the implementation: reduce-scatter + sharded update + all-gather
+            algo_ms = max((n * (2 + 4 * 2 + state * 4 * 2) / world + n * 2) / HBM_GBS, n * 2 * (world - 1) / world / NVL_GBS) / 1e6
+            row = dict(kernel=('rvn_fused_twoshot_' if two_shot else 'rvn_fused_allreduce_') + ('lamb1+lamb2' if kind == 'lamb' else 'update'), mode='two-shot' if two_shot else 'one-shot',
+                       optimizer=kind, n_gpus=world, params=n, fused_ms=round(t_fused, 4), nccl_plus_torch_ms=round(t_lib, 4),
                        speedup=round(t_lib / t_fused, 2), roofline_ms=round(roof_ms, 4), fraction_of_roofline=round(roof_ms / t_fused, 3),
+                       algorithmic_floor_ms=round(algo_ms, 4), fraction_of_algorithmic_floor=round(algo_ms / t_fused, 3),
                        nvlink_gbs_per_gpu=round(nvl_bytes / t_fused / 1e6, 1), hbm_gbs=round(hbm_bytes / t_fused / 1e6, 1))
             rows.append(row)
             if rank == 0:
@@ -78,7 +86,7 @@ def main():
             torch.cuda.empty_cache()
     if rank == 0:
         os.makedirs('gpurun_out', exist_ok=True)
-        json.dump(rows, open('gpurun_out/k1_bench_n{}.json'.format(world), 'w'), indent=1)
+        json.dump(rows, open('gpurun_out/k1_bench_n{}_{}.json'.format(world, 'twoshot' if rows and rows[-1]['mode'] == 'two-shot' else 'oneshot'), 'w'), indent=1)
     dist.barrier()
     dist.destroy_process_group()
 
