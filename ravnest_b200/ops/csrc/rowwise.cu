@@ -232,7 +232,23 @@ __global__ void __launch_bounds__(256) rvn_layernorm_bwd_params(const __nv_bfloa
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dg[j] = 0.f; db[j] = 0.f; }
   if (c0 < H) {
-    for (int r = row0 + rl; r < row1; r += 8) {
+    int r = row0 + rl;
+    for (; r + 8 < row1; r += 16) {                     // two rows (four independent 16-byte loads) in flight per thread
+      bf16x8 a0, b0, a1, b1;
+      a0.load(dy + static_cast<size_t>(r) * H + c0);
+      b0.load(x + static_cast<size_t>(r) * H + c0);
+      a1.load(dy + static_cast<size_t>(r + 8) * H + c0);
+      b1.load(x + static_cast<size_t>(r + 8) * H + c0);
+      float g0[8], x0[8], g1[8], x1[8];
+      a0.to_float(g0); b0.to_float(x0); a1.to_float(g1); b1.to_float(x1);
+      const float m0 = mean_in[r], s0 = rstd_in[r], m1 = mean_in[r + 8], s1 = rstd_in[r + 8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dg[j] += g0[j] * (x0[j] - m0) * s0 + g1[j] * (x1[j] - m1) * s1;
+        db[j] += g0[j] + g1[j];
+      }
+    }
+    for (; r < row1; r += 8) {
       bf16x8 a, b;
       float g[8], xv[8];
       a.load(dy + static_cast<size_t>(r) * H + c0);
@@ -387,7 +403,21 @@ __global__ void __launch_bounds__(256) rvn_colsum(const __nv_bfloat16* __restric
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (c0 + 8 <= C) {
-    for (int r = row0 + rl; r < row1; r += 8) {
+    int r = row0 + rl;
+    // four independent 16-byte loads in flight per thread: the kernel is a pure stream and was latency-bound with one
+    // (8 us for the 6.3 MB of a 4096 x 768 gradient: 0.8 TB/s)
+    for (; r + 24 < row1; r += 32) {
+      bf16x8 a0, a1, a2, a3;
+      a0.load(x + static_cast<size_t>(r) * ld + c0);
+      a1.load(x + static_cast<size_t>(r + 8) * ld + c0);
+      a2.load(x + static_cast<size_t>(r + 16) * ld + c0);
+      a3.load(x + static_cast<size_t>(r + 24) * ld + c0);
+      float f0[8], f1[8], f2[8], f3[8];
+      a0.to_float(f0); a1.to_float(f1); a2.to_float(f2); a3.to_float(f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < row1; r += 8) {
       bf16x8 a;
       float f[8];
       a.load(x + static_cast<size_t>(r) * ld + c0);
@@ -482,7 +512,7 @@ extern "C" int rvn_column_sum(const void* x, int ld, float* ws, unsigned* counte
                               int num_sms, cudaStream_t stream) {
   const int col_blocks = (C + 255) / 256;
   int chunks = (2 * num_sms + col_blocks - 1) / col_blocks;
-  if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
+  if (chunks > (rows + 31) / 32) chunks = (rows + 31) / 32;
   if (chunks < 1) chunks = 1;
   const int rpb = (rows + chunks - 1) / chunks;
   dim3 grid(col_blocks, (rows + rpb - 1) / rpb);

@@ -301,9 +301,9 @@ def next_rng_snapshot(device) -> torch.Tensor:
 
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, heads, kbias, causal, dropout_p):
+    def forward(ctx, qkv, heads, kbias, causal, dropout_p, scale=None):
         qc = qkv.contiguous()
-        scale = 1.0 / math.sqrt(qc.shape[-1] // 3 // heads)
+        scale = float(scale) if scale is not None else 1.0 / math.sqrt(qc.shape[-1] // 3 // heads)
         rng = next_rng_snapshot(qc.device) if dropout_p > 0.0 else None
         out, lse = C().fmha_fwd(qc, heads, kbias, causal, scale, rng, dropout_p)
         calls['fmha_fwd'] += 1
@@ -316,7 +316,7 @@ class _Attention(torch.autograd.Function):
         qc, out, lse, kbias, rng = ctx.saved_tensors
         dqkv = C().fmha_bwd(qc, out, d_out.contiguous(), lse, ctx.heads, kbias, ctx.causal, ctx.scale, rng, ctx.dropout_p)
         calls['fmha_bwd'] += 1
-        return dqkv, None, None, None, None
+        return dqkv, None, None, None, None, None
 
 
 def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0):
@@ -332,7 +332,21 @@ def attention_qkv(qkv, heads, key_padding_mask=None, causal=False, dropout_p=0.0
             else:
                 kbias = torch.zeros(B, S, dtype=torch.float32, device=qkv.device).masked_fill_(~key_padding_mask.bool(), float('-inf'))
         return _Attention.apply(qkv, heads, kbias, causal, float(dropout_p))
-    # head dims other than 64: library SDPA (tracked in DESIGN.md as not-yet-native)
+    if D < 64 and D % 8 == 0 and qkv.dtype == torch.bfloat16:
+        # small heads (minGPT gpt-nano: 16; 32, 48): zero-pad every head to the kernel's 64 lanes.  q.k is unchanged by zero lanes
+        # (the softmax scale stays 1/sqrt(D)), the padded lanes of P.V are zero and are dropped again — the same tcgen05 kernel,
+        # no library attention on any of the five benchmark configs.
+        kbias = None
+        if key_padding_mask is not None:
+            if key_padding_mask.is_floating_point():
+                kbias = key_padding_mask.float().contiguous()
+            else:
+                kbias = torch.zeros(B, S, dtype=torch.float32, device=qkv.device).masked_fill_(~key_padding_mask.bool(), float('-inf'))
+        padded = F.pad(qkv.view(B, S, 3 * heads, D), (0, 64 - D)).view(B, S, 3 * heads * 64)
+        out = _Attention.apply(padded, heads, kbias, causal, float(dropout_p), 1.0 / math.sqrt(D))
+        calls['fmha_padded_head'] += 1
+        return out.view(B, S, heads, 64)[..., :D].reshape(B, S, H)
+    # other head dims: library SDPA
     q, k, v = qkv.view(B, S, 3, heads, D).permute(2, 0, 3, 1, 4)
     mask = None
     if key_padding_mask is not None:
@@ -548,8 +562,12 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     cin, cout = weight.shape[1], weight.shape[0]
     base_ok = (groups == 1 and x.dim() == 4 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
                and cin % 8 == 0 and cout % 8 == 0)
-    if base_ok and kh == 1 and kw == 1 and ph == 0 and pw == 0:
-        if sh != 1 or sw != 1:
+    strided = sh != 1 or sw != 1
+    if base_ok and kh == 1 and kw == 1 and ph == 0 and pw == 0 and not (strided and STRIDED_1X1_IMPLICIT and sh == sw and sh == 2):
+        # (strided pointwise convs — ResNet's three downsample projections — take the implicit-GEMM kernel below: its TMA box load
+        #  strides over the input pixels itself, where the sub-sampling slice here costs a strided copy forward and a fill + strided
+        #  scatter backward, ~100 us each on the 100 x 256 x 56 x 56 map)
+        if strided:
             x = x[:, :, ::sh, ::sw]
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
@@ -566,6 +584,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
 
 IMPLICIT_GEMM_CONV = True
 NATIVE_CONV_WGRAD = True
+STRIDED_1X1_IMPLICIT = True
 
 
 class _BatchNormAct(torch.autograd.Function):

@@ -238,7 +238,8 @@ def test_cross_entropy(rows, V):
 # ----------------------------------------------------------------------------------------------- convolution
 @pytest.mark.parametrize('N,C,H,W,K,R,stride,pad', [(4, 64, 56, 56, 64, 3, 1, 1), (8, 128, 28, 28, 128, 3, 1, 1), (3, 256, 14, 14, 256, 3, 1, 1),
                                                     (5, 512, 7, 7, 512, 3, 1, 1), (4, 128, 56, 56, 128, 3, 2, 1), (2, 48, 32, 32, 64, 5, 1, 2),
-                                                    (2, 64, 17, 17, 96, 3, 1, 0), (6, 64, 56, 56, 256, 1, 1, 0)])
+                                                    (2, 64, 17, 17, 96, 3, 1, 0), (6, 64, 56, 56, 256, 1, 1, 0), (4, 256, 56, 56, 512, 1, 2, 0),
+                                                    (2, 64, 9, 9, 64, 1, 2, 0)])
 def test_conv2d_implicit_gemm(N, C, H, W, K, R, stride, pad):
     from ravnest_b200 import ops
     from ravnest_b200.ops import native
@@ -416,6 +417,27 @@ def test_fmha_forward_backward(B, S, heads, causal, padded):
     assert _rel_err(qkv.grad[..., :H], ref_in.grad[..., :H]) < 3e-2              # dQ
     from ravnest_b200.ops import native
     assert native.calls['fmha_fwd'] > 0 and native.calls['fmha_bwd'] > 0
+
+
+@pytest.mark.parametrize('B,S,heads,D,causal', [(64, 11, 3, 16, True), (4, 130, 2, 32, False), (2, 64, 4, 48, True)])
+def test_fmha_small_heads_run_on_the_native_kernel(B, S, heads, D, causal):
+    """minGPT gpt-nano (3 heads x 16, S=11, causal) and other head dims < 64 are zero-padded onto the 64-lane tcgen05 kernel."""
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(10)
+    H = heads * D
+    qkv = _rand(B, S, 3 * H, scale=0.8).requires_grad_(True)
+    before = native.fallbacks['attention']
+    out = ops.attention_qkv(qkv, heads, None, causal, 0.0)
+    g = _rand(B, S, H)
+    out.backward(g)
+    ref_in = qkv.detach().float().requires_grad_(True)
+    ref = ops.reference_attention_qkv(ref_in, heads, None, causal, 0.0)
+    ref.backward(g.float())
+    assert out.shape == (B, S, H)
+    assert _rel_err(out, ref) < 2e-2
+    assert _rel_err(qkv.grad, ref_in.grad) < 3e-2
+    assert native.fallbacks['attention'] == before and native.calls['fmha_padded_head'] > 0
 
 
 def test_fmha_dropout_is_replayable_and_unbiased():
