@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--proportions', default=None, help='comma-separated parameter shares per stage (reference policy) instead of the compute-balanced plan')
     ap.add_argument('--prefetch-h2d', action='store_true', help='start the H2D copy of a batch at submit time on a copy stream (experimental)')
     ap.add_argument('--no-graphs', action='store_true', help='disable CUDA-graph capture of the stage step')
+    ap.add_argument('--rebalance', type=int, default=1, help='rounds of profile-guided re-planning before the warm-up (pipelines only): the plan '
+                    'is cut again with cost shares corrected by the measured per-stage step time')
     ap.add_argument('--layers', type=int, default=None, help='debug only: shrink the model (result marked invalid)')
     ap.add_argument('--diagnose', type=int, default=0, help='after the timed regions: profile this many steady-state steps on every rank and '
                     'write gpurun_out/diag_<model>_n<N>_rank<r>.txt (per-stream busy time, gaps, top kernels, native call counters)')
@@ -102,9 +104,11 @@ def topology_for(model, n):
     return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}[n]
 
 
-def build_model(args):
+def build_model(args, meta_only=False):
     import torch
     from ravnest_b200 import models
+    if meta_only:
+        return None, None, None, {'bert': 8, 'inception': 64, 'sorter': 64, 'cnn': 64}.get(args.model, 100)
     if args.model == 'bert':
         cfg = models.BertConfig()
         if args.layers:
@@ -276,22 +280,29 @@ def bench_one(args, rank, world, dev, gloo, milestone):
         assert stages * replicas == world
     home = os.path.join(os.environ.get('RAVNEST_BENCH_HOME') or os.path.join(tempfile.gettempdir(), 'rvn_bench_{}'.format(os.environ.get('MASTER_PORT', '0'))), args.model)
     os.environ['RAVNEST_HOME'] = home
-    model, ex_args, ex_kwargs, batch = build_model(args)
+    _, _, _, batch = build_model(args, meta_only=True)
     if args.batch:
         batch = args.batch
-    if rank == 0:
-        os.makedirs(home, exist_ok=True)
-        # stages are balanced by the planner's step-time estimate (balance='compute'), not by parameter bytes
-        props = [float(v) for v in args.proportions.split(',')] if args.proportions else None
-        ex_tensors = [t for t in list(ex_args) + list(ex_kwargs.values()) if hasattr(t, 'shape')]
-        cost_scale = batch / max(1, ex_tensors[0].shape[0])          # the plan is traced on a 2-sample example of the real shape
-        rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
-                      node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props,
-                      balance='params' if props else args.balance, cost_scale=cost_scale, plan_device=dev)
-    milestone('plan written' if rank == 0 else 'waiting for the plan')
-    if world > 1:
-        dist.barrier(group=gloo)
-    del model
+    user_props = [float(v) for v in args.proportions.split(',')] if args.proportions else None
+    plan_state = {'proportions': user_props, 'rounds': 0, 'history': []}
+
+    def plan(props, balance):
+        """(Re)write the cluster plan (rank 0) and wait for it (everybody)."""
+        if rank == 0:
+            os.makedirs(home, exist_ok=True)
+            model, ex_args, ex_kwargs, _ = build_model(args)
+            ex_tensors = [t for t in list(ex_args) + list(ex_kwargs.values()) if hasattr(t, 'shape')]
+            cost_scale = batch / max(1, ex_tensors[0].shape[0])          # the plan is traced on a 2-sample example of the real shape
+            rv.clusterize(model, example_args=ex_args, example_kwargs=ex_kwargs, topology={'stages': stages, 'replicas': replicas},
+                          node_configs=rv.default_gpu_configs(world), base_dir=home, proportions=props,
+                          balance=balance, cost_scale=cost_scale, plan_device=dev)
+            del model
+        milestone('plan written' if rank == 0 else 'waiting for the plan')
+        if world > 1:
+            dist.barrier(group=gloo)
+
+    # stages are balanced by measured step time (balance='measured'), not by parameter bytes, unless --proportions pins the reference policy
+    plan(user_props, 'params' if user_props else args.balance)
     milestone('building node')
 
     cfg = rv.load_node_json_configs('node_{}'.format(rank), base_dir=home)
@@ -355,9 +366,12 @@ def bench_one(args, rank, world, dev, gloo, milestone):
         def __len__(self):
             return 1 << 30
 
-    node = rv.Node(name='node_{}'.format(rank), criterion=criterion, labels=Labels(), device=dev, base_dir=home,
-                   reduce_factor=1 << 30, dp_mode='gradient', fused_optimizer=fused, loss_filename=None,
-                   recompute=False, use_cuda_graphs=not args.no_graphs, prefetch_h2d=args.prefetch_h2d, **node_kwargs)
+    def make_node():
+        return rv.Node(name='node_{}'.format(rank), criterion=criterion, labels=Labels(), device=dev, base_dir=home,
+                       reduce_factor=1 << 30, dp_mode='gradient', fused_optimizer=fused, loss_filename=None,
+                       recompute=False, use_cuda_graphs=not args.no_graphs, prefetch_h2d=args.prefetch_h2d, **node_kwargs)
+
+    node = make_node()
     driver = node.node_type in ('root', 'solo')
 
     def sync():
@@ -397,6 +411,45 @@ def bench_one(args, rank, world, dev, gloo, milestone):
     # timed region whatever W the caller picks
     prewarm = 12 + 2 * stages
     run(prewarm, 'dev', False)
+
+    def stage_busy(steps=8):
+        """Device time every stage spends in its own handlers per step (max over the replicas of a stage)."""
+        node.tracer.resolve(block=True)
+        e0 = node.tracer.totals_ms.get('exposed_comm', 0.0)
+        b0 = sum(v for k, v in node.tracer.totals_ms.items() if k != 'exposed_comm')
+        run(steps, 'dev', False)
+        node.tracer.resolve(block=True)
+        own = (sum(v for k, v in node.tracer.totals_ms.items() if k != 'exposed_comm') - b0) / steps
+        own -= (node.tracer.totals_ms.get('exposed_comm', 0.0) - e0) / steps
+        mine = (int(cfg.get('stage_index', 0)), own)
+        every = [None] * world
+        dist.all_gather_object(every, mine, group=gloo)
+        per_stage = [0.0] * stages
+        for st, ms in every:
+            per_stage[st] = max(per_stage[st], ms)
+        return per_stage
+
+    # profile-guided re-planning: the planner's per-node estimates miss what only the running pipeline shows (graph replay,
+    # boundary copies, clocks); cut the plan again with shares corrected by the measured stage times (rv.rebalanced_proportions)
+    while stages > 1 and user_props is None and plan_state['rounds'] < args.rebalance:
+        busy_now = stage_busy()
+        plan_state['history'].append([round(v, 3) for v in busy_now])
+        if max(busy_now) <= 1.05 * (sum(busy_now) / len(busy_now)):
+            break
+        cur = plan_state['proportions'] or [1.0 / stages] * stages
+        plan_state['proportions'] = rv.rebalanced_proportions(cur, busy_now)
+        plan_state['rounds'] += 1
+        milestone('re-planning with shares {}'.format([round(v, 3) for v in plan_state['proportions']]))
+        sync()
+        if driver:
+            node.stop()
+        node._stop.wait(20)
+        time.sleep(0.2)
+        sync()
+        node = None
+        plan(plan_state['proportions'], 'measured')
+        node = make_node()
+        run(prewarm, 'dev', False)
     run(max(3, args.warmup), 'dev', False)
     milestone('warm-up done, timing')
     sampler = ClockSampler(dev.index or 0)
@@ -466,6 +519,7 @@ def bench_one(args, rank, world, dev, gloo, milestone):
                        'global_batch': replicas * batch, 'per_replica_batch': batch, 'seq_len': 512 if args.model == 'bert' else None,
                        'parallelism': 'pp{}xdp{}'.format(stages, replicas), 'optimizer': {'bert': 'LAMB', 'sorter': 'Adam'}.get(args.model, 'SGD-momentum'),
                        'update_frequency': upd, 'schedule': 'async 1F1B, weight stashing, activations resident (no recompute)', 'cuda_graphs': not args.no_graphs, 'prewarm_steps_before_warmup': prewarm,
+                       'stage_shares': plan_state['proportions'], 'replan_rounds': plan_state['rounds'], 'stage_busy_before_replan_ms': plan_state['history'],
                        'l2': 'working set (weights+activations, >1 GB/step) exceeds the 126 MB L2; no explicit flush'},
             'clocks': clocks, 'e2e': e2e,
             'gpu_launches': (launches or {}).get('ours_per_step', 0) * args.steps if isinstance(launches, dict) else 0,

@@ -180,6 +180,19 @@ def get_memory_reqs(model=None, input_size=None, input_data=None, depth=3, call_
     return int(math.ceil((in_bytes + out_bytes[0] + param_bytes) / 1e6))
 
 
+def rebalanced_proportions(proportions: Sequence[float], stage_busy_ms: Sequence[float], damping: float = 1.0) -> List[float]:
+    """Profile-guided re-planning (new): given the cost shares a plan was cut with and the device time every stage of that plan
+    actually spends per step (``StageTracer`` / ``bench.py: stage_busy_ms_per_rank``), return the shares to cut the next plan with so
+    that the stages take equal time: a stage that ran ``r`` times longer than the mean gets ``1/r`` of its share.  The planner's
+    per-node estimates are only locally right (eager launch gaps, cuDNN heuristics, graph-replay effects); one or two rounds of this
+    feedback remove what they miss.  ``clusterize(..., proportions=rebalanced_proportions(...), balance='measured')``."""
+    assert len(proportions) == len(stage_busy_ms) and len(proportions) > 0
+    mean = sum(stage_busy_ms) / len(stage_busy_ms)
+    raw = [p * (mean / max(b, 1e-6)) ** damping for p, b in zip(proportions, stage_busy_ms)]
+    total = sum(raw)
+    return [r / total for r in raw]
+
+
 def equal_proportions(n: int) -> List[float]:
     """round(1/n, 1) for all but the last stage, remainder to the last
     (reference operations/utils.py:430-435: n=3 -> [.3,.3,.4], n=4 -> [.2,.2,.2,.4])."""

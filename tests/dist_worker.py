@@ -36,6 +36,7 @@ def main():
     ap.add_argument('--val', type=int, default=0)
     ap.add_argument('--optimizer', default='adam')
     ap.add_argument('--dump', type=int, default=0, help='write the final master parameters to master.<rank>.pt')
+    ap.add_argument('--replan', type=int, default=0, help='after the run: stop every node, cut the plan again with rebalanced shares, build new nodes in the SAME processes and train again')
     args = ap.parse_args()
     rank, world, dev = init_distributed()
     rv.set_seed(42)
@@ -59,6 +60,32 @@ def main():
     node._stop.wait(30)
     time.sleep(0.3)
     node.compute_session.flush_losses()
+    if args.replan:
+        # profile-guided re-planning inside a running job (bench.py does this on GPUs): new stage boundaries, new Node objects, same
+        # process group and communicators
+        from ravnest_b200 import models
+        first_run_backwards = node.n_backwards
+        torch.distributed.barrier()
+        stages = cfg['cluster_length']
+        if rank == 0:
+            shares = rv.rebalanced_proportions([1.0 / stages] * stages, [1.0 + 0.5 * i for i in range(stages)])
+            rv.set_seed(43)
+            rv.clusterize(models.CNN_Net(), example_args=(torch.rand(32, 1, 8, 8),), topology={'stages': stages, 'replicas': cfg['ring_size']},
+                          node_configs=rv.default_gpu_configs(world), proportions=shares, balance='compute', base_dir=os.environ.get('RAVNEST_HOME', '.'))
+        torch.distributed.barrier()
+        node = rv.Node(name='node_{}'.format(rank), optimizer=opt_cls, optimizer_params=opt_params,
+                       criterion=loss_fn, labels=loader, test_labels=loader, device=dev, reduce_factor=2,
+                       dp_mode=args.dp_mode, recompute=bool(args.recompute), loss_filename='losses2_{}.txt'.format(rank))
+        trainer = rv.Trainer(node=node, train_loader=loader, epochs=args.epochs, inputs_dtype=torch.float32)
+        trainer.train()
+        if trainer.is_driver:
+            node.wait_for_backwards()
+            time.sleep(0.2)
+            node.stop()
+        node._stop.wait(30)
+        time.sleep(0.3)
+        node.compute_session.flush_losses()
+        assert node.n_backwards == first_run_backwards, (node.n_backwards, first_run_backwards)
     if args.dump:
         torch.save({n: v.clone() for n, v in zip(node.compute_session.store.names, node.compute_session.store.master_views)},
                    'master.{}.pt'.format(rank))

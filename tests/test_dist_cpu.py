@@ -154,3 +154,17 @@ def test_gradient_mode_data_parallel_equals_large_batch_sgd(workdir, free_ports)
     for name, p in ref.named_parameters():
         assert torch.allclose(got[0][name], got[1][name], atol=1e-7), name             # replicas identical
         assert torch.allclose(got[0][name], p.detach(), atol=1e-5), name               # ... and equal to large-batch SGD
+
+
+@pytest.mark.slow
+def test_replanning_rebuilds_nodes_in_the_same_processes(workdir, free_ports):
+    """Stop a 4-stage pipeline, cut the plan again with ``rebalanced_proportions`` and train on new Node objects over the same
+    process group / communicators (what ``bench.py --rebalance`` does between its pre-warm and its warm-up)."""
+    res = _launch(workdir, 29000 + free_ports(1)[0] % 900, ['--epochs', '2', '--recompute', '0', '--replan', '1'], stages=4, replicas=1,
+                  proportions=None)
+    assert [r['node_type'] for r in res] == ['root', 'stem', 'stem', 'leaf']
+    assert all(r['n_backwards'] == 16 for r in res[:3])
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses2_3.txt'))]
+    assert len(losses) == 16 and losses[-1] < losses[0]
+    shares = rv.rebalanced_proportions([0.25] * 4, [1.0, 1.5, 2.0, 2.5])
+    assert abs(sum(shares) - 1.0) < 1e-9 and shares[0] > shares[1] > shares[2] > shares[3]
