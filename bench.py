@@ -220,7 +220,7 @@ def main():
         return 1
     import faulthandler
     # a hung multi-GPU run must be cheap and diagnosable: dump every thread's stack and exit instead of burning the box
-    watchdog_s = int(os.environ.get('RVN_BENCH_WATCHDOG', '300'))
+    watchdog_s = int(os.environ.get('RVN_BENCH_WATCHDOG', '150'))
 
     def milestone(text):
         """Re-arm the watchdog (each phase gets the full budget) and, with RAVNEST_TRACE_STARTUP=1, log progress on stderr."""
@@ -249,6 +249,7 @@ def main():
             sub.batch = 0
             sub.diagnose = 0
         results[name] = bench_one(sub, rank, world, dev, gloo, milestone)
+        _release_gpu_objects(dev)
     if rank == 0:
         result = results[args.model]
         extra = {k: v for k, v in results.items() if k != args.model and v is not None}
@@ -266,6 +267,17 @@ def main():
         dist.barrier(group=gloo)
         dist.destroy_process_group()
     return 0
+
+
+def _release_gpu_objects(dev):
+    """Collect dead Node / CUDA-graph objects now.  Left to the cyclic GC they can be destroyed at an arbitrary later moment — e.g. inside
+    the next stage-graph capture, where freeing a graph's memory pool is an illegal operation and invalidates the capture
+    (cudaErrorStreamCaptureIsolation, seen once on the second re-planning round)."""
+    import gc
+    import torch
+    gc.collect()
+    torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
 
 
 def bench_one(args, rank, world, dev, gloo, milestone):
@@ -434,7 +446,7 @@ def bench_one(args, rank, world, dev, gloo, milestone):
     while stages > 1 and user_props is None and plan_state['rounds'] < args.rebalance:
         busy_now = stage_busy()
         plan_state['history'].append([round(v, 3) for v in busy_now])
-        if max(busy_now) <= 1.05 * (sum(busy_now) / len(busy_now)):
+        if max(busy_now) <= 1.06 * (sum(busy_now) / len(busy_now)):
             break
         cur = plan_state['proportions'] or [1.0 / stages] * stages
         plan_state['proportions'] = rv.rebalanced_proportions(cur, busy_now)
@@ -447,6 +459,7 @@ def bench_one(args, rank, world, dev, gloo, milestone):
         time.sleep(0.2)
         sync()
         node = None
+        _release_gpu_objects(dev)       # the old stage graphs must be gone BEFORE anything new is captured
         plan(plan_state['proportions'], 'measured')
         node = make_node()
         run(prewarm, 'dev', False)
@@ -541,6 +554,7 @@ def bench_one(args, rank, world, dev, gloo, milestone):
     time.sleep(0.2)
     if world > 1:
         dist.barrier(group=gloo)
+    node = None
     return result
 
 

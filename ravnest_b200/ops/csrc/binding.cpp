@@ -16,6 +16,8 @@ int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int 
                   int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int split_k,
                   int reduce_out, int num_sms,
                   cudaStream_t stream);
+int rvn_gemm_bf16_2cta(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
+                       const void* bias, int act, int block_n, int num_sms, cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
@@ -215,6 +217,29 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   res.push_back(D.size(1) == N ? D : D.narrow(1, 0, N));
   if (store_preact) res.push_back(P.size(1) == N ? P : P.narrow(1, 0, N));
   return res;
+}
+
+// 2-CTA (cta_group::2, 256 x BN tile per CTA pair) GEMM: D = act(op(A) op(B)^T + bias).  Plain epilogue only (see gemm2_sm100.cu).
+torch::Tensor gemm_2cta(const torch::Tensor& A, bool a_mn, const torch::Tensor& B, bool b_mn, const c10::optional<torch::Tensor>& bias,
+                        int64_t act, int64_t block_n) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm_2cta expects CUDA bf16");
+  c10::cuda::CUDAGuard guard(A.device());
+  const int M = a_mn ? A.size(1) : A.size(0);
+  const int K = a_mn ? A.size(0) : A.size(1);
+  const int N = b_mn ? B.size(1) : B.size(0);
+  TORCH_CHECK((b_mn ? B.size(0) : B.size(1)) == K, "inner dimensions differ");
+  const int lda = ld_of(A), ldb = ld_of(B);
+  const int ldd = (N + 7) / 8 * 8;
+  torch::Tensor D = torch::empty({M, ldd}, A.options());
+  const void* bias_ptr = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->is_contiguous() && bias->numel() == N, "bad bias");
+    bias_ptr = bias->data_ptr();
+  }
+  check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
+                           block_n == 128 ? 128 : 256, sm_count(), cur_stream()),
+        "gemm_bf16_2cta");
+  return D.size(1) == N ? D : D.narrow(1, 0, N);
 }
 
 const long long* rng_ptr(const c10::optional<torch::Tensor>& rng) {
@@ -752,6 +777,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("aux_in") = py::none(), py::arg("store_preact") = false,
         py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none(),
         py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0, py::arg("split_k") = 0);
+  m.def("gemm_2cta", &gemm_2cta, "bf16 tcgen05 GEMM on CTA pairs (cta_group::2)", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
+        py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("block_n") = 256);
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("x"), py::arg("gamma"), py::arg("mean"), py::arg("rstd"), py::arg("rng"),
         py::arg("dropout_p"), py::arg("grad_gamma") = py::none(), py::arg("grad_beta") = py::none());

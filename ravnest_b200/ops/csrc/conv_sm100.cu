@@ -49,6 +49,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// shared -> global bulk reduction (element-wise add at the L2), 3-D tile, element type from the tensor map
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -316,6 +323,20 @@ static int make_map_nd(CUtensorMap* map, const void* base, int rank, const uint6
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// fp32 variant (weight-gradient accumulator): same encoder, 4-byte elements
+static int make_map_nd_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                           const uint32_t* box) {
+  EncodeTiledFn3 enc = conv_encode();
+  if (enc == nullptr) return -1;
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_elems[i] * 4;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
 // pick the output patch (TW, TH, TN), TW*TH*TN <= 128, that wastes the fewest MMA rows for this layer
 static void pick_patch(int Wo, int Ho, int N, int& TW, int& TH, int& TN) {
   double best = -1.0;
@@ -438,7 +459,8 @@ struct WgradSmem {
 
 template <int BN>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-rvn_conv_wgrad_tcgen05(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
+rvn_conv_wgrad_tcgen05(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                       const __grid_constant__ CUtensorMap map_dw, const WgradParams p) {
   using L = WgradSmem<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t IDESC = make_idesc_bf16(128, BN, true, true);
@@ -464,6 +486,7 @@ rvn_conv_wgrad_tcgen05(const __grid_constant__ CUtensorMap map_dy, const __grid_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_dy);
     tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dw);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -522,26 +545,39 @@ rvn_conv_wgrad_tcgen05(const __grid_constant__ CUtensorMap map_dy, const __grid_
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (patch1 > patch0) {
-    // epilogue: thread == output-channel row; fp32 atomics into dW[co, tap, ci]
-    const int ewarp = (warp - 2) & 3;                     // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
-    const int quad = warp & 3;
+    // epilogue: thread == output-channel row.  The split-K partial tile goes into dW[co, tap, ci] as BULK reductions: every 128 x 32
+    // fp32 chunk is staged (128B-swizzled) in the now idle operand stages and added at the L2 by one cp.reduce.async.bulk.tensor,
+    // instead of 32 scalar red.global.add.f32 per thread and chunk (16 K atomics per CTA: the wgrad kernels spent most of their
+    // time in the atomic unit — tensor pipe 22 %).  Cout / Cin tails are clipped by the tensor map.
+    const int quad = warp & 3;                            // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
     const int row = quad * 32 + lane_id();
-    (void)ewarp;
-    mbar_wait(done_bar, 0);
+    const bool issuer = threadIdx.x == 64;                // first epilogue thread
+    mbar_wait(done_bar, 0);                               // every MMA has retired: the smem stages are free
     tcgen05_fence_after();
-    const int co = co_blk * 128 + row;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      uint8_t* buf = smem + (c & 1) * (128 * 128);        // two 16 KB staging tiles inside stage 0
+      if (c >= 2) {
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the reduction that last read this tile is done
+        named_bar_sync(1, 128);
+      }
       uint32_t v[32];
       tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
       tmem_ld_wait();
-      if (co < p.Cout) {
-        float* dst = p.dw + (static_cast<size_t>(co) * p.R * p.S + tap) * p.Cin + ci_blk * BN + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (ci_blk * BN + c * 32 + j < p.Cin) atomicAdd(dst + j, __uint_as_float(v[j]));
+      for (int j = 0; j < 32; j += 4) {
+        uint4 w4;
+        w4.x = v[j]; w4.y = v[j + 1]; w4.z = v[j + 2]; w4.w = v[j + 3];
+        *reinterpret_cast<uint4*>(buf + row * 128 + (((j >> 2) ^ (row & 7)) << 4)) = w4;
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer) {
+        tma_reduce_add_3d(&map_dw, buf, ci_blk * BN + c * 32, tap, co_blk * 128);
+        tma_store_commit();
       }
     }
+    if (issuer) tma_store_wait_all();
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -592,6 +628,13 @@ static int wgrad_launch(const void* dy, const void* x, WgradParams p, int num_sm
     const uint32_t es[4] = {1u, (uint32_t)p.stride, (uint32_t)p.stride, 1u};
     e |= make_map_nd(&mx, x, 4, dims, st, box, es);
   }
+  CUtensorMap mdw;
+  {
+    const uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)(p.R * p.S), (uint64_t)p.Cout};
+    const uint64_t st[2] = {(uint64_t)p.Cin, (uint64_t)p.R * p.S * p.Cin};
+    const uint32_t box[3] = {32u, 1u, 128u};
+    e |= make_map_nd_f32(&mdw, p.dw, 3, dims, st, box);
+  }
   if (e != 0) return 1000 + e;
   auto kern = rvn_conv_wgrad_tcgen05<BN>;
   static bool configured = false;
@@ -599,7 +642,7 @@ static int wgrad_launch(const void* dy, const void* x, WgradParams p, int num_sm
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return 2000;
     configured = true;
   }
-  kern<<<base_tiles * p.splits, WG_THREADS, L::TOTAL, stream>>>(mdy, mx, p);
+  kern<<<base_tiles * p.splits, WG_THREADS, L::TOTAL, stream>>>(mdy, mx, mdw, p);
   return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 

@@ -42,6 +42,25 @@ def test_gemm_nt(M, N, K, block_n):
     assert _rel_err(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize('M,N,K,a_mn,b_mn', [(256, 256, 64, False, False), (512, 512, 256, False, False), (4096, 30528, 768, False, False),
+                                              (1000, 520, 328, False, False), (4096, 768, 2304, False, True), (768, 3072, 4096, True, True),
+                                              (2048, 2048, 2048, True, False)])
+@pytest.mark.parametrize('block_n', [128, 256])
+def test_gemm_2cta(M, N, K, a_mn, b_mn, block_n):
+    """cta_group::2 kernel (CTA pair per 256 x BN tile) in every operand layout, with bias + GELU, against fp32 matmul."""
+    torch.manual_seed(21)
+    a = _rand(K, M, scale=0.5) if a_mn else _rand(M, K, scale=0.5)
+    b = _rand(K, N, scale=0.05) if b_mn else _rand(N, K, scale=0.05)
+    bias = _rand(N) if N % 8 == 0 else None
+    ref = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
+    out = _C().gemm_2cta(a, a_mn, b, b_mn, None, 0, block_n)
+    assert out.shape == (M, N)
+    assert _rel_err(out, ref) < 1e-2
+    if bias is not None:
+        out = _C().gemm_2cta(a, a_mn, b, b_mn, bias, 1, block_n)
+        assert _rel_err(out, torch.nn.functional.gelu(ref + bias.float())) < 1.5e-2
+
+
 @pytest.mark.parametrize('M,N,K', [(256, 128, 128), (4096, 768, 2304), (520, 264, 200)])
 def test_gemm_dgrad_layout(M, N, K):
     """D[M,N] = A[M,K] @ B[K,N] with B read MN-major (dx = dy @ W)."""

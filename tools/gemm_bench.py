@@ -54,6 +54,8 @@ if sweep:       # every (block_n, split_k) the kernel offers, per shape; wgrad s
                 else:
                     fn = lambda: C.gemm(A, amn, Bm, bmn, None, 0, None, False, bn)
                 row['bn{}_sk{}'.format(bn, sk)] = round(timed(fn, 7) * 1e3, 2)
+        for bn in (128, 256):                   # CTA-pair kernel (cta_group::2), plain epilogue
+            row['2cta_bn{}'.format(bn)] = round(timed(lambda: C.gemm_2cta(A, amn, Bm, bmn, None, 0, bn), 7) * 1e3, 2)
         if wgrad:
             row['auto_us'] = round(timed(lambda: C.gemm(A, amn, Bm, bmn, None, 0, G, False, 0, 2, G)) * 1e3, 2)
         else:
