@@ -64,6 +64,21 @@ for it in range(2):
         idx = torch.randint(0, 30522, (8, 512), device=dev)
         y = ops.dropout(ops.embedding(idx, w, 0), 0.1, True)
         y.backward(r(8, 512, 768))
+    elif target == 'gemm':                                 # BERT shapes through the tile / split-K model: fwd (bn256, bn192), dgrad, accumulate wgrad
+        x, w_qkv, w_ffn2 = r(4096, 768), r(2304, 768, scale=0.03), r(768, 3072, scale=0.03)
+        C.gemm(x, False, w_qkv, False, None, 0, None, False, 0)                     # 4096 x 2304 x 768  (bn256)
+        h = r(4096, 3072)
+        C.gemm(h, False, w_ffn2, False, None, 0, None, False, 0)                    # 4096 x 768 x 3072  (bn192)
+        dy = r(4096, 768)
+        C.gemm(dy, False, w_ffn2, True, None, 0, None, False, 0)                    # dgrad 4096 x 3072 x 768
+        g = torch.zeros(768, 768, dtype=torch.bfloat16, device=dev)
+        C.gemm(dy, True, x, True, None, 0, g, False, 0, 2, g)                       # wgrad 768 x 768 x 4096: split-K + TMA reduce-add
+        g2 = torch.zeros(2304, 768, dtype=torch.bfloat16, device=dev)
+        C.gemm(r(4096, 2304), True, x, True, None, 0, g2, False, 0, 2, g2)
+    elif target == 'gemm2':                                # CTA-pair kernel on the LM-head shape and a large square
+        C.gemm_2cta(r(4096, 768), False, r(30528, 768, scale=0.03), False, None, 0, 256)
+        C.gemm_2cta(r(8192, 8192, scale=0.1), False, r(8192, 8192, scale=0.1), False, None, 0, 256)
+        C.gemm(r(8192, 8192, scale=0.1), False, r(8192, 8192, scale=0.1), False, None, 0, None, False, 256)
     elif target == 'optim':
         from ravnest_b200.parallel.fused_optim import FusedFlatOptimizer
         from ravnest_b200.runtime.param_store import ParamStore
