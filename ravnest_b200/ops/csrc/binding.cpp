@@ -17,7 +17,7 @@ int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int 
                   int reduce_out, int num_sms,
                   cudaStream_t stream);
 int rvn_gemm_bf16_2cta(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
-                       const void* bias, int act, int block_n, int num_sms, cudaStream_t stream);
+                       const void* bias, int act, int reduce_out, int block_n, int num_sms, cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
@@ -35,9 +35,9 @@ int rvn_fmha_backward(const void* qkv, const void* o, const void* d_o, const flo
                       void* dqkv, int B, int S, int heads, int causal, float scale, const long long* rng, float dropout_p, int num_sms,
                       cudaStream_t stream);
 int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho, int Wo,
-                     int Cout, int R, int S, int stride, int pad, int dil, int transposed, int num_sms, cudaStream_t stream);
+                     int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, int num_sms, cudaStream_t stream);
 int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
-                   int stride, int pad, int dil, int num_sms, cudaStream_t stream);
+                   int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream);
 int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean, void* running_var,
                           long long* batches_tracked, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
                           float momentum, int relu, int training, int param_bf16, int stats_bf16, int num_sms, cudaStream_t stream);
@@ -114,7 +114,7 @@ int ld_of(const torch::Tensor& t) {
 // ceil(units / SMs) work units back to back; a unit costs (k-blocks / split) * BN / eff(BN) plus one exposed epilogue.  eff = achieved
 // fraction of the tensor peak per tile shape (128-wide tiles are shared-memory-bandwidth bound: A + B = 128 B/clk).  Explicit
 // block_n / split_k > 0 (or RVN_GEMM_BN / RVN_GEMM_SPLITK) override the model.
-static void choose_tiling(int M, int N, int K, bool can_split, int sms, int64_t* block_n, int64_t* split_k) {
+static double choose_tiling(int M, int N, int K, bool can_split, int sms, int64_t* block_n, int64_t* split_k) {
   static const int env_bn = getenv("RVN_GEMM_BN") ? atoi(getenv("RVN_GEMM_BN")) : 0;
   static const int env_sk = getenv("RVN_GEMM_SPLITK") ? atoi(getenv("RVN_GEMM_SPLITK")) : 0;
   if (*block_n <= 0 && env_bn > 0) *block_n = env_bn;
@@ -144,6 +144,27 @@ static void choose_tiling(int M, int N, int K, bool can_split, int sms, int64_t*
   }
   if (*block_n <= 0 || (*block_n != 128 && *block_n != 192 && *block_n != 256)) *block_n = best_bn;
   if (*split_k <= 0) *split_k = best_s;
+  return best;
+}
+
+// Same wave model for the CTA-pair kernel (gemm2_sm100.cu): 256 x BN tiles on sms/2 pairs; per-tile efficiency measured on B200
+// (8192^3: tensor pipe 98 % vs 84 % for the 1-CTA kernel; LM head 4096 x 30528 x 768: 125 us vs 147 us).  Returns the cost, sets *bn2.
+static double pair_tiling_cost(int M, int N, int K, int sms, int* bn2) {
+  static const int off = getenv("RVN_GEMM_2CTA") ? (atoi(getenv("RVN_GEMM_2CTA")) == 0) : 0;
+  if (off) return 1e30;
+  const int m2 = (M + 255) / 256, nkb = (K + 63) / 64, pairs = sms / 2;
+  const int bns[2] = {128, 256};
+  const double eff[2] = {0.72, 1.0};
+  double best = 1e30;
+  for (int i = 0; i < 2; ++i) {
+    const int bn = bns[i];
+    if (bn > 128 && N < bn) continue;
+    const long tiles = static_cast<long>(m2) * ((N + bn - 1) / bn);
+    const long waves = (tiles + pairs - 1) / pairs;
+    const double cost = waves * (nkb + 1.5) * bn / eff[i] + 5.0 * bn;      // same units as choose_tiling (a pair tile is two CTA tiles)
+    if (cost < best) { best = cost; *bn2 = bn; }
+  }
+  return best;
 }
 
 // D[M,N] = epi(op(A) * op(B)^T).  A: [M,K] (a_mn=false) or [K,M] (a_mn=true); B: [N,K] (b_mn=false) or [K,N] (b_mn=true).
@@ -196,7 +217,21 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   const bool reduce_out = dact_ptr != nullptr && aux_mode == 2 && out.has_value() && out->defined() &&
                           dact_ptr == out->data_ptr() && ld_dact == ldd && !store_preact && !(bias.has_value() && bias->defined()) && act == 0;
   if (reduce_out) dact_ptr = nullptr;
-  choose_tiling(M, N, K, reduce_out, sm_count(), &block_n, &split_k);
+  const bool explicit_tiling = block_n > 0 || split_k > 0;
+  const double cost1 = choose_tiling(M, N, K, reduce_out, sm_count(), &block_n, &split_k);
+  // plain epilogues (bias / activation, or accumulate-into-output) may run on the CTA-pair kernel when the wave model prefers it
+  if (!explicit_tiling && dact_ptr == nullptr && !store_preact && !(b_copy_dst.has_value() && b_copy_dst->defined()) && M >= 256) {
+    int bn2 = 256;
+    const double cost2 = pair_tiling_cost(M, N, K, sm_count(), &bn2);
+    if (cost2 < 0.97 * cost1) {
+      check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
+                               reduce_out ? 1 : 0, bn2, sm_count(), cur_stream()),
+            "gemm_bf16_2cta");
+      std::vector<torch::Tensor> res2;
+      res2.push_back(D.size(1) == N ? D : D.narrow(1, 0, N));
+      return res2;
+    }
+  }
   void* bcopy_ptr = nullptr;
   int ld_bcopy = 0;
   if (b_copy_dst.has_value() && b_copy_dst->defined()) {   // K2: B lives in a peer's HBM; land it locally while multiplying
@@ -236,7 +271,7 @@ torch::Tensor gemm_2cta(const torch::Tensor& A, bool a_mn, const torch::Tensor& 
     TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->is_contiguous() && bias->numel() == N, "bad bias");
     bias_ptr = bias->data_ptr();
   }
-  check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
+  check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act), 0,
                            block_n == 128 ? 128 : 256, sm_count(), cur_stream()),
         "gemm_bf16_2cta");
   return D.size(1) == N ? D : D.narrow(1, 0, N);
@@ -513,7 +548,8 @@ torch::Tensor fmha_bwd(const torch::Tensor& qkv, const torch::Tensor& out, const
 // x: [N,H,W,Cin] bf16 contiguous (NHWC); w: [Cout,R,S,Cin] contiguous.  transposed=false: y = conv(x, w) -> [N,Ho,Wo,Cout].
 // transposed=true (dgrad, stride 1): x is dy [N,Ho,Wo,Cout], result is dx [N,H,W,Cin]; `out_hw` gives the result's H, W.
 torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c10::optional<torch::Tensor>& bias, int64_t stride,
-                        int64_t pad, int64_t dil, bool relu, bool transposed, int64_t out_h, int64_t out_w) {
+                        int64_t pad, int64_t dil, bool relu, bool transposed, int64_t out_h, int64_t out_w, int64_t pad_w) {
+  if (pad_w < 0) pad_w = pad;          // square padding unless a horizontal one is given (rectangular kernels)
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 &&
               w.scalar_type() == torch::kBFloat16, "conv_nhwc expects contiguous bf16 NHWC activations and [Cout,R,S,Cin] weights");
@@ -528,19 +564,22 @@ torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c1
     Ho = out_h; Wo = out_w;
   } else {
     Ho = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
-    Wo = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+    Wo = (W + 2 * pad_w - dil * (S - 1) - 1) / stride + 1;
   }
   auto y = torch::empty({N, Ho, Wo, n_ch}, x.options());
   const void* bias_ptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
   const int eff_pad = transposed ? static_cast<int>(dil * (R - 1) - pad) : static_cast<int>(pad);
+  const int eff_pad_w = transposed ? static_cast<int>(dil * (S - 1) - pad_w) : static_cast<int>(pad_w);
   check(rvn_conv_forward(x.data_ptr(), w.data_ptr(), y.data_ptr(), bias_ptr, relu, N, H, W, k_ch, Ho, Wo, n_ch, R, S, static_cast<int>(stride),
-                         eff_pad, static_cast<int>(dil), transposed, sm_count(), cur_stream()),
+                         eff_pad, eff_pad_w, static_cast<int>(dil), transposed, sm_count(), cur_stream()),
         "conv_forward");
   return y;
 }
 
 // dy [N,Ho,Wo,Cout], x [N,H,W,Cin] (NHWC bf16) -> dW [Cout,R,S,Cin] fp32
-torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t dil) {
+torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t dil,
+                              int64_t pad_w) {
+  if (pad_w < 0) pad_w = pad;
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dy.scalar_type() == torch::kBFloat16 && x.scalar_type() == torch::kBFloat16,
               "conv_wgrad_nhwc expects contiguous bf16 NHWC tensors");
@@ -549,7 +588,7 @@ torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, i
   TORCH_CHECK(Cin % 8 == 0 && Cout % 8 == 0, "channel counts must be multiples of 8");
   auto dw = torch::zeros({Cout, R, S, Cin}, x.options().dtype(torch::kFloat32));
   check(rvn_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), N, H, W, Cin, Ho, Wo, Cout, static_cast<int>(R), static_cast<int>(S),
-                       static_cast<int>(stride), static_cast<int>(pad), static_cast<int>(dil), sm_count(), cur_stream()),
+                       static_cast<int>(stride), static_cast<int>(pad), static_cast<int>(pad_w), static_cast<int>(dil), sm_count(), cur_stream()),
         "conv_wgrad");
   return dw;
 }
@@ -791,12 +830,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dropout_apply", &dropout_apply);
   m.def("pack_f32", &pack_f32);
   m.def("rng_next", &rng_next);
-  m.def("conv_nhwc", &conv_nhwc);
+  m.def("conv_nhwc", &conv_nhwc, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("relu"),
+        py::arg("transposed"), py::arg("out_h"), py::arg("out_w"), py::arg("pad_w") = -1);
   m.def("pool_fwd", &pool_fwd);
   m.def("pool_bwd", &pool_bwd);
   m.def("batchnorm_fwd", &batchnorm_fwd);
   m.def("batchnorm_bwd", &batchnorm_bwd);
-  m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc);
+  m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc, py::arg("dy"), py::arg("x"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"),
+        py::arg("dil"), py::arg("pad_w") = -1);
   m.def("fmha_fwd", &fmha_fwd);
   m.def("fmha_bwd", &fmha_bwd);
   m.def("fused_update", &fused_update);

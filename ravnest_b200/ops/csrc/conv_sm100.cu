@@ -33,6 +33,7 @@ constexpr int CV_SLAB_BYTES = CV_BLOCK_M * CV_SLAB_N * 2;
 struct ConvParams {
   int N, H, W, Cin, Ho, Wo, Cout;
   int R, S, stride, pad, dil;
+  int pad_w;                      // horizontal padding (pad = vertical): rectangular kernels (1x7, 7x1, 1x3, 3x1)
   int TW, TH, TN;                 // output patch of one CTA tile (TW*TH*TN <= 128)
   int tiles_w, tiles_h, tiles_n;  // patches per dimension
   int num_n_blocks;               // Cout / BN (rounded up)
@@ -164,7 +165,7 @@ rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const 
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], a_bytes + L::B_BYTES);
           // input patch of this tap: coordinates may be negative / beyond the image -> TMA zero fill == padding
-          tma_load_4d(sa, &map_x, &full_bar[stage], c0, wo0 * p.stride + s * p.dil - p.pad, ho0 * p.stride + r * p.dil - p.pad, n0);
+          tma_load_4d(sa, &map_x, &full_bar[stage], c0, wo0 * p.stride + s * p.dil - p.pad_w, ho0 * p.stride + r * p.dil - p.pad, n0);
           if constexpr (!B_MN) {
             tma_load_3d(sb, &map_w, &full_bar[stage], c0, tap, co0);                       // {64 ci, 1 tap, BN co}
           } else {
@@ -409,11 +410,11 @@ static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int 
 // x [N,H,W,Cin], w [Cout,R,S,Cin] (or, transposed=1, the SAME buffer consumed as a map from Cout_in -> Cin_out for dgrad:
 // then `Cin`/`Cout` below are the GEMM K / N channel counts, i.e. Cin = channels of the incoming gradient), y [N,Ho,Wo,Cout].
 extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho,
-                                int Wo, int Cout, int R, int S, int stride, int pad, int dil, int transposed, int num_sms,
+                                int Wo, int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, int num_sms,
                                 cudaStream_t stream) {
   rvn::ConvParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
-  p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.pad_w = pad_w; p.dil = dil;
   p.flip = transposed;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.relu = relu;
@@ -442,7 +443,7 @@ constexpr int WG_THREADS = 192;                 // warp 0 TMA, warp 1 MMA + TMEM
 
 struct WgradParams {
   int N, H, W, Cin, Ho, Wo, Cout;
-  int R, S, stride, pad, dil;
+  int R, S, stride, pad, dil, pad_w;
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;
   int co_blocks, ci_blocks, splits, patches_per_split;
   float* dw;                                    // [Cout, R*S, Cin] fp32, zero-initialised by the caller
@@ -520,7 +521,7 @@ rvn_conv_wgrad_tcgen05(const __grid_constant__ CUtensorMap map_dy, const __grid_
           tma_load_4d(sa + j * (WG_PIX * 128), &map_dy, &full_bar[stage], co_blk * 128 + j * 64, wo0, ho0, n0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(sb + j * (WG_PIX * 128), &map_x, &full_bar[stage], ci_blk * BN + j * 64, wo0 * p.stride + s * p.dil - p.pad,
+          tma_load_4d(sb + j * (WG_PIX * 128), &map_x, &full_bar[stage], ci_blk * BN + j * 64, wo0 * p.stride + s * p.dil - p.pad_w,
                       ho0 * p.stride + r * p.dil - p.pad, n0);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -650,10 +651,10 @@ static int wgrad_launch(const void* dy, const void* x, WgradParams p, int num_sm
 
 // dy [N,Ho,Wo,Cout], x [N,H,W,Cin] bf16 NHWC; dw [Cout,R,S,Cin] fp32 zero-initialised (accumulated into)
 extern "C" int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R,
-                              int S, int stride, int pad, int dil, int num_sms, cudaStream_t stream) {
+                              int S, int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream) {
   rvn::WgradParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
-  p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.pad_w = pad_w; p.dil = dil;
   p.dw = dw;
   if (Cin > 64) return rvn::wgrad_launch<128>(dy, x, p, num_sms, stream);
   return rvn::wgrad_launch<64>(dy, x, p, num_sms, stream);

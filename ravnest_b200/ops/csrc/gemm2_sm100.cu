@@ -13,8 +13,11 @@
 //   warps 4-11 (both)  : epilogue of the CTA's own 128 rows (tcgen05.ld -> bias / activation -> bf16 -> swizzled smem -> TMA store);
 //                        both CTAs hand the accumulator stage back by arriving on the LEADER's tmem_empty barrier
 //
-// Epilogue features: bias + activation (the large forward GEMMs: LM head, square benchmarks).  GEMMs that need the auxiliary tile
-// paths (activation-gradient, accumulate, pre-activation store, K2 pull) stay on the 1-CTA kernel in gemm_sm100.cu.
+// Epilogue features: bias + activation, or accumulate-into-output through TMA reduce-add (the large forward GEMMs and the LM-head weight
+// gradient).  GEMMs that need the auxiliary tile paths (activation-gradient multiply, pre-activation store, K2 pull) or split-K stay on
+// the 1-CTA kernel in gemm_sm100.cu; binding.cpp picks per call with the wave model (pair_tiling_cost vs choose_tiling).
+// Measured on B200 (profiles/ncu_gemm2_r2.md, gemm_sweep_r2i.json): 8192^3 722 us at 98 % tensor-pipe activity (1-CTA kernel: 776 us, 84 %;
+// cuBLAS 644 us); LM head 4096 x 30528 x 768: 125 us (1-CTA 147 us, cuBLAS 141 us).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -39,6 +42,7 @@ struct Params {
   int M, N, K;
   const __nv_bfloat16* bias;
   int act;
+  int reduce_out;                 // D += acc by TMA reduce-add (gradient accumulation into the bucket) instead of a store
   int num_m2_blocks, num_n_blocks, num_k_blocks;
 };
 
@@ -165,6 +169,7 @@ rvn_gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap map_a, const __gr
   }
   tcgen05_fence_before();
   cluster_sync_all();                               // barrier inits and the TMEM allocation of BOTH CTAs are visible
+  __syncthreads();                                  // (implied by the cluster barrier; spelled out for compute-sanitizer racecheck)
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -298,7 +303,7 @@ rvn_gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap map_a, const __gr
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_THREADS);
         if (issuer) {
-          tma_store_2d(&map_d, buf, col0, m0);
+          if (p.reduce_out) tma_reduce_add_2d(&map_d, buf, col0, m0); else tma_store_2d(&map_d, buf, col0, m0);
           tma_store_commit();
         }
         ++slab_counter;
@@ -371,11 +376,12 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 
 // 2-CTA GEMM entry: D[M,N] = act(op(A) op(B)^T + bias); layouts as in rvn_gemm_bf16.  block_n in {128, 256}.
 extern "C" int rvn_gemm_bf16_2cta(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
-                                  const void* bias, int act, int block_n, int num_sms, cudaStream_t stream) {
+                                  const void* bias, int act, int reduce_out, int block_n, int num_sms, cudaStream_t stream) {
   rvn::g2::Params p{};
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.act = act;
+  p.reduce_out = reduce_out;
 #define RVN_D2(BN_)                                                                                              \
   if (!a_mn && !b_mn) return rvn::g2::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, p, num_sms, stream);       \
   if (!a_mn && b_mn) return rvn::g2::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, p, num_sms, stream);         \

@@ -469,14 +469,16 @@ class _ConvNHWC(torch.autograd.Function):
     ``weight`` is the [O, I, kh, kw] parameter itself; stored channels_last (ParamStore does) its OHWI view is free."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, weight, bias, stride, pad, dil, relu):
+    def forward(ctx, x_nhwc, weight, bias, stride, pad, dil, relu, pad_w=-1):
         w_ohwi = weight.permute(0, 2, 3, 1)
         if not w_ohwi.is_contiguous():
             w_ohwi = w_ohwi.contiguous()
             calls['conv_weight_permute'] += 1
-        y = C().conv_nhwc(x_nhwc, w_ohwi, bias, stride, pad, dil, relu, False, 0, 0)
+        pad_w = pad if pad_w < 0 else pad_w
+        y = C().conv_nhwc(x_nhwc, w_ohwi, bias, stride, pad, dil, relu, False, 0, 0, pad_w)
         calls['conv_fwd'] += 1
         ctx.cfg = (stride, pad, dil, relu)
+        ctx.pad_w = pad_w
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x_nhwc, weight, w_ohwi, y if relu else None)
         return y
@@ -491,25 +493,26 @@ class _ConvNHWC(torch.autograd.Function):
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         native_dx = need_dx and stride == 1
+        pad_w = ctx.pad_w
         if native_dx:
-            dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2])
+            dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2], pad_w)
             calls['conv_dgrad'] += 1
         if need_dw and NATIVE_CONV_WGRAD:
-            dw = _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, w.shape[1], w.shape[2], stride, pad, dil))
+            dw = _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, w.shape[1], w.shape[2], stride, pad, dil, pad_w))
             calls['conv_wgrad'] += 1
             need_dw = False
         if need_dw or (need_dx and not native_dx) or ctx.has_bias:
             # library path on NCHW-shaped channels_last views (zero-copy)
             gx, gw, gb = torch.ops.aten.convolution_backward(
                 dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), [w.shape[0]] if ctx.has_bias else None,
-                [stride, stride], [pad, pad], [dil, dil], False, [0, 0], 1, [need_dx and not native_dx, need_dw, ctx.has_bias])
+                [stride, stride], [pad, pad_w], [dil, dil], False, [0, 0], 1, [need_dx and not native_dx, need_dw, ctx.has_bias])
             fallbacks['conv_dgrad_s2' if not need_dw else 'conv_wgrad'] += 1
             if need_dx and not native_dx:
                 dx = gx.permute(0, 2, 3, 1).contiguous()
             if need_dw:
                 dw = gw
             db = gb
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 class _Conv1x1(torch.autograd.Function):
@@ -573,10 +576,11 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
             x = x.contiguous(memory_format=torch.channels_last)
         y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight, bias)           # zero-copy NHWC view in, NHWC out
         return y.permute(0, 3, 1, 2)                                      # NCHW-shaped, channels_last-strided
-    if base_ok and sh == sw and ph == pw and dh == dw_ and kh == kw and sh in (1, 2) and IMPLICIT_GEMM_CONV:
+    if base_ok and sh == sw and dh == dw_ and sh in (1, 2) and IMPLICIT_GEMM_CONV and (kh == kw and ph == pw or RECTANGULAR_CONV):
+        # square and rectangular (Inception's 1x7 / 7x1 / 1x3 / 3x1, separate vertical / horizontal padding) kernels
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), weight, bias, sh, ph, dh, False)
+        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), weight, bias, sh, ph, dh, False, pw)
         return y.permute(0, 3, 1, 2)
     fallbacks['conv2d'] += 1
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
@@ -585,6 +589,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
 IMPLICIT_GEMM_CONV = True
 NATIVE_CONV_WGRAD = True
 STRIDED_1X1_IMPLICIT = True
+RECTANGULAR_CONV = True
 
 
 class _BatchNormAct(torch.autograd.Function):

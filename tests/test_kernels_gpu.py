@@ -61,6 +61,19 @@ def test_gemm_2cta(M, N, K, a_mn, b_mn, block_n):
         assert _rel_err(out, torch.nn.functional.gelu(ref + bias.float())) < 1.5e-2
 
 
+def test_gemm_auto_tiling_routes_large_problems_to_the_pair_kernel():
+    """Default tiling (block_n = 0): the wave model sends the LM-head shapes to the cta_group::2 kernel — plain and accumulate epilogues."""
+    torch.manual_seed(22)
+    a, b, bias = _rand(2048, 768, scale=0.5), _rand(8192, 768, scale=0.05), _rand(8192)
+    out = _C().gemm(a, False, b, False, bias, 0, None, False, 0)[0]
+    assert _rel_err(out, a.float() @ b.float().t() + bias.float()) < 1e-2
+    at, bt = _rand(1024, 8192, scale=0.1), _rand(1024, 768, scale=0.1)       # dW[8192, 768] += A^T B  (vocab wgrad shape class)
+    g0 = _rand(8192, 768)
+    g = g0.clone()
+    _C().gemm(at, True, bt, True, None, 0, g, False, 0, 2, g)
+    assert _rel_err(g, g0.float() + at.float().t() @ bt.float()) < 1.5e-2
+
+
 @pytest.mark.parametrize('M,N,K', [(256, 128, 128), (4096, 768, 2304), (520, 264, 200)])
 def test_gemm_dgrad_layout(M, N, K):
     """D[M,N] = A[M,K] @ B[K,N] with B read MN-major (dx = dy @ W)."""
@@ -276,6 +289,28 @@ def test_conv2d_implicit_gemm(N, C, H, W, K, R, stride, pad):
     assert _rel_err(x.grad, xr.grad) < 2e-2
     assert _rel_err(w.grad, wr.grad) < 2e-2
     assert native.calls['conv_fwd'] + native.calls['conv1x1_as_gemm'] > 0
+
+
+@pytest.mark.parametrize('N,C,H,W,K,kh,kw,ph,pw', [(4, 128, 17, 17, 128, 1, 7, 0, 3), (4, 128, 17, 17, 192, 7, 1, 3, 0), (2, 384, 8, 8, 384, 1, 3, 0, 1),
+                                                   (2, 384, 8, 8, 384, 3, 1, 1, 0), (3, 48, 32, 32, 64, 5, 5, 2, 2)])
+def test_conv2d_rectangular_kernels(N, C, H, W, K, kh, kw, ph, pw):
+    """Inception's 1x7 / 7x1 / 1x3 / 3x1 (and 5x5) convolutions on the implicit-GEMM kernel: forward, dgrad, wgrad, no library fallback."""
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(15)
+    x = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = _rand(K, C, kh, kw, scale=0.05).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = native.fallbacks['conv2d']
+    y = ops.conv2d(x, w, None, 1, (ph, pw), 1, 1)
+    g = _rand(*y.shape).contiguous(memory_format=torch.channels_last)
+    y.backward(g)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, None, 1, (ph, pw))
+    yr.backward(g.float())
+    assert y.shape == yr.shape and native.fallbacks['conv2d'] == before
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 2e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
 
 
 @pytest.mark.parametrize('N,C,H,W', [(8, 64, 56, 56), (4, 256, 28, 28), (3, 2048, 7, 7), (2, 48, 17, 17)])
