@@ -177,6 +177,25 @@ def _tensor_specs(skeleton: Any, out: List[Tuple[Tuple[int, ...], torch.dtype]])
             _tensor_specs(v, out)
 
 
+_VOLATILE = ('forward_pass_id', 'epoch_change', 'action')
+_FAST_MAGIC = 0x52564E46          # 'RVNF'
+
+
+def _signature(obj: Any) -> Any:
+    """Hashable structural signature of a tensor-free skeleton (keys, placeholders with shape / dtype, scalar leaves)."""
+    if isinstance(obj, dict):
+        return ('d',) + tuple((k, _signature(v)) for k, v in obj.items())
+    if isinstance(obj, (list, tuple)):
+        return ('l' if isinstance(obj, list) else 't',) + tuple(_signature(v) for v in obj)
+    return obj if isinstance(obj, (int, float, str, bool, bytes, type(None), torch.dtype)) else repr(obj)
+
+
+def _strip_volatile(message: Dict[str, Any]) -> Tuple[Dict[str, Any], Tuple[Any, ...]]:
+    """Split a message into its per-step scalars and the rest (whose tensor-free skeleton is identical step after step)."""
+    rest = {k: v for k, v in message.items() if k not in _VOLATILE}
+    return rest, (message.get('action'), int(message.get('forward_pass_id', -1)), bool(message.get('epoch_change', False)))
+
+
 class DistTransport:
     kind = 'dist'
 
@@ -206,6 +225,14 @@ class DistTransport:
         self.bytes_out = 0
         self.rings = None
         self.just_in_time = os.environ.get('RAVNEST_P2P_JIT', '1') != '0'
+        # static wire plan, learned: the first message of a given shape on a lane travels with its pickled skeleton and gets an id;
+        # every later message with the same skeleton is announced by a fixed 64-byte binary header (id, action code, fpid, flags) —
+        # no pickle / unpickle, no shape metadata on the wire in steady state (the cut tensors of a stage never change shape)
+        self.static_headers = os.environ.get('RAVNEST_STATIC_HEADERS', '1') != '0'
+        self._sent_skeletons: Dict[str, Dict[bytes, int]] = {FORWARD: {}, BACKWARD: {}}
+        self._known_skeletons: Dict[str, Dict[int, Any]] = {FORWARD: {}, BACKWARD: {}}
+        self._known_volatile: Dict[Tuple[str, int], Tuple[str, ...]] = {}
+        self.header_stats = {'pickled': 0, 'static': 0}
 
     # ------------------------------------------------------------------ lifecycle
     def start(self) -> None:
@@ -276,16 +303,37 @@ class DistTransport:
                     # for the producer's event HERE (this thread sleeps, the scheduler thread is not involved) keeps both NCCL
                     # kernels down to the transfer itself.
                     ev.synchronize()
-                raw = pickle.dumps(skeleton, protocol=pickle.HIGHEST_PROTOCOL)
-                # ONE fixed-size frame carries the length and (almost always) the whole pickled skeleton; only a header that
-                # does not fit is followed by a second message with the rest (was: a length message + a blob message per hop)
                 frame = torch.zeros(_FRAME, dtype=torch.uint8)
-                frame[:8] = torch.frombuffer(bytearray(len(raw).to_bytes(8, 'little')), dtype=torch.uint8)
-                head = min(len(raw), _FRAME - 8)
-                frame[8:8 + head] = torch.frombuffer(bytearray(raw[:head]), dtype=torch.uint8)
-                dist.send(frame, dst=peer, group=hgroup, tag=_TAG[lane])
-                if len(raw) > head:
-                    dist.send(torch.frombuffer(bytearray(raw[head:]), dtype=torch.uint8), dst=peer, group=hgroup, tag=_TAG[lane])
+                fast_id = None
+                if self.static_headers and bag:
+                    from ..strings import ACTION_CODES
+                    rest_skel, (action, fpid, epoch_change) = _strip_volatile(skeleton)
+                    code = ACTION_CODES.get(action)
+                    if code is not None:
+                        key = _signature(rest_skel)
+                        known = self._sent_skeletons[lane]
+                        fast_id = known.get(key)
+                        if fast_id is None:
+                            known[key] = len(known) + 1              # announced by THIS (pickled) message, usable from the next one
+                            skeleton = dict(skeleton, _skeleton_id=known[key])
+                if fast_id is not None:
+                    import struct
+                    frame[:8] = torch.frombuffer(bytearray((0).to_bytes(8, 'little')), dtype=torch.uint8)       # length 0 = static header
+                    frame[8:40] = torch.frombuffer(bytearray(struct.pack('<IIqqII', _FAST_MAGIC, fast_id, fpid, code, int(epoch_change), 0)),
+                                                   dtype=torch.uint8)
+                    dist.send(frame, dst=peer, group=hgroup, tag=_TAG[lane])
+                    self.header_stats['static'] += 1
+                else:
+                    raw = pickle.dumps(skeleton, protocol=pickle.HIGHEST_PROTOCOL)
+                    # ONE fixed-size frame carries the length and (almost always) the whole pickled skeleton; only a header that
+                    # does not fit is followed by a second message with the rest (was: a length message + a blob message per hop)
+                    frame[:8] = torch.frombuffer(bytearray(len(raw).to_bytes(8, 'little')), dtype=torch.uint8)
+                    head = min(len(raw), _FRAME - 8)
+                    frame[8:8 + head] = torch.frombuffer(bytearray(raw[:head]), dtype=torch.uint8)
+                    dist.send(frame, dst=peer, group=hgroup, tag=_TAG[lane])
+                    if len(raw) > head:
+                        dist.send(torch.frombuffer(bytearray(raw[head:]), dtype=torch.uint8), dst=peer, group=hgroup, tag=_TAG[lane])
+                    self.header_stats['pickled'] += 1
                 if bag:
                     if self.cuda:
                         stream = self.send_stream[lane]
@@ -331,7 +379,24 @@ class DistTransport:
                 if self._stop.is_set():
                     return
                 raise
-            skeleton = pickle.loads(raw)
+            if total == 0:
+                # static header: the skeleton (structure, shapes, dtypes) was announced by an earlier message of this lane
+                import struct
+                from ..strings import CODE_ACTIONS
+                magic, skel_id, fpid, code, epoch_change, _pad = struct.unpack('<IIqqII', frame[8:40].numpy().tobytes())
+                assert magic == _FAST_MAGIC, 'corrupt static header'
+                skeleton = dict(self._known_skeletons[lane][skel_id])
+                skeleton['action'] = CODE_ACTIONS[int(code)]
+                skeleton['forward_pass_id'] = int(fpid)
+                if epoch_change or 'epoch_change' in self._known_volatile.get((lane, skel_id), ()):
+                    skeleton['epoch_change'] = bool(epoch_change)
+            else:
+                skeleton = pickle.loads(raw)
+                skel_id = skeleton.pop('_skeleton_id', None)
+                if skel_id is not None:
+                    rest_skel, _ = _strip_volatile(skeleton)
+                    self._known_skeletons[lane][skel_id] = rest_skel
+                    self._known_volatile[(lane, skel_id)] = tuple(k for k in _VOLATILE if k in skeleton)
             specs: List[Tuple[Tuple[int, ...], torch.dtype]] = []
             _tensor_specs(skeleton, specs)
             bag: List[torch.Tensor] = []

@@ -91,7 +91,8 @@ def main():
                    'master.{}.pt'.format(rank))
     summary = {'rank': rank, 'node_type': node.node_type, 'n_backwards': node.n_backwards,
                'version': node.compute_session.current_version(),
-               'checksum': float(node.compute_session.store.master.double().sum())}
+               'checksum': float(node.compute_session.store.master.double().sum()),
+               'header_stats': dict(getattr(node.transport, 'header_stats', {}))}
     with open('{}.{}'.format(args.out, rank), 'w') as fh:
         json.dump(summary, fh)
     torch.distributed.barrier()

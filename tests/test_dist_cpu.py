@@ -58,6 +58,11 @@ def test_four_stage_pipeline_over_gloo(workdir, free_ports):
     assert all(r['n_backwards'] == 16 for r in res[:3])                  # 2 epochs x 8 batches, one replica
     losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_3.txt'))]
     assert len(losses) == 16 and losses[-1] < losses[0]
+    # steady state travels on the static wire plan: per lane only the first message of a shape is pickled, the rest carry a fixed
+    # binary header (id, action, fpid, flags)
+    for r in res:
+        hs = r['header_stats']
+        assert hs['static'] > 4 * hs['pickled'] > 0, hs
 
 
 @pytest.mark.slow
