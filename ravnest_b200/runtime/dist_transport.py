@@ -220,6 +220,8 @@ class DistTransport:
         self._pending = 0
         self._pending_cv = threading.Condition()
         self._inflight: Dict[str, List[Any]] = {FORWARD: [], BACKWARD: []}
+        self._inflight_since: Dict[str, List[Any]] = {FORWARD: [], BACKWARD: []}     # (work, enqueue time) for the TransferWatchdog
+        self.watchdog = None
         self.send_stream = {FORWARD: None, BACKWARD: None}
         self.recv_stream = {FORWARD: None, BACKWARD: None}
         self.bytes_out = 0
@@ -252,6 +254,16 @@ class DistTransport:
                                  name='{}-{}-{}'.format(self.node.name, fn.__name__, lane))
             t.start()
             self._threads.append(t)
+        timeout = float(os.environ.get('RAVNEST_TRANSFER_TIMEOUT', '0') or 0)
+        if self.cuda and timeout > 0:
+            from .watchdog import TransferWatchdog
+
+            def failed(lane, reason):
+                with self.node._cv:
+                    self.node._errors.append(RuntimeError('{} lane of {}: {}'.format(lane, self.node.name, reason)))
+                    self.node._cv.notify_all()
+            self.watchdog = TransferWatchdog(self, timeout=timeout, on_failure=failed)
+            self.watchdog.start()
 
     def stop(self) -> None:
         if self._stop.is_set():
@@ -261,6 +273,8 @@ class DistTransport:
             if peer is not None:
                 self.send(lane, {'action': ActionTypes.SHUTDOWN, 'forward_pass_id': -1, 'data': {}})
         self.flush(timeout=10)
+        if self.watchdog is not None:
+            self.watchdog.stop()
         self._stop.set()
         for q in self._queues.values():
             q.put(None)
@@ -349,6 +363,10 @@ class DistTransport:
                         keep = self._inflight[lane]
                         keep.extend(works)
                         self._inflight[lane] = [(w, t) for w, t in keep if not w.is_completed()][-64:]
+                        import time as _time
+                        now = _time.time()
+                        self._inflight_since[lane] = [(w, s0) for w, s0 in self._inflight_since[lane] if not w.is_completed()][-64:] + \
+                            [(w, now) for w, _t in works]
                     else:
                         for t in bag:
                             dist.send(t.contiguous(), dst=peer, group=group, tag=_TAG[lane] + 1)

@@ -129,3 +129,33 @@ def test_planner_reference_aliases():
     assert len(res.stages) == 3
     assert ops_plan.remake_proportions([0.2, 0.6, 0.2]) == [0.2, 0.5, 0.3]
     assert ops_plan.CustomTracer is ops_plan.StageTracer
+
+
+def test_transfer_watchdog_flags_stalled_and_failed_transfers():
+    """The dist transport's NCCL watchdog: a transfer pending beyond the timeout, or a work object carrying an exception, becomes an
+    ``on_failure`` callback (the Node turns it into an exception on the training thread)."""
+    import time
+    from ravnest_b200.runtime.watchdog import TransferWatchdog
+
+    class Work:
+        def __init__(self, done, exc=None):
+            self.done, self.exc = done, exc
+
+        def is_completed(self):
+            return self.done
+
+        def exception(self):
+            return self.exc
+
+    class Transport:
+        pass
+
+    tr = Transport()
+    now = time.time()
+    tr._inflight_since = {'forward': [(Work(False), now - 100.0), (Work(True), now - 100.0), (Work(False), now - 1.0)],
+                          'backward': [(Work(True, RuntimeError('ncclRemoteError')), now)]}
+    seen = []
+    wd = TransferWatchdog(tr, timeout=30.0, on_failure=lambda lane, why: seen.append((lane, why)))
+    found = wd.check_once(now)
+    assert sorted(l for l, _ in found) == ['backward', 'forward']
+    assert any('pending for 100 s' in why for _, why in found) and any('ncclRemoteError' in why for _, why in found)
