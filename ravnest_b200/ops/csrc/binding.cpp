@@ -40,10 +40,10 @@ int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W
                    int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream);
 int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean, void* running_var,
                           long long* batches_tracked, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
-                          float momentum, int relu, int training, int param_bf16, int stats_bf16, int num_sms, cudaStream_t stream);
+                          float momentum, int relu, int training, int param_bf16, int stats_bf16, void* relu_mask, int num_sms, cudaStream_t stream);
 int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const void* gamma, const float* mean, const float* invstd,
                            float* sums, void* dx, void* dres, void* dgamma, void* dbeta, long long M, int C, int relu, int param_bf16,
-                           int accumulate, int num_sms, cudaStream_t stream);
+                           int accumulate, const void* relu_mask, int num_sms, cudaStream_t stream);
 int rvn_pool_forward(const void* x, void* y, void* arg, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, int is_max,
                      int num_sms, cudaStream_t stream);
 int rvn_pool_backward(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad,
@@ -606,7 +606,7 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
                                          const torch::Tensor& beta, const c10::optional<torch::Tensor>& mean_in,
                                          const c10::optional<torch::Tensor>& invstd_in, double eps, bool relu, bool training,
                                          const c10::optional<torch::Tensor>& running_mean, const c10::optional<torch::Tensor>& running_var,
-                                         const c10::optional<torch::Tensor>& batches_tracked, double momentum) {
+                                         const c10::optional<torch::Tensor>& batches_tracked, double momentum, bool want_mask) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kBFloat16, "batchnorm expects contiguous bf16 NHWC input");
   const int pbf = is_bf16_or_f32(gamma, "gamma");
@@ -634,10 +634,14 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
       nbt = reinterpret_cast<long long*>(batches_tracked->data_ptr());
     }
   }
+  torch::Tensor mask;                        // ReLU sign bits (one per element) for the backward pass: it then never reads y
+  if (want_mask && relu) mask = torch::empty({static_cast<int64_t>(x.numel() / 8)}, x.options().dtype(torch::kUInt8));
   check(rvn_batchnorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr(), beta.data_ptr(), rm, rv, nbt, mean.data_ptr<float>(),
                               invstd.data_ptr<float>(), sums.data_ptr<float>(), y.data_ptr(), M, C, static_cast<float>(eps),
-                              static_cast<float>(momentum), relu, training, pbf, sbf, sm_count(), cur_stream()),
+                              static_cast<float>(momentum), relu, training, pbf, sbf, mask.defined() ? mask.data_ptr() : nullptr, sm_count(),
+                              cur_stream()),
         "batchnorm_fwd");
+  if (mask.defined()) return {y, mean, invstd, mask};
   return {y, mean, invstd};
 }
 
@@ -646,7 +650,7 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
 std::vector<torch::Tensor> batchnorm_bwd(const torch::Tensor& dy, const c10::optional<torch::Tensor>& y, const torch::Tensor& x,
                                          const torch::Tensor& gamma, const torch::Tensor& mean, const torch::Tensor& invstd, bool relu,
                                          bool want_dres, const c10::optional<torch::Tensor>& grad_gamma,
-                                         const c10::optional<torch::Tensor>& grad_beta) {
+                                         const c10::optional<torch::Tensor>& grad_beta, const c10::optional<torch::Tensor>& relu_mask) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(dy.is_contiguous() && x.is_contiguous(), "batchnorm_bwd expects contiguous tensors");
   const int pbf = is_bf16_or_f32(gamma, "gamma");
@@ -670,10 +674,15 @@ std::vector<torch::Tensor> batchnorm_bwd(const torch::Tensor& dy, const c10::opt
     dg_ptr = dgamma.data_ptr();
     db_ptr = dbeta.data_ptr();
   }
-  const void* y_ptr = relu ? y.value().data_ptr() : nullptr;
+  const void* mask_ptr = nullptr;
+  if (relu && relu_mask.has_value() && relu_mask->defined()) {
+    TORCH_CHECK(relu_mask->scalar_type() == torch::kUInt8 && relu_mask->numel() == x.numel() / 8, "bad relu mask");
+    mask_ptr = relu_mask->data_ptr();
+  }
+  const void* y_ptr = (relu && mask_ptr == nullptr) ? y.value().data_ptr() : nullptr;
   check(rvn_batchnorm_backward(dy.data_ptr(), y_ptr, x.data_ptr(), gamma.data_ptr(), mean.data_ptr<float>(), invstd.data_ptr<float>(),
                                sums.data_ptr<float>(), dx.data_ptr(), want_dres ? dres.data_ptr() : nullptr, dg_ptr, db_ptr, M, C, relu, pbf,
-                               acc ? 1 : 0, sm_count(), cur_stream()),
+                               acc ? 1 : 0, mask_ptr, sm_count(), cur_stream()),
         "batchnorm_bwd");
   return {dx, dres, dgamma, dbeta};
 }
@@ -834,8 +843,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("transposed"), py::arg("out_h"), py::arg("out_w"), py::arg("pad_w") = -1);
   m.def("pool_fwd", &pool_fwd);
   m.def("pool_bwd", &pool_bwd);
-  m.def("batchnorm_fwd", &batchnorm_fwd);
-  m.def("batchnorm_bwd", &batchnorm_bwd);
+  m.def("batchnorm_fwd", &batchnorm_fwd, py::arg("x"), py::arg("res"), py::arg("gamma"), py::arg("beta"), py::arg("mean_in"), py::arg("invstd_in"),
+        py::arg("eps"), py::arg("relu"), py::arg("training"), py::arg("running_mean"), py::arg("running_var"), py::arg("batches_tracked"),
+        py::arg("momentum"), py::arg("want_mask") = false);
+  m.def("batchnorm_bwd", &batchnorm_bwd, py::arg("dy"), py::arg("y"), py::arg("x"), py::arg("gamma"), py::arg("mean"), py::arg("invstd"),
+        py::arg("relu"), py::arg("want_dres"), py::arg("grad_gamma") = py::none(), py::arg("grad_beta") = py::none(),
+        py::arg("relu_mask") = py::none());
   m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc, py::arg("dy"), py::arg("x"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"),
         py::arg("dil"), py::arg("pad_w") = -1);
   m.def("fmha_fwd", &fmha_fwd);

@@ -104,7 +104,8 @@ __global__ void rvn_bn_finalize(const float* __restrict__ sums, float* __restric
 __global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                     const void* __restrict__ gamma, const void* __restrict__ beta,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                    __nv_bfloat16* __restrict__ y, size_t nvec, int C, int relu, int param_bf16) {
+                                                    __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ relu_mask, size_t nvec, int C,
+                                                    int relu, int param_bf16) {
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int c0 = static_cast<int>(tid % (C / 8)) * 8;
@@ -130,6 +131,12 @@ __global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restr
       for (int j = 0; j < 8; ++j) f[j] += rf[j];
     }
     if (relu) {
+      if (relu_mask != nullptr) {                   // one bit per element: what backward needs of y (1/16 of its bytes)
+        unsigned m = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+        relu_mask[i] = static_cast<uint8_t>(m);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
     }
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                          const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                                                          const float* __restrict__ invstd, float* __restrict__ sums, size_t nvec, int C,
-                                                         int relu) {
+                                                         int relu, const uint8_t* __restrict__ relu_mask) {
   extern __shared__ float sh[];
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -160,12 +167,18 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __
     a.to_float(g);
     b.to_float(xv);
     if (relu) {
-      v8 c;
-      float yv[8];
-      c.load(y + i * 8);
-      c.to_float(yv);
+      if (relu_mask != nullptr) {                   // the forward's bitmask: 1 byte instead of the 16-byte y vector
+        const unsigned m = relu_mask[i];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+        for (int j = 0; j < 8; ++j) g[j] = ((m >> j) & 1u) ? g[j] : 0.f;
+      } else {
+        v8 c;
+        float yv[8];
+        c.load(y + i * 8);
+        c.to_float(yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -189,7 +202,7 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __r
                                                         const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
                                                         __nv_bfloat16* __restrict__ dres, void* __restrict__ dgamma,
                                                         void* __restrict__ dbeta, size_t nvec, int C, float count, int relu,
-                                                        int param_bf16, int accumulate) {
+                                                        int param_bf16, int accumulate, const uint8_t* __restrict__ relu_mask) {
   if (blockIdx.x == 0 && dgamma != nullptr) {       // parameter gradients in the parameter dtype, optionally accumulated in place
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const float dg = sums[C + c] + (accumulate ? ldp(dgamma, c, param_bf16) : 0.f);
@@ -218,12 +231,18 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __r
     a.to_float(g);
     b.to_float(xv);
     if (relu) {
-      v8 c;
-      float yv[8];
-      c.load(y + i * 8);
-      c.to_float(yv);
+      if (relu_mask != nullptr) {
+        const unsigned m = relu_mask[i];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+        for (int j = 0; j < 8; ++j) g[j] = ((m >> j) & 1u) ? g[j] : 0.f;
+      } else {
+        v8 c;
+        float yv[8];
+        c.load(y + i * 8);
+        c.to_float(yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+      }
     }
     if (dres != nullptr) {
       o.from_float(g);
@@ -254,7 +273,7 @@ static int bn_grid(size_t nvec, int C, int num_sms, int waves) {
 extern "C" int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean,
                                      void* running_var, long long* batches_tracked, float* mean, float* invstd, float* sums, void* y,
                                      long long M, int C, float eps, float momentum, int relu, int training, int param_bf16,
-                                     int stats_bf16, int num_sms, cudaStream_t stream) {
+                                     int stats_bf16, void* relu_mask, int num_sms, cudaStream_t stream) {
   if (C % 8 != 0 || C > 4096) return -2;
   const size_t nvec = static_cast<size_t>(M) * C / 8;
   using T = const __nv_bfloat16*;
@@ -264,23 +283,24 @@ extern "C" int rvn_batchnorm_forward(const void* x, const void* res, const void*
     rvn::rvn_bn_finalize<<<(C + 127) / 128, 128, 0, stream>>>(sums, mean, invstd, running_mean, running_var, batches_tracked,
                                                                static_cast<float>(M), eps, momentum, C, stats_bf16);
   }
-  rvn::rvn_bn_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)x, (T)res, gamma, beta, mean, invstd, (__nv_bfloat16*)y, nvec, C,
-                                                                      relu, param_bf16);
+  rvn::rvn_bn_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)x, (T)res, gamma, beta, mean, invstd, (__nv_bfloat16*)y,
+                                                                      static_cast<uint8_t*>(relu_mask), nvec, C, relu, param_bf16);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 // sums (2*C fp32) holds {dbeta = sum dz, dgamma = sum dz*xhat} on return
 extern "C" int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const void* gamma, const float* mean,
                                       const float* invstd, float* sums, void* dx, void* dres, void* dgamma, void* dbeta, long long M,
-                                      int C, int relu, int param_bf16, int accumulate, int num_sms, cudaStream_t stream) {
+                                      int C, int relu, int param_bf16, int accumulate, const void* relu_mask, int num_sms,
+                                      cudaStream_t stream) {
   if (C % 8 != 0 || C > 4096) return -2;
   const size_t nvec = static_cast<size_t>(M) * C / 8;
   using T = const __nv_bfloat16*;
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream);
   rvn::rvn_bn_bwd_reduce<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)dy, (T)y, (T)x, mean, invstd, sums, nvec, C,
-                                                                                            relu);
+                                                                                            relu, static_cast<const uint8_t*>(relu_mask));
   rvn::rvn_bn_bwd_apply<<<bn_grid(nvec, C, num_sms, 8), 256, 0, stream>>>((T)dy, (T)y, (T)x, gamma, mean, invstd, sums, (__nv_bfloat16*)dx,
                                                                           (__nv_bfloat16*)dres, dgamma, dbeta, nvec, C, static_cast<float>(M),
-                                                                          relu, param_bf16, accumulate);
+                                                                          relu, param_bf16, accumulate, static_cast<const uint8_t*>(relu_mask));
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -590,6 +590,7 @@ IMPLICIT_GEMM_CONV = True
 NATIVE_CONV_WGRAD = True
 STRIDED_1X1_IMPLICIT = True
 RECTANGULAR_CONV = True
+BN_RELU_BITMASK = True
 
 
 class _BatchNormAct(torch.autograd.Function):
@@ -599,21 +600,23 @@ class _BatchNormAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, relu, eps, running_mean, running_var, batches_tracked, momentum):
-        y, mean, invstd = C().batchnorm_fwd(x, residual, weight, bias, None, None, eps, relu, True, running_mean, running_var,
-                                            batches_tracked, momentum)
+        outs = C().batchnorm_fwd(x, residual, weight, bias, None, None, eps, relu, True, running_mean, running_var,
+                                 batches_tracked, momentum, BN_RELU_BITMASK and relu)
+        y, mean, invstd = outs[0], outs[1], outs[2]
+        mask = outs[3] if len(outs) > 3 else None          # ReLU sign bits: backward reads 1 byte per 8 elements instead of y
         calls['batchnorm_fwd'] += 1
         ctx.relu, ctx.has_res = relu, residual is not None
-        ctx.save_for_backward(x, y if relu else None, weight, bias, mean, invstd)
+        ctx.save_for_backward(x, y if (relu and mask is None) else None, weight, bias, mean, invstd, mask)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        x, y, weight, bias, mean, invstd, mask = ctx.saved_tensors
         gg, gb = weight.grad, bias.grad
         acc = (ACCUMULATE_INTO_GRAD and gg is not None and gb is not None and gg.dtype == weight.dtype and gb.dtype == weight.dtype
                and gg.is_contiguous() and gb.is_contiguous() and ctx.needs_input_grad[1] and ctx.needs_input_grad[2])
         dx, dres, dgamma, dbeta = C().batchnorm_bwd(dy.contiguous(), y, x, weight, mean, invstd, ctx.relu, ctx.has_res and ctx.relu,
-                                                    gg if acc else None, gb if acc else None)
+                                                    gg if acc else None, gb if acc else None, mask)
         calls['batchnorm_bwd'] += 1
         if ctx.has_res and not ctx.relu:
             dres = dy
