@@ -56,7 +56,24 @@ __global__ void __launch_bounds__(256) rvn_bn_stats(const __nv_bfloat16* __restr
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
   size_t i = tid;
-  for (; i + stride < nvec; i += 2 * stride) {      // two independent loads in flight
+  for (; i + 3 * stride < nvec; i += 4 * stride) {  // four independent loads in flight
+    v8 a, b, c, d;
+    float fa[8], fb[8], fc[8], fd[8];
+    a.load(x + i * 8);
+    b.load(x + (i + stride) * 8);
+    c.load(x + (i + 2 * stride) * 8);
+    d.load(x + (i + 3 * stride) * 8);
+    a.to_float(fa);
+    b.to_float(fb);
+    c.to_float(fc);
+    d.to_float(fd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += (fa[j] + fb[j]) + (fc[j] + fd[j]);
+      q[j] += (fa[j] * fa[j] + fb[j] * fb[j]) + (fc[j] * fc[j] + fd[j] * fd[j]);
+    }
+  }
+  for (; i + stride < nvec; i += 2 * stride) {
     v8 a, b;
     float fa[8], fb[8];
     a.load(x + i * 8);
@@ -74,10 +91,26 @@ __global__ void __launch_bounds__(256) rvn_bn_stats(const __nv_bfloat16* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += fa[j]; q[j] += fa[j] * fa[j]; }
   }
+  // narrow layers (C = 64 / 128: the LARGEST activations) put 32 / (C/8) lanes of a warp on the same channel group: fold those with
+  // shuffles first, otherwise 32 - 256 threads of the CTA hammer the same shared-memory word with (CAS-emulated) float atomics
+  const int groups = C / 8;
+  bool owner = true;
+  if (groups < 32 && (32 % groups) == 0) {
+    for (int off = groups; off < 32; off <<= 1) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sh[c0 + j], s[j]);
-    atomicAdd(&sh[C + c0 + j], q[j]);
+      for (int j = 0; j < 8; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+      }
+    }
+    owner = (threadIdx.x & 31) < groups;
+  }
+  if (owner) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[c0 + j], s[j]);
+      atomicAdd(&sh[C + c0 + j], q[j]);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(&sums[c], sh[c]);
@@ -101,7 +134,7 @@ __global__ void rvn_bn_finalize(const float* __restrict__ sums, float* __restric
 }
 
 // y = act((x - mean) * invstd * gamma + beta + residual)
-__global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+__global__ void __launch_bounds__(256, 5) rvn_bn_apply(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                     const void* __restrict__ gamma, const void* __restrict__ beta,
                                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                                     __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ relu_mask, size_t nvec, int C,
@@ -115,17 +148,14 @@ __global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restr
     sc[j] = ldp(gamma, c0 + j, param_bf16) * invstd[c0 + j];
     sf[j] = ldp(beta, c0 + j, param_bf16) - mean[c0 + j] * sc[j];
   }
-  for (size_t i = tid; i < nvec; i += stride) {
-    v8 a, o;
+  auto finish = [&](size_t i, const v8& a, const v8& r) {
+    v8 o;
     float f[8];
-    a.load(x + i * 8);
     a.to_float(f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sf[j]);
     if (res != nullptr) {
-      v8 r;
       float rf[8];
-      r.load(res + i * 8);
       r.to_float(rf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] += rf[j];
@@ -142,11 +172,29 @@ __global__ void __launch_bounds__(256) rvn_bn_apply(const __nv_bfloat16* __restr
     }
     o.from_float(f);
     o.store(y + i * 8);
+  };
+  size_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {      // all loads of two vectors in flight before either is consumed (pure stream:
+    v8 a0, a1, r0, r1;                              // bytes in flight per SM decide the bandwidth)
+    a0.load(x + i * 8);
+    a1.load(x + (i + stride) * 8);
+    if (res != nullptr) {
+      r0.load(res + i * 8);
+      r1.load(res + (i + stride) * 8);
+    }
+    finish(i, a0, r0);
+    finish(i + stride, a1, r1);
+  }
+  if (i < nvec) {
+    v8 a0, r0;
+    a0.load(x + i * 8);
+    if (res != nullptr) r0.load(res + i * 8);
+    finish(i, a0, r0);
   }
 }
 
 // sums[0..C) += sum dz ; sums[C..2C) += sum dz * xhat      with dz = dy * (y > 0) when relu
-__global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(256, 4) rvn_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                          const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                                                          const float* __restrict__ invstd, float* __restrict__ sums, size_t nvec, int C,
                                                          int relu, const uint8_t* __restrict__ relu_mask) {
@@ -159,22 +207,16 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __
   float mu[8], is[8], s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; s[j] = 0.f; q[j] = 0.f; }
-  for (size_t i = tid; i < nvec; i += stride) {
-    v8 a, b;
+  auto accumulate_vec = [&](const v8& a, const v8& b, const v8& c, unsigned m) {
     float g[8], xv[8];
-    a.load(dy + i * 8);
-    b.load(x + i * 8);
     a.to_float(g);
     b.to_float(xv);
     if (relu) {
       if (relu_mask != nullptr) {                   // the forward's bitmask: 1 byte instead of the 16-byte y vector
-        const unsigned m = relu_mask[i];
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = ((m >> j) & 1u) ? g[j] : 0.f;
       } else {
-        v8 c;
         float yv[8];
-        c.load(y + i * 8);
         c.to_float(yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
@@ -185,18 +227,58 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_reduce(const __nv_bfloat16* __
       s[j] += g[j];
       q[j] += g[j] * (xv[j] - mu[j]) * is[j];
     }
+  };
+  const bool use_y = relu && relu_mask == nullptr;
+  const bool use_m = relu && relu_mask != nullptr;
+  size_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {      // two vectors: 4 - 6 independent 16-byte loads in flight per thread
+    v8 a0, b0, c0v, a1, b1, c1v;
+    unsigned m0 = 0, m1 = 0;
+    a0.load(dy + i * 8);
+    b0.load(x + i * 8);
+    a1.load(dy + (i + stride) * 8);
+    b1.load(x + (i + stride) * 8);
+    if (use_y) { c0v.load(y + i * 8); c1v.load(y + (i + stride) * 8); }
+    if (use_m) { m0 = relu_mask[i]; m1 = relu_mask[i + stride]; }
+    accumulate_vec(a0, b0, c0v, m0);
+    accumulate_vec(a1, b1, c1v, m1);
   }
+  if (i < nvec) {
+    v8 a0, b0, c0v;
+    unsigned m0 = 0;
+    a0.load(dy + i * 8);
+    b0.load(x + i * 8);
+    if (use_y) c0v.load(y + i * 8);
+    if (use_m) m0 = relu_mask[i];
+    accumulate_vec(a0, b0, c0v, m0);
+  }
+  // narrow layers (C = 64 / 128: the LARGEST activations) put 32 / (C/8) lanes of a warp on the same channel group: fold those with
+  // shuffles first, otherwise 32 - 256 threads of the CTA hammer the same shared-memory word with (CAS-emulated) float atomics
+  const int groups = C / 8;
+  bool owner = true;
+  if (groups < 32 && (32 % groups) == 0) {
+    for (int off = groups; off < 32; off <<= 1) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sh[c0 + j], s[j]);
-    atomicAdd(&sh[C + c0 + j], q[j]);
+      for (int j = 0; j < 8; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+      }
+    }
+    owner = (threadIdx.x & 31) < groups;
+  }
+  if (owner) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[c0 + j], s[j]);
+      atomicAdd(&sh[C + c0 + j], q[j]);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(&sums[c], sh[c]);
 }
 
 // dx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dres = dz (gradient of the fused residual branch)
-__global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) rvn_bn_bwd_apply(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                         const __nv_bfloat16* __restrict__ x, const void* __restrict__ gamma,
                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
                                                         const float* __restrict__ sums, __nv_bfloat16* __restrict__ dx,
@@ -223,22 +305,17 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __r
     m1[j] = sums[c0 + j] / count;
     m2[j] = sums[C + c0 + j] / count;
   }
-  for (size_t i = tid; i < nvec; i += stride) {
-    v8 a, b, o;
+  auto finish = [&](size_t i, const v8& a, const v8& b, const v8& c, unsigned m) {
+    v8 o;
     float g[8], xv[8];
-    a.load(dy + i * 8);
-    b.load(x + i * 8);
     a.to_float(g);
     b.to_float(xv);
     if (relu) {
       if (relu_mask != nullptr) {
-        const unsigned m = relu_mask[i];
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = ((m >> j) & 1u) ? g[j] : 0.f;
       } else {
-        v8 c;
         float yv[8];
-        c.load(y + i * 8);
         c.to_float(yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
@@ -252,6 +329,30 @@ __global__ void __launch_bounds__(256) rvn_bn_bwd_apply(const __nv_bfloat16* __r
     for (int j = 0; j < 8; ++j) g[j] = gi[j] * (g[j] - m1[j] - (xv[j] - mu[j]) * is[j] * m2[j]);
     o.from_float(g);
     o.store(dx + i * 8);
+  };
+  const bool use_y = relu && relu_mask == nullptr;
+  const bool use_m = relu && relu_mask != nullptr;
+  size_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {
+    v8 a0, b0, c0v, a1, b1, c1v;
+    unsigned k0 = 0, k1 = 0;
+    a0.load(dy + i * 8);
+    b0.load(x + i * 8);
+    a1.load(dy + (i + stride) * 8);
+    b1.load(x + (i + stride) * 8);
+    if (use_y) { c0v.load(y + i * 8); c1v.load(y + (i + stride) * 8); }
+    if (use_m) { k0 = relu_mask[i]; k1 = relu_mask[i + stride]; }
+    finish(i, a0, b0, c0v, k0);
+    finish(i + stride, a1, b1, c1v, k1);
+  }
+  if (i < nvec) {
+    v8 a0, b0, c0v;
+    unsigned k0 = 0;
+    a0.load(dy + i * 8);
+    b0.load(x + i * 8);
+    if (use_y) c0v.load(y + i * 8);
+    if (use_m) k0 = relu_mask[i];
+    finish(i, a0, b0, c0v, k0);
   }
 }
 
