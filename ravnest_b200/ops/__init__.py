@@ -160,9 +160,10 @@ def cross_entropy(logits, target, ignore_index=-100):
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     """2-D convolution.  On CUDA (bf16, channels_last) pointwise convolutions run on the tcgen05 GEMM — in NHWC a 1x1
-    convolution IS ``[N*H*W, Cin] x [Cout, Cin]^T`` with zero data movement — and square k x k convolutions (stride 1 / 2) on the
-    implicit-GEMM kernel (forward, stride-1 dgrad, split-K wgrad).  Remaining library cases (cuDNN): Cin % 8 != 0 (the RGB stem),
-    rectangular kernels, stride-2 data gradients, groups > 1 — counted in ``ops.native.fallbacks``."""
+    convolution IS ``[N*H*W, Cin] x [Cout, Cin]^T`` with zero data movement (strided 1x1: the implicit-GEMM kernel, whose TMA
+    element strides do the sub-sampling) — and square or rectangular kh x kw convolutions (stride 1 / 2, per-axis padding) on the
+    implicit-GEMM kernel (forward, stride-1 dgrad, split-K wgrad with bulk reductions).  Remaining library cases (cuDNN):
+    Cin % 8 != 0 (the RGB stem), stride-2 data gradients, groups > 1, dilation — counted in ``ops.native.fallbacks``."""
     if _native(x, weight):
         from . import native
         return native.conv2d(x, weight, bias, stride, padding, dilation, groups)

@@ -10,7 +10,7 @@ export RVN_BENCH_WATCHDOG=${WD:-150}
 OUT=gpurun_out/overlap_sweep_${MODEL}_${TOPO}.txt; : > $OUT
 for b in $BATCHES; do
   timeout -k 10 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 300)) \
-      bench.py --gpus $N --model $MODEL --topology $TOPO --batch $b --steps 32 --warmup 8 --no-e2e > gpurun_out/sweep_${MODEL}_b$b.log 2>&1
+      bench.py --gpus $N --model $MODEL --topology $TOPO --batch $b --steps 32 --warmup 8 --no-e2e --rebalance 0 > gpurun_out/sweep_${MODEL}_b$b.log 2>&1
   grep '^{"metric"' gpurun_out/sweep_${MODEL}_b$b.log | tail -n 1 | python -c "
 import json, sys
 line = sys.stdin.read().strip()
