@@ -21,6 +21,7 @@ Design differences (B200-first):
   * optimizer step runs over flat buffers and (on CUDA) through the fused all-reduce+update kernel
     in ``ravnest_b200.parallel.fused_optim``.
 """
+import os
 import threading
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
@@ -75,6 +76,10 @@ class Compute:
         self.is_last = is_last
         self.loss_filename = loss_filename
         self.store = ParamStore(model, self.device, n_slots=cluster_length + 2, compute_dtype=compute_dtype)
+        if self.device.type == 'cuda':
+            from . import ops
+            if ops.backend() == 'native' and os.environ.get('RAVNEST_WGRAD_STAGING', '1') != '0':
+                self.store.enable_wgrad_staging()       # fp32 accumulator for convolution weight gradients, flushed per update
         self.flights: Dict[int, Flight] = {}
         self.n_backwards = 0
         self.n_updates = 0
@@ -118,6 +123,7 @@ class Compute:
     def optimizer_step(self) -> None:
         """Apply the accumulated gradient to the newest weights and publish a new version."""
         with torch.no_grad():
+            self.store.flush_wgrad()                # staged convolution weight gradients -> gradient bucket (no-op without staging)
             if self._fused is not None:
                 self._fused.step()              # all-reduce (+) update (+) cast-publish in one kernel
             else:
@@ -158,7 +164,8 @@ class Compute:
                     a = a.to(self.device, non_blocking=True)
                 if a.is_floating_point() and a.dtype != self.store.compute_dtype and a.dtype in (torch.float32, torch.float16, torch.bfloat16):
                     a = a.to(self.store.compute_dtype)
-                if self.channels_last and a.dim() == 4 and a.is_floating_point():
+                if self.channels_last and a.dim() == 4 and a.is_floating_point() and a.shape[1] >= 8:
+                    # (image batches — fewer than 8 channels — stay as they are: the stem's pack kernel reads any layout)
                     a = a.contiguous(memory_format=torch.channels_last)
                 if need_grad and a.is_floating_point():
                     a.requires_grad_(True)

@@ -19,7 +19,8 @@ class Bottleneck(nn.Module):
     def __init__(self, inplanes, planes, stride=1, downsample=False):
         super().__init__()
         out = planes * self.expansion
-        self.conv1 = rnn.Conv2d(inplanes, planes, 1, bias=False)
+        # identity blocks: conv1 also hands out the skip branch, so its data gradient lands IN the skip gradient (no add kernel)
+        self.conv1 = rnn.Conv2d(inplanes, planes, 1, bias=False, fork=not downsample)
         self.bn1 = rnn.BatchNorm2d(planes, relu=True)
         self.conv2 = rnn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
         self.bn2 = rnn.BatchNorm2d(planes, relu=True)
@@ -30,9 +31,12 @@ class Bottleneck(nn.Module):
             self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False), rnn.BatchNorm2d(out))
 
     def forward(self, x):
-        y = self.bn1(self.conv1(x))
-        y = self.bn2(self.conv2(y))
-        identity = x if self.downsample is None else self.downsample(x)
+        if self.conv1.fork:
+            both = self.conv1(x)
+            y, identity = both[0], both[1]
+        else:
+            y, identity = self.conv1(x), self.downsample(x)
+        y = self.bn2(self.conv2(self.bn1(y)))
         return self.bn3(self.conv3(y), identity)
 
 

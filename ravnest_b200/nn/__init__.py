@@ -97,9 +97,22 @@ class SelfAttention(nn.Module):
 
 class Conv2d(nn.Conv2d):
     """Drop-in ``nn.Conv2d`` (same parameters / state dict).  Pointwise convolutions of channels_last bf16 activations run
-    on the tcgen05 GEMM; everything else goes to cuDNN."""
+    on the tcgen05 GEMM, spatial ones on the implicit-GEMM kernel, the rest on cuDNN (``ops.conv2d``).
+
+    ``fork=True`` (bias-free stride-1 pointwise convolutions only) makes ``forward`` return ``(conv(x), x)``: the convolution
+    that opens a residual block hands the block its identity branch, and in backward adds its data gradient into the skip
+    connection's gradient inside the GEMM epilogue (``ops.conv1x1_fork``)."""
+
+    def __init__(self, *args, fork=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.fork = bool(fork)
+        if self.fork and (self.kernel_size != (1, 1) or self.stride != (1, 1) or self.padding != (0, 0) or self.bias is not None
+                          or self.groups != 1):
+            raise ValueError('fork=True needs a bias-free, stride-1, ungrouped 1x1 convolution')
 
     def forward(self, x):
+        if self.fork:
+            return ops.conv1x1_fork(x, self.weight)
         if isinstance(self.padding, str) or self.padding_mode != 'zeros':
             return super().forward(x)
         return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)

@@ -478,6 +478,9 @@ def split_graph(gm: fx.GraphModule, boundaries: Sequence[fx.Node], input_names: 
             stage_of[node] = n_stages - 1
             continue
         stage_of[node] = current
+        if node.op == 'call_function' and node.target is operator.getitem and isinstance(node.args[0], fx.Node) \
+                and node.args[0] in stage_of:
+            stage_of[node] = stage_of[node.args[0]]      # a tuple never crosses a cut: its elements are unpacked where it is made
     # parameters / constants referenced with get_attr live with their first consumer
     for node in gm.graph.nodes:
         if node.op == 'get_attr' and node.users:

@@ -38,6 +38,15 @@ int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, in
                      int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, int num_sms, cudaStream_t stream);
 int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
                    int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream);
+int rvn_conv_forward_strided(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho, int Wo,
+                             int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, long long xs_w, long long xs_h,
+                             long long xs_n, int num_sms, cudaStream_t stream);
+int rvn_conv_wgrad_strided(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
+                           int stride, int pad, int pad_w, int dil, long long xs_w, long long xs_h, long long xs_n, int num_sms,
+                           cudaStream_t stream);
+int rvn_stem_pack(const void* x, int x_is_bf16, void* out, int N, int C, int H, int W, int Hp, int Wp, int pad_h, int pad_w, long long sn,
+                  long long sc, long long sh, long long sw, int num_sms, cudaStream_t stream);
+int rvn_wgrad_flush(float* acc, void* grad, int grad_is_bf16, size_t n, int num_sms, cudaStream_t stream);
 int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean, void* running_var,
                           long long* batches_tracked, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
                           float momentum, int relu, int training, int param_bf16, int stats_bf16, void* relu_mask, int num_sms, cudaStream_t stream);
@@ -547,12 +556,25 @@ torch::Tensor fmha_bwd(const torch::Tensor& qkv, const torch::Tensor& out, const
 
 // x: [N,H,W,Cin] bf16 contiguous (NHWC); w: [Cout,R,S,Cin] contiguous.  transposed=false: y = conv(x, w) -> [N,Ho,Wo,Cout].
 // transposed=true (dgrad, stride 1): x is dy [N,Ho,Wo,Cout], result is dx [N,H,W,Cin]; `out_hw` gives the result's H, W.
+// element strides (W, H, N) of an NHWC activation view for the TMA descriptor: {0, 0, 0} when dense.  Views with a unit channel
+// stride and 16-byte-multiple outer strides are consumed in place — including OVERLAPPING ones (the small-Cin stem, conv_aux.cu)
+static void nhwc_strides(const torch::Tensor& x, long long* st) {
+  st[0] = st[1] = st[2] = 0;
+  if (x.is_contiguous()) return;
+  TORCH_CHECK(x.dim() == 4 && x.stride(3) == 1 && x.stride(2) % 8 == 0 && x.stride(1) % 8 == 0 && x.stride(0) % 8 == 0 && x.stride(2) > 0 &&
+                  reinterpret_cast<uintptr_t>(x.data_ptr()) % 16 == 0,
+              "strided NHWC input: channel stride must be 1, the other strides multiples of 8 elements, the base 16-byte aligned");
+  st[0] = x.stride(2); st[1] = x.stride(1); st[2] = x.stride(0);
+}
+
 torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c10::optional<torch::Tensor>& bias, int64_t stride,
                         int64_t pad, int64_t dil, bool relu, bool transposed, int64_t out_h, int64_t out_w, int64_t pad_w) {
   if (pad_w < 0) pad_w = pad;          // square padding unless a horizontal one is given (rectangular kernels)
   c10::cuda::CUDAGuard guard(x.device());
-  TORCH_CHECK(x.is_contiguous() && w.is_contiguous() && x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 &&
-              w.scalar_type() == torch::kBFloat16, "conv_nhwc expects contiguous bf16 NHWC activations and [Cout,R,S,Cin] weights");
+  TORCH_CHECK(w.is_contiguous() && x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 &&
+              w.scalar_type() == torch::kBFloat16, "conv_nhwc expects bf16 NHWC activations and contiguous [Cout,R,S,Cin] weights");
+  long long xs[3];
+  nhwc_strides(x, xs);
   const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
   const int R = w.size(1), S = w.size(2);
   const int k_ch = transposed ? w.size(0) : w.size(3);      // channels reduced over
@@ -570,27 +592,68 @@ torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c1
   const void* bias_ptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
   const int eff_pad = transposed ? static_cast<int>(dil * (R - 1) - pad) : static_cast<int>(pad);
   const int eff_pad_w = transposed ? static_cast<int>(dil * (S - 1) - pad_w) : static_cast<int>(pad_w);
-  check(rvn_conv_forward(x.data_ptr(), w.data_ptr(), y.data_ptr(), bias_ptr, relu, N, H, W, k_ch, Ho, Wo, n_ch, R, S, static_cast<int>(stride),
-                         eff_pad, eff_pad_w, static_cast<int>(dil), transposed, sm_count(), cur_stream()),
+  check(rvn_conv_forward_strided(x.data_ptr(), w.data_ptr(), y.data_ptr(), bias_ptr, relu, N, H, W, k_ch, Ho, Wo, n_ch, R, S,
+                                 static_cast<int>(stride), eff_pad, eff_pad_w, static_cast<int>(dil), transposed, xs[0], xs[1], xs[2], sm_count(),
+                                 cur_stream()),
         "conv_forward");
   return y;
 }
 
-// dy [N,Ho,Wo,Cout], x [N,H,W,Cin] (NHWC bf16) -> dW [Cout,R,S,Cin] fp32
+// dy [N,Ho,Wo,Cout], x [N,H,W,Cin] (NHWC bf16, x possibly a strided view) -> dW [Cout,R,S,Cin] fp32.  With `acc` (a contiguous fp32
+// tensor of that many elements, e.g. the stage's persistent weight-gradient accumulator) the gradient is ADDED into it and returned
 torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t dil,
-                              int64_t pad_w) {
+                              int64_t pad_w, const c10::optional<torch::Tensor>& acc) {
   if (pad_w < 0) pad_w = pad;
   c10::cuda::CUDAGuard guard(x.device());
-  TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dy.scalar_type() == torch::kBFloat16 && x.scalar_type() == torch::kBFloat16,
-              "conv_wgrad_nhwc expects contiguous bf16 NHWC tensors");
+  TORCH_CHECK(dy.is_contiguous() && x.dim() == 4 && dy.scalar_type() == torch::kBFloat16 && x.scalar_type() == torch::kBFloat16,
+              "conv_wgrad_nhwc expects bf16 NHWC tensors (dy contiguous)");
+  long long xs[3];
+  nhwc_strides(x, xs);
   const int N = x.size(0), H = x.size(1), W = x.size(2), Cin = x.size(3);
   const int Ho = dy.size(1), Wo = dy.size(2), Cout = dy.size(3);
   TORCH_CHECK(Cin % 8 == 0 && Cout % 8 == 0, "channel counts must be multiples of 8");
-  auto dw = torch::zeros({Cout, R, S, Cin}, x.options().dtype(torch::kFloat32));
-  check(rvn_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), N, H, W, Cin, Ho, Wo, Cout, static_cast<int>(R), static_cast<int>(S),
-                       static_cast<int>(stride), static_cast<int>(pad), static_cast<int>(pad_w), static_cast<int>(dil), sm_count(), cur_stream()),
+  torch::Tensor dw;
+  if (acc.has_value() && acc->defined()) {
+    TORCH_CHECK(acc->is_contiguous() && acc->scalar_type() == torch::kFloat32 && acc->numel() == static_cast<int64_t>(Cout) * R * S * Cin &&
+                    acc->device() == x.device() && reinterpret_cast<uintptr_t>(acc->data_ptr()) % 16 == 0,
+                "acc must be a contiguous, 16-byte aligned fp32 tensor of Cout*R*S*Cin elements");
+    dw = *acc;
+  } else {
+    dw = torch::zeros({Cout, R, S, Cin}, x.options().dtype(torch::kFloat32));
+  }
+  check(rvn_conv_wgrad_strided(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), N, H, W, Cin, Ho, Wo, Cout, static_cast<int>(R),
+                               static_cast<int>(S), static_cast<int>(stride), static_cast<int>(pad), static_cast<int>(pad_w),
+                               static_cast<int>(dil), xs[0], xs[1], xs[2], sm_count(), cur_stream()),
         "conv_wgrad");
   return dw;
+}
+
+// [N, C <= 8, H, W]-shaped images (any strides, bf16 or fp32) -> zero-bordered dense [N, Hp, Wp, 8] bf16 (conv_aux.cu)
+torch::Tensor stem_pack(const torch::Tensor& x, int64_t pad_h, int64_t pad_w, int64_t Hp, int64_t Wp) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.size(1) >= 1 && x.size(1) <= 8 &&
+                  (x.scalar_type() == torch::kBFloat16 || x.scalar_type() == torch::kFloat32),
+              "stem_pack expects an [N, C <= 8, H, W] bf16 / fp32 CUDA tensor");
+  TORCH_CHECK(Hp >= x.size(2) + pad_h && Wp >= x.size(3) + pad_w && pad_h >= 0 && pad_w >= 0, "padded extent smaller than the image");
+  auto out = torch::empty({x.size(0), Hp, Wp, 8}, x.options().dtype(torch::kBFloat16));
+  check(rvn_stem_pack(x.data_ptr(), x.scalar_type() == torch::kBFloat16, out.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3),
+                      static_cast<int>(Hp), static_cast<int>(Wp), static_cast<int>(pad_h), static_cast<int>(pad_w), x.stride(0), x.stride(1),
+                      x.stride(2), x.stride(3), sm_count(), cur_stream()),
+        "stem_pack");
+  return out;
+}
+
+// grad += acc; acc = 0   (fp32 convolution-weight-gradient accumulator -> flat gradient bucket, conv_aux.cu)
+void wgrad_flush(torch::Tensor acc, torch::Tensor grad) {
+  c10::cuda::CUDAGuard guard(acc.device());
+  TORCH_CHECK(acc.is_cuda() && acc.is_contiguous() && grad.is_contiguous() && acc.scalar_type() == torch::kFloat32 &&
+                  acc.numel() == grad.numel() && acc.numel() % 8 == 0 &&
+                  (grad.scalar_type() == torch::kBFloat16 || grad.scalar_type() == torch::kFloat32) &&
+                  reinterpret_cast<uintptr_t>(acc.data_ptr()) % 32 == 0 && reinterpret_cast<uintptr_t>(grad.data_ptr()) % 16 == 0,
+              "wgrad_flush expects a contiguous fp32 accumulator and a bf16 / fp32 gradient bucket of the same (multiple of 8) length");
+  check(rvn_wgrad_flush(acc.data_ptr<float>(), grad.data_ptr(), grad.scalar_type() == torch::kBFloat16, static_cast<size_t>(acc.numel()),
+                        sm_count(), cur_stream()),
+        "wgrad_flush");
 }
 
 // x: [..., C] bf16 contiguous (NHWC flattened); gamma / beta in the parameter dtype (bf16 or fp32), mean / invstd fp32 [C].
@@ -850,7 +913,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("relu"), py::arg("want_dres"), py::arg("grad_gamma") = py::none(), py::arg("grad_beta") = py::none(),
         py::arg("relu_mask") = py::none());
   m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc, py::arg("dy"), py::arg("x"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"),
-        py::arg("dil"), py::arg("pad_w") = -1);
+        py::arg("dil"), py::arg("pad_w") = -1, py::arg("acc") = py::none());
+  m.def("stem_pack", &stem_pack, "zero-bordered 8-channel NHWC bf16 copy of an image batch");
+  m.def("wgrad_flush", &wgrad_flush, "grad += acc; acc = 0");
   m.def("fmha_fwd", &fmha_fwd);
   m.def("fmha_bwd", &fmha_bwd);
   m.def("fused_update", &fused_update);

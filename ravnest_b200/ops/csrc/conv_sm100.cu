@@ -41,6 +41,8 @@ struct ConvParams {
   int flip;                       // 1: walk taps mirrored (dgrad)
   const __nv_bfloat16* bias;      // [Cout] or nullptr
   int relu;
+  long long xs_w, xs_h, xs_n;     // host only: element strides of the input's W / H / N dimensions (0 = dense NHWC).  They may
+                                  // OVERLAP (xs_w < Cin): the small-Cin stem reads 8 neighbouring 8-channel pixels as one 64-wide K block
 };
 
 // 4-D / 3-D TMA loads and the 4-D store
@@ -367,7 +369,8 @@ static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int 
   int e = 0;
   {   // x: [N, H, W, Cin] -> dims (Cin, W, H, N); box walks `stride` elements per output pixel
     const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
-    const uint64_t st[3] = {(uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    uint64_t st[3] = {(uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    if (p.xs_w > 0) { st[0] = (uint64_t)p.xs_w; st[1] = (uint64_t)p.xs_h; st[2] = (uint64_t)p.xs_n; }
     const uint32_t box[4] = {64u, (uint32_t)((p.TW - 1) * p.stride + 1), (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TN};
     const uint32_t es[4] = {1u, (uint32_t)p.stride, (uint32_t)p.stride, 1u};
     e |= make_map_nd(&mx, x, 4, dims, st, box, es);
@@ -409,12 +412,14 @@ static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int 
 
 // x [N,H,W,Cin], w [Cout,R,S,Cin] (or, transposed=1, the SAME buffer consumed as a map from Cout_in -> Cin_out for dgrad:
 // then `Cin`/`Cout` below are the GEMM K / N channel counts, i.e. Cin = channels of the incoming gradient), y [N,Ho,Wo,Cout].
-extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho,
-                                int Wo, int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, int num_sms,
-                                cudaStream_t stream) {
+// xs_w / xs_h / xs_n: element strides of x's W / H / N dimensions (0 = dense NHWC); the channel stride is always 1.
+extern "C" int rvn_conv_forward_strided(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin,
+                                        int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed,
+                                        long long xs_w, long long xs_h, long long xs_n, int num_sms, cudaStream_t stream) {
   rvn::ConvParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.pad_w = pad_w; p.dil = dil;
+  p.xs_w = xs_w; p.xs_h = xs_h; p.xs_n = xs_n;
   p.flip = transposed;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.relu = relu;
@@ -426,6 +431,13 @@ extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const voi
   }
   if (wide) return rvn::conv_launch<256, false>(x, w, y, p, num_sms, stream);
   return rvn::conv_launch<128, false>(x, w, y, p, num_sms, stream);
+}
+
+extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho,
+                                int Wo, int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, int num_sms,
+                                cudaStream_t stream) {
+  return rvn_conv_forward_strided(x, w, y, bias, relu, N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, pad_w, dil, transposed, 0, 0, 0, num_sms,
+                                  stream);
 }
 
 // ================================================================================================ weight gradient
@@ -446,7 +458,8 @@ struct WgradParams {
   int R, S, stride, pad, dil, pad_w;
   int TW, TH, TN, tiles_w, tiles_h, tiles_n;
   int co_blocks, ci_blocks, splits, patches_per_split;
-  float* dw;                                    // [Cout, R*S, Cin] fp32, zero-initialised by the caller
+  float* dw;                                    // [Cout, R*S, Cin] fp32, accumulated into (zero it first for a plain gradient)
+  long long xs_w, xs_h, xs_n;                   // host only: element strides of x's W / H / N dimensions (0 = dense NHWC)
 };
 
 template <int BN>
@@ -624,7 +637,8 @@ static int wgrad_launch(const void* dy, const void* x, WgradParams p, int num_sm
   }
   {
     const uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
-    const uint64_t st[3] = {(uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    uint64_t st[3] = {(uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    if (p.xs_w > 0) { st[0] = (uint64_t)p.xs_w; st[1] = (uint64_t)p.xs_h; st[2] = (uint64_t)p.xs_n; }
     const uint32_t box[4] = {64u, (uint32_t)((p.TW - 1) * p.stride + 1), (uint32_t)((p.TH - 1) * p.stride + 1), (uint32_t)p.TN};
     const uint32_t es[4] = {1u, (uint32_t)p.stride, (uint32_t)p.stride, 1u};
     e |= make_map_nd(&mx, x, 4, dims, st, box, es);
@@ -649,13 +663,21 @@ static int wgrad_launch(const void* dy, const void* x, WgradParams p, int num_sm
 
 }  // namespace rvn
 
-// dy [N,Ho,Wo,Cout], x [N,H,W,Cin] bf16 NHWC; dw [Cout,R,S,Cin] fp32 zero-initialised (accumulated into)
-extern "C" int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R,
-                              int S, int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream) {
+// dy [N,Ho,Wo,Cout], x [N,H,W,Cin] bf16 NHWC (x's W / H / N element strides may be given, 0 = dense); dw [Cout,R,S,Cin] fp32 is
+// ACCUMULATED into: a zeroed buffer gives the plain gradient, a persistent fp32 accumulator collects several passes
+extern "C" int rvn_conv_wgrad_strided(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                                      int R, int S, int stride, int pad, int pad_w, int dil, long long xs_w, long long xs_h,
+                                      long long xs_n, int num_sms, cudaStream_t stream) {
   rvn::WgradParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.pad_w = pad_w; p.dil = dil;
   p.dw = dw;
+  p.xs_w = xs_w; p.xs_h = xs_h; p.xs_n = xs_n;
   if (Cin > 64) return rvn::wgrad_launch<128>(dy, x, p, num_sms, stream);
   return rvn::wgrad_launch<64>(dy, x, p, num_sms, stream);
+}
+
+extern "C" int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R,
+                              int S, int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream) {
+  return rvn_conv_wgrad_strided(dy, x, dw, N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, pad_w, dil, 0, 0, 0, num_sms, stream);
 }

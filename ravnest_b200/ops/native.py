@@ -463,6 +463,21 @@ def _conv_grad_acc(weight, dw_f32_ohwi):
     return dw_f32_ohwi.view(weight.shape[0], weight.shape[2], weight.shape[3], weight.shape[1]).to(weight.dtype).permute(0, 3, 1, 2)
 
 
+def _conv_wgrad_into(weight, acc, dy, x, R, S, stride, pad, dil, pad_w=-1):
+    """Weight gradient of a convolution, delivered where the leaf wants it: ``acc`` is the leaf's slice of the stage's persistent
+    fp32 accumulator (``ParamStore.enable_wgrad_staging``) — the split-K kernel's bulk reductions add straight into it and ONE
+    flush per optimizer step moves everything into the gradient bucket; without it, a zeroed fp32 buffer + a cast-add per layer."""
+    if acc is not None and WGRAD_STAGING and ACCUMULATE_INTO_GRAD:
+        C().conv_wgrad_nhwc(dy, x, R, S, stride, pad, dil, pad_w, acc)
+        calls['conv_wgrad_staged'] += 1
+        return None
+    return _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, R, S, stride, pad, dil, pad_w))
+
+
+def _wgrad_acc_of(weight):
+    return getattr(weight, '_rvn_wgrad_acc', None)
+
+
 class _ConvNHWC(torch.autograd.Function):
     """Implicit-GEMM convolution (ops/csrc/conv_sm100.cu) on NHWC activations: forward, stride-1 data gradient and the split-K
     weight gradient run on the tcgen05 kernels; stride-2 data gradients still go through cuDNN (tracked in DESIGN.md).
@@ -480,6 +495,7 @@ class _ConvNHWC(torch.autograd.Function):
         ctx.cfg = (stride, pad, dil, relu)
         ctx.pad_w = pad_w
         ctx.has_bias = bias is not None
+        ctx.wgrad_acc = _wgrad_acc_of(weight)
         ctx.save_for_backward(x_nhwc, weight, w_ohwi, y if relu else None)
         return y
 
@@ -498,7 +514,7 @@ class _ConvNHWC(torch.autograd.Function):
             dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2], pad_w)
             calls['conv_dgrad'] += 1
         if need_dw and NATIVE_CONV_WGRAD:
-            dw = _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, w.shape[1], w.shape[2], stride, pad, dil, pad_w))
+            dw = _conv_wgrad_into(weight, ctx.wgrad_acc, dy, x, w.shape[1], w.shape[2], stride, pad, dil, pad_w)
             calls['conv_wgrad'] += 1
             need_dw = False
         if need_dw or (need_dx and not native_dx) or ctx.has_bias:
@@ -527,6 +543,7 @@ class _Conv1x1(torch.autograd.Function):
         y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, bias, 0, None, False, 0)[0]
         calls['conv1x1_as_gemm'] += 1
         ctx.has_bias = bias is not None
+        ctx.wgrad_acc = _wgrad_acc_of(weight)
         ctx.save_for_backward(x_nhwc, weight, w2)
         return y2.view(n, h, w, w2.shape[0])
 
@@ -541,11 +558,121 @@ class _Conv1x1(torch.autograd.Function):
             dx = C().gemm(dy2, False, w2, True, None, 0, None, False, 0)[0].view(n, h, w, c)
             calls['gemm_dgrad'] += 1
         if ctx.needs_input_grad[1]:
-            dw = _conv_grad_acc(weight, C().conv_wgrad_nhwc(dy, x, 1, 1, 1, 0, 1))
+            dw = _conv_wgrad_into(weight, ctx.wgrad_acc, dy, x, 1, 1, 1, 0, 1)
             calls['conv_wgrad'] += 1
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy2, w2)
         return dx, dw, db
+
+
+class _Conv1x1Fork(torch.autograd.Function):
+    """``(conv1x1(x), x)``: the pointwise convolution that opens a residual block, together with the block's identity branch.
+    Autograd would otherwise meet the two gradients of ``x`` — the convolution's data gradient and the one arriving over the skip
+    connection — with a separate add kernel (19 per ResNet-50 step, 26 us each on the 100 x 56 x 56 x 256 maps); here the dgrad GEMM
+    adds its tile into the skip gradient through its TMA reduce-add epilogue (``D += dy W``), no extra pass over the activation.
+    The skip gradient is updated IN PLACE: use it only where that tensor has a single owner (the fused BN+add+ReLU backward writes a
+    fresh one), as ``nn.Conv2d(fork=True)`` in ``models/resnet.py`` does."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, weight):
+        n, h, w, c = x_nhwc.shape
+        w2 = weight.reshape(weight.shape[0], c)
+        y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, None, 0, None, False, 0)[0]
+        calls['conv1x1_as_gemm'] += 1
+        ctx.wgrad_acc = _wgrad_acc_of(weight)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x_nhwc, weight, w2)
+        return y2.view(n, h, w, w2.shape[0]), x_nhwc            # an input returned as-is: autograd hands out an alias
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x, weight, w2 = ctx.saved_tensors
+        n, h, w, c = x.shape
+        dx = dw = None
+        if dy is not None:
+            dy = dy.contiguous()
+            dy2 = dy.view(n * h * w, w2.shape[0])
+            if ctx.needs_input_grad[0]:
+                if (dskip is not None and CONV_FORK_ACCUMULATE and dskip.is_contiguous() and dskip.dtype == torch.bfloat16
+                        and dskip.data_ptr() % 16 == 0 and dskip.data_ptr() != dy.data_ptr()):
+                    d2 = dskip.view(n * h * w, c)
+                    C().gemm(dy2, False, w2, True, None, 0, d2, False, 0, 2, d2)        # dskip += dy W
+                    calls['gemm_dgrad_fork_acc'] += 1
+                    dx = dskip
+                else:
+                    dx = C().gemm(dy2, False, w2, True, None, 0, None, False, 0)[0].view(n, h, w, c)
+                    calls['gemm_dgrad'] += 1
+                    if dskip is not None:
+                        dx = dx + dskip
+            if ctx.needs_input_grad[1]:
+                dw = _conv_wgrad_into(weight, ctx.wgrad_acc, dy, x, 1, 1, 1, 0, 1)
+                calls['conv_wgrad'] += 1
+        elif ctx.needs_input_grad[0]:
+            dx = dskip
+        return dx, dw
+
+
+class _ConvSmallCin(torch.autograd.Function):
+    """The image stem: a kh x kw convolution (kw <= 8) over 1 - 8 input channels, which TMA cannot tile directly (a pixel is 2 - 8
+    bytes; the unit works in 16-byte granules).  ``stem_pack`` writes a zero-bordered 8-channel copy of the batch; the convolution
+    then runs on the implicit-GEMM kernel as a kh x 1 convolution over a VIRTUAL 64-channel tensor whose "pixel" w is the 8 packed
+    pixels w .. w+7 of a row — a strided view with overlapping pixels (W stride 8 elements, extent 64), so the im2col along the
+    row is done by the TMA unit and the weight is the [Cout, kh, 8 x 8] zero-padded filter row.  Forward and the split-K weight
+    gradient only (images carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, ph, pw):
+        n, cin, h, w = x.shape
+        cout, _, kh, kw = weight.shape
+        ho = (h + 2 * ph - kh) // stride + 1
+        wo = (w + 2 * pw - kw) // stride + 1
+        hp = h + 2 * ph
+        wp = max(w + 2 * pw, (wo - 1) * stride + 8)
+        xp = C().stem_pack(x, ph, pw, hp, wp)
+        calls['stem_pack'] += 1
+        hv, wv = (ho - 1) * stride + kh, (wo - 1) * stride + 1
+        xv = _stem_view(xp, hv, wv)
+        wrow = torch.zeros(cout, kh, 8, 8, dtype=torch.bfloat16, device=x.device)
+        wrow[:, :, :kw, :cin] = weight.permute(0, 2, 3, 1)
+        y = C().conv_nhwc(xv, wrow.view(cout, kh, 1, 64), bias, stride, 0, 1, False, False, 0, 0, 0)
+        calls['conv_stem'] += 1
+        ctx.cfg = (stride, kh, kw, cin)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xv, weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xv, weight, bias = ctx.saved_tensors
+        stride, kh, kw, cin = ctx.cfg
+        dy = dy.contiguous()
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dwrow = C().conv_wgrad_nhwc(dy, xv, kh, 1, stride, 0, 1, 0)                 # [Cout, kh, 1, 64] fp32
+            calls['conv_stem_wgrad'] += 1
+            d_ohwi = dwrow.view(weight.shape[0], kh, 8, 8)[:, :, :kw, :cin]             # -> [Cout, kh, kw, Cin]
+            g = weight.grad
+            if ACCUMULATE_INTO_GRAD and g is not None:
+                g.permute(0, 2, 3, 1).add_(d_ohwi)
+            else:
+                dw = d_ohwi.permute(0, 3, 1, 2).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _bias_grad(dy.view(-1, dy.shape[-1]), bias)
+        return None, dw, db, None, None, None
+
+
+_STEM_OVERLAP_OK = True
+
+
+def _stem_view(xp, hv, wv):
+    """[N, hv, wv, 64] view of the packed [N, Hp, Wp, 8] batch: "pixel" w = packed pixels w .. w+7 (overlapping strides)."""
+    n, hp, wp, _ = xp.shape
+    xv = xp.as_strided((n, hv, wv, 64), (hp * wp * 8, wp * 8, 8, 1))
+    if not _STEM_OVERLAP_OK:
+        # a driver that refuses overlapping tensor-map strides: materialise the row-im2col once (8x the packed bytes, same kernels)
+        calls['conv_stem_materialized'] += 1
+        return xv.contiguous()
+    return xv
 
 
 def _pair(v):
@@ -566,6 +693,12 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     base_ok = (groups == 1 and x.dim() == 4 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
                and cin % 8 == 0 and cout % 8 == 0)
     strided = sh != 1 or sw != 1
+    if (SMALL_CIN_STEM and groups == 1 and x.dim() == 4 and cin < 8 and kw <= 8 and cout % 8 == 0 and sh == sw and sh in (1, 2)
+            and dh == 1 and dw_ == 1 and weight.dtype == torch.bfloat16 and x.dtype in (torch.bfloat16, torch.float32)
+            and not x.requires_grad and (bias is None or bias.dtype == torch.bfloat16)):
+        # image stems (RGB / grey-scale): 8-channel zero-bordered pack + overlapping-stride TMA im2col, see _ConvSmallCin
+        y = _stem_apply(x, weight, bias, sh, ph, pw)
+        return y.permute(0, 3, 1, 2)
     if base_ok and kh == 1 and kw == 1 and ph == 0 and pw == 0 and not (strided and STRIDED_1X1_IMPLICIT and sh == sw and sh == 2):
         # (strided pointwise convs — ResNet's three downsample projections — take the implicit-GEMM kernel below: its TMA box load
         #  strides over the input pixels itself, where the sub-sampling slice here costs a strided copy forward and a fill + strided
@@ -586,8 +719,36 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 
+def _stem_apply(x, weight, bias, stride, ph, pw):
+    global _STEM_OVERLAP_OK
+    try:
+        return _ConvSmallCin.apply(x, weight, bias, stride, ph, pw)
+    except RuntimeError as exc:
+        if not _STEM_OVERLAP_OK or 'conv_forward' not in str(exc):
+            raise
+        _STEM_OVERLAP_OK = False          # tensor-map encoder rejected the overlapping view: use the materialised one from now on
+        return _ConvSmallCin.apply(x, weight, bias, stride, ph, pw)
+
+
+def conv1x1_fork(x, weight):
+    """``(conv1x1(x), x)`` for the block-opening pointwise convolution of a residual block (NCHW-shaped channels_last bf16)."""
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    y, skip = _Conv1x1Fork.apply(x.permute(0, 2, 3, 1), weight)
+    return y.permute(0, 3, 1, 2), skip.permute(0, 3, 1, 2)
+
+
+def wgrad_flush(acc, grad):
+    """grad += acc; acc = 0 — the stage's fp32 convolution-weight-gradient accumulator into its flat gradient bucket."""
+    C().wgrad_flush(acc, grad)
+    calls['wgrad_flush'] += 1
+
+
 IMPLICIT_GEMM_CONV = True
 NATIVE_CONV_WGRAD = True
+SMALL_CIN_STEM = True
+CONV_FORK_ACCUMULATE = True
+WGRAD_STAGING = True
 STRIDED_1X1_IMPLICIT = True
 RECTANGULAR_CONV = True
 BN_RELU_BITMASK = True

@@ -110,10 +110,8 @@ class GraphedStage:
         # private weight copy + leaves that accumulate into the stage's flat gradient bucket
         self.wbuf = torch.empty_like(store.current.flat)
         self.params = {}
-        for k, (name, g) in enumerate(zip(store.names, store.grad_views)):
-            leaf = store.view_of(self.wbuf, k).detach().requires_grad_(True)
-            leaf.grad = g
-            self.params[name] = leaf
+        for k, name in enumerate(store.names):
+            self.params[name] = store.make_leaf(self.wbuf, k)
 
         def stage(t):
             return torch.empty(t.shape, dtype=t.dtype, device=dev).copy_(t, non_blocking=True)

@@ -313,6 +313,132 @@ def test_conv2d_rectangular_kernels(N, C, H, W, K, kh, kw, ph, pw):
     assert _rel_err(w.grad, wr.grad) < 2e-2
 
 
+@pytest.mark.parametrize('N,C,H,W,K,kh,kw,stride,ph,pw,src', [
+    (4, 3, 64, 64, 64, 7, 7, 2, 3, 3, 'bf16_cl'),          # ResNet-50 stem (TinyImageNet-sized)
+    (2, 3, 224, 224, 64, 7, 7, 2, 3, 3, 'f32_nchw'),       # ResNet-50 stem, ImageNet-sized, fp32 NCHW images
+    (3, 3, 37, 45, 32, 3, 3, 2, 0, 0, 'bf16_nchw'),        # Inception stem (stride 2, no padding), odd extents
+    (4, 3, 32, 32, 192, 3, 3, 1, 1, 1, 'bf16_cl'),         # Inception CIFAR stem
+    (5, 1, 28, 28, 16, 3, 3, 1, 1, 1, 'f32_nchw'),         # CNN_Net: one input channel
+    (2, 4, 19, 23, 24, 5, 8, 1, 2, 3, 'bf16_nchw')])       # widest supported filter row
+def test_conv2d_small_cin_stem(N, C, H, W, K, kh, kw, stride, ph, pw, src):
+    """Image stems run on the implicit-GEMM kernel over an 8-channel zero-bordered pack read through an overlapping-stride
+    tensor map (ops/native.py: _ConvSmallCin): forward and weight gradient vs fp32 torch, no cuDNN fallback."""
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(21)
+    x32 = torch.randn(N, C, H, W, device=DEV)
+    if src == 'f32_nchw':
+        x = x32
+    elif src == 'bf16_nchw':
+        x = x32.to(torch.bfloat16)
+    else:
+        x = x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = _rand(K, C, kh, kw, scale=0.1).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    b = _rand(K, scale=0.5).requires_grad_(True) if C == 1 else None
+    before, stems = native.fallbacks['conv2d'], native.calls['conv_stem']
+    y = ops.conv2d(x, w, b, stride, (ph, pw), 1, 1)
+    g = _rand(*y.shape).contiguous(memory_format=torch.channels_last)
+    y.backward(g)
+    xr = x.float() if src != 'f32_nchw' else x32.to(torch.bfloat16).float()      # the pack rounds fp32 images to bf16
+    wr = w.detach().float().requires_grad_(True)
+    br = b.detach().float().requires_grad_(True) if b is not None else None
+    yr = torch.nn.functional.conv2d(xr, wr, br, stride, (ph, pw))
+    yr.backward(g.float())
+    assert y.shape == yr.shape and y.dtype == torch.bfloat16
+    assert native.fallbacks['conv2d'] == before and native.calls['conv_stem'] == stems + 1
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
+    if b is not None:
+        assert _rel_err(b.grad, br.grad) < 2e-2
+    # a second backward accumulates into the existing .grad
+    g1 = w.grad.float().clone()
+    ops.conv2d(x, w, b, stride, (ph, pw), 1, 1).backward(g)
+    assert _rel_err(w.grad, 2 * g1) < 2e-2
+    print('stem materialized fallbacks:', native.calls['conv_stem_materialized'])
+
+
+def test_stem_pack_layouts():
+    """rvn_stem_pack: fp32 / bf16, NCHW / channels_last sources -> zero-bordered [N, Hp, Wp, 8] bf16."""
+    torch.manual_seed(22)
+    x32 = torch.randn(3, 3, 11, 13, device=DEV)
+    ref = torch.zeros(3, 11 + 4, 13 + 9, 8, device=DEV)
+    ref[:, 2:13, 3:16, :3] = x32.to(torch.bfloat16).float().permute(0, 2, 3, 1)
+    for x in (x32, x32.to(torch.bfloat16), x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+              x32.contiguous(memory_format=torch.channels_last)):
+        out = _C().stem_pack(x, 2, 3, 15, 22)
+        assert out.shape == (3, 15, 22, 8) and out.dtype == torch.bfloat16
+        assert torch.equal(out.float(), ref)
+
+
+@pytest.mark.parametrize('N,C,H,W,K', [(4, 256, 14, 14, 64), (100, 256, 56, 56, 64), (3, 1024, 7, 9, 256)])
+def test_conv1x1_fork_accumulates_into_the_skip_gradient(N, C, H, W, K):
+    """(conv1x1(x), x): the dgrad GEMM adds its tiles into the gradient arriving over the skip branch (TMA reduce-add epilogue)."""
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(23)
+    x = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = _rand(K, C, 1, 1, scale=0.05).requires_grad_(True)
+    r = _rand(N, C, H, W).contiguous(memory_format=torch.channels_last)
+    gy = _rand(N, K, H, W).contiguous(memory_format=torch.channels_last)
+    before = native.calls['gemm_dgrad_fork_acc']
+    y, skip = ops.conv1x1_fork(x, w)
+    assert skip.data_ptr() == x.data_ptr()
+    ((y.float() * gy.float()).sum() + (skip.float() * r.float()).sum()).backward()
+    assert native.calls['gemm_dgrad_fork_acc'] == before + 1
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr)
+    ((yr * gy.float()).sum() + (xr * r.float()).sum()).backward()
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 2e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
+    # the skip branch alone (no gradient for y) and y alone
+    x.grad = None
+    ops.conv1x1_fork(x, w)[1].float().mul(r.float()).sum().backward()
+    assert _rel_err(x.grad, r) < 1e-2
+    x.grad = None
+    ops.conv1x1_fork(x, w)[0].backward(gy)
+    assert _rel_err(x.grad, xr.grad - r.float()) < 2e-2
+
+
+def test_conv_wgrad_staging_and_flush():
+    """Convolution weight gradients collected in the stage's fp32 accumulator over two micro-steps, then flushed into the bf16
+    gradient bucket in one pass that leaves the accumulator zero (ParamStore.enable_wgrad_staging / flush_wgrad)."""
+    from ravnest_b200 import nn as rnn
+    from ravnest_b200.ops import native
+    from ravnest_b200.runtime.param_store import ParamStore
+    torch.manual_seed(24)
+    model = torch.nn.Sequential(rnn.Conv2d(64, 64, 3, padding=1, bias=False), rnn.Conv2d(64, 128, 1, bias=False),
+                                rnn.Conv2d(128, 128, (1, 7), padding=(0, 3), bias=False), rnn.Conv2d(128, 64, 3, stride=2, padding=1, bias=False),
+                                torch.nn.Flatten(), torch.nn.Linear(64 * 8 * 8, 16)).to(DEV, torch.bfloat16)
+    store = ParamStore(model, DEV, n_slots=2, compute_dtype=torch.bfloat16)
+    assert store.enable_wgrad_staging() and store.wgrad_acc.dtype == torch.float32
+    x = _rand(6, 64, 16, 16).contiguous(memory_format=torch.channels_last)
+    slot = store.acquire()
+    staged = native.calls['conv_wgrad_staged']
+    for _ in range(2):
+        torch.func.functional_call(model, slot.param_dict, (x,)).float().pow(2).sum().backward()
+    assert native.calls['conv_wgrad_staged'] == staged + 8
+    conv_idx = [k for k, sh in enumerate(store.shapes) if len(sh) == 4]
+    assert all(float(store.grad_views[k].abs().sum()) == 0.0 for k in conv_idx)          # nothing reached the bucket yet
+    lin_before = store.grad_views[store.index_of('5.weight')].float().clone()
+    store.flush_wgrad()
+    assert float(store.wgrad_acc.abs().sum()) == 0.0
+    ref = torch.nn.Sequential(torch.nn.Conv2d(64, 64, 3, padding=1, bias=False), torch.nn.Conv2d(64, 128, 1, bias=False),
+                              torch.nn.Conv2d(128, 128, (1, 7), padding=(0, 3), bias=False),
+                              torch.nn.Conv2d(128, 64, 3, stride=2, padding=1, bias=False), torch.nn.Flatten(),
+                              torch.nn.Linear(64 * 8 * 8, 16)).to(DEV)
+    ref.load_state_dict({k: v.float() for k, v in store.master_state().items()})
+    for _ in range(2):
+        ref(x.float()).pow(2).sum().backward()
+    grads = dict(zip(store.names, store.grad_views))
+    for name, p in ref.named_parameters():
+        assert _rel_err(grads[name], p.grad) < 5e-2, name
+    assert torch.equal(store.grad_views[store.index_of('5.weight')].float(), lin_before)    # the flush touched only staged ranges
+    store.flush_wgrad()                                                                       # idempotent when nothing is staged
+    for name, p in ref.named_parameters():
+        assert _rel_err(grads[name], p.grad) < 5e-2, name
+
+
 @pytest.mark.parametrize('N,C,H,W', [(8, 64, 56, 56), (4, 256, 28, 28), (3, 2048, 7, 7), (2, 48, 17, 17)])
 @pytest.mark.parametrize('relu,with_res', [(True, False), (True, True), (False, False)])
 def test_batchnorm_relu_add(N, C, H, W, relu, with_res):

@@ -71,6 +71,28 @@ def test_fused_resnet50_splits_and_matches_torchvision():
     assert torch.allclose(r.run_local(x), m(x), atol=1e-5)
 
 
+def test_tuple_valued_nodes_never_cross_a_cut():
+    """Identity bottlenecks open with ``conv1(x) -> (y, x)`` (nn.Conv2d(fork=True)): a cut that lands on one of the tuple's getitem
+    nodes is moved behind them, so stages exchange tensors only."""
+    import operator
+    from ravnest_b200.operations.splitter import split_graph, trace_model, propagate_meta
+    m = models.resnet50(num_classes=10).eval()
+    assert m.layer1[1].conv1.fork and not m.layer1[0].conv1.fork
+    x = torch.rand(2, 3, 64, 64)
+    gm, names = trace_model(m, (x,))[:2]
+    propagate_meta(gm, [x])
+    items = [n for n in gm.graph.nodes if n.op == 'call_function' and n.target is operator.getitem]
+    assert len(items) == 2 * 12
+    for cut in (items[0], items[1], items[7]):
+        r = split_graph(gm, [cut], names)
+        for st in r.stages:
+            st.module.eval()
+        assert all(isinstance(o['meta'], dict) or o['meta'] is None or not isinstance(o['meta'], (tuple, list))
+                   for st in r.stages for o in st.outputs)
+        assert torch.allclose(r.run_local(x), m(x), atol=1e-5)
+        assert len(r.stages[0].outputs) == 2          # y and the skip tensor, unpacked on the producing side
+
+
 def test_inception_and_gpt_splits_run():
     m = models.Inception3().eval()
     x = torch.rand(2, 3, 32, 32)
