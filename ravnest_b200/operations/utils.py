@@ -253,7 +253,13 @@ def clusterize(model=None, example_args=(), example_kwargs=None, pass_data=False
     os.makedirs(root, exist_ok=True)
     delete_all_folders(root)
 
-    full_model_size = get_memory_reqs(model, call_args=tuple(example_args), call_kwargs=example_kwargs)
+    # reference operations/utils.py:393-412: with a single positional example and ``pass_data=False`` the model is sized on a random
+    # tensor of the example's SHAPE (torchinfo's input_size mode); ``pass_data=True`` — and every kwargs form — runs the given data
+    if len(example_args) == 1 and not example_kwargs and not pass_data and isinstance(example_args[0], torch.Tensor) \
+            and example_args[0].is_floating_point():
+        full_model_size = get_memory_reqs(model, input_size=tuple(example_args[0].shape))
+    else:
+        full_model_size = get_memory_reqs(model, call_args=tuple(example_args), call_kwargs=example_kwargs)
     if verbose:
         print('Model memory (MB):', full_model_size)
 
