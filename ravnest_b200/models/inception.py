@@ -18,7 +18,7 @@ from .. import nn as rnn
 class BasicConv2d(nn.Module):
     def __init__(self, in_channels, out_channels, **kwargs):
         super().__init__()
-        self.conv = rnn.Conv2d(in_channels, out_channels, bias=False, **kwargs)
+        self.conv = rnn.Conv2d(in_channels, out_channels, bias=False, bn_stats=True, **kwargs)
         self.bn = rnn.BatchNorm2d(out_channels, eps=0.001, relu=True)      # BN + ReLU in one kernel
 
     def forward(self, x):

@@ -20,15 +20,15 @@ class Bottleneck(nn.Module):
         super().__init__()
         out = planes * self.expansion
         # identity blocks: conv1 also hands out the skip branch, so its data gradient lands IN the skip gradient (no add kernel)
-        self.conv1 = rnn.Conv2d(inplanes, planes, 1, bias=False, fork=not downsample)
+        self.conv1 = rnn.Conv2d(inplanes, planes, 1, bias=False, fork=not downsample, bn_stats=True)
         self.bn1 = rnn.BatchNorm2d(planes, relu=True)
-        self.conv2 = rnn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.conv2 = rnn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False, bn_stats=True)
         self.bn2 = rnn.BatchNorm2d(planes, relu=True)
-        self.conv3 = rnn.Conv2d(planes, out, 1, bias=False)
+        self.conv3 = rnn.Conv2d(planes, out, 1, bias=False, bn_stats=True)
         self.bn3 = rnn.BatchNorm2d(out, relu=True)           # relu(BN(conv3) + identity)
         self.downsample = None
         if downsample:
-            self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False), rnn.BatchNorm2d(out))
+            self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False, bn_stats=True), rnn.BatchNorm2d(out))
 
     def forward(self, x):
         if self.conv1.fork:
@@ -43,7 +43,7 @@ class Bottleneck(nn.Module):
 class ResNet(nn.Module):
     def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, zero_init_residual=False):
         super().__init__()
-        self.conv1 = rnn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.conv1 = rnn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False, bn_stats=True)
         self.bn1 = rnn.BatchNorm2d(64, relu=True)
         self.maxpool = rnn.MaxPool2d(3, stride=2, padding=1)
         inplanes = 64

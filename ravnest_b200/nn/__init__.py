@@ -101,21 +101,24 @@ class Conv2d(nn.Conv2d):
 
     ``fork=True`` (bias-free stride-1 pointwise convolutions only) makes ``forward`` return ``(conv(x), x)``: the convolution
     that opens a residual block hands the block its identity branch, and in backward adds its data gradient into the skip
-    connection's gradient inside the GEMM epilogue (``ops.conv1x1_fork``)."""
+    connection's gradient inside the GEMM epilogue (``ops.conv1x1_fork``).  ``bn_stats=True`` declares that a BatchNorm consumes the
+    output: in training the producing kernel's epilogue then also collects the per-channel batch statistics (``ops.conv2d``)."""
 
-    def __init__(self, *args, fork=False, **kwargs):
+    def __init__(self, *args, fork=False, bn_stats=False, **kwargs):
         super().__init__(*args, **kwargs)
         self.fork = bool(fork)
+        self.bn_stats = bool(bn_stats)      # a BatchNorm consumes the output: let the kernel's epilogue collect its batch statistics
         if self.fork and (self.kernel_size != (1, 1) or self.stride != (1, 1) or self.padding != (0, 0) or self.bias is not None
                           or self.groups != 1):
             raise ValueError('fork=True needs a bias-free, stride-1, ungrouped 1x1 convolution')
 
     def forward(self, x):
+        stats = self.bn_stats and self.training
         if self.fork:
-            return ops.conv1x1_fork(x, self.weight)
+            return ops.conv1x1_fork(x, self.weight, stats)
         if isinstance(self.padding, str) or self.padding_mode != 'zeros':
             return super().forward(x)
-        return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        return ops.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups, stats)
 
 
 class BatchNorm2d(nn.BatchNorm2d):

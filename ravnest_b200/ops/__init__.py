@@ -158,7 +158,7 @@ def cross_entropy(logits, target, ignore_index=-100):
     return reference_cross_entropy(logits, target, ignore_index)
 
 
-def conv1x1_fork(x, weight):
+def conv1x1_fork(x, weight, bn_stats=False):
     """``(conv1x1(x), x)``: the pointwise convolution that opens a residual block plus the block's identity branch.  On the native
     path the convolution's data gradient is accumulated INTO the gradient arriving over the skip connection by the dgrad GEMM's
     reduce-add epilogue (no separate add pass; ``ops/native.py: _Conv1x1Fork``) — the skip must therefore end in an op whose
@@ -167,20 +167,22 @@ def conv1x1_fork(x, weight):
     if (_native(x, weight) and x.dim() == 4 and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and cin % 8 == 0
             and cout % 8 == 0 and weight.shape[2] == 1 and weight.shape[3] == 1):
         from . import native
-        return native.conv1x1_fork(x, weight)
+        return native.conv1x1_fork(x, weight, bn_stats)
     return conv2d(x, weight), x
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, bn_stats=False):
     """2-D convolution.  On CUDA (bf16, channels_last) pointwise convolutions run on the tcgen05 GEMM — in NHWC a 1x1
     convolution IS ``[N*H*W, Cin] x [Cout, Cin]^T`` with zero data movement (strided 1x1: the implicit-GEMM kernel, whose TMA
     element strides do the sub-sampling) — and square or rectangular kh x kw convolutions (stride 1 / 2, per-axis padding) on the
     implicit-GEMM kernel (forward, stride-1 dgrad, split-K wgrad with bulk reductions).  Image stems (Cin < 8, e.g. RGB) run on the same kernel over an 8-channel
     zero-bordered pack of the batch, read through an overlapping-stride tensor map.  Remaining library cases (cuDNN): other
-    Cin % 8 != 0, stride-2 data gradients, groups > 1, dilation — counted in ``ops.native.fallbacks``."""
+    Cin % 8 != 0, stride-2 data gradients, groups > 1, dilation — counted in ``ops.native.fallbacks``.  ``bn_stats=True`` (a training
+    BatchNorm follows): the producing kernel's epilogue also collects the per-channel sum and sum of squares of the output and hands
+    them to ``batch_norm_act`` with the tensor, which then skips its statistics pass."""
     if _native(x, weight):
         from . import native
-        return native.conv2d(x, weight, bias, stride, padding, dilation, groups)
+        return native.conv2d(x, weight, bias, stride, padding, dilation, groups, bn_stats)
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 

@@ -14,10 +14,10 @@ extern "C" {
 int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
                   const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out, int ld_preact,
                   int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n, int split_k,
-                  int reduce_out, int num_sms,
+                  int reduce_out, float* stats, int num_sms,
                   cudaStream_t stream);
 int rvn_gemm_bf16_2cta(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
-                       const void* bias, int act, int reduce_out, int block_n, int num_sms, cudaStream_t stream);
+                       const void* bias, int act, int reduce_out, float* stats, int block_n, int num_sms, cudaStream_t stream);
 int rvn_layernorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* y, void* sum_out, float* mean,
                           float* rstd, int rows, int H, float eps, const long long* rng, float dropout_p, cudaStream_t stream);
 int rvn_layernorm_backward(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, void* dsum,
@@ -40,7 +40,7 @@ int rvn_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W
                    int stride, int pad, int pad_w, int dil, int num_sms, cudaStream_t stream);
 int rvn_conv_forward_strided(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho, int Wo,
                              int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, long long xs_w, long long xs_h,
-                             long long xs_n, int num_sms, cudaStream_t stream);
+                             long long xs_n, float* stats, int num_sms, cudaStream_t stream);
 int rvn_conv_wgrad_strided(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
                            int stride, int pad, int pad_w, int dil, long long xs_w, long long xs_h, long long xs_n, int num_sms,
                            cudaStream_t stream);
@@ -49,7 +49,8 @@ int rvn_stem_pack(const void* x, int x_is_bf16, void* out, int N, int C, int H, 
 int rvn_wgrad_flush(float* acc, void* grad, int grad_is_bf16, size_t n, int num_sms, cudaStream_t stream);
 int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean, void* running_var,
                           long long* batches_tracked, float* mean, float* invstd, float* sums, void* y, long long M, int C, float eps,
-                          float momentum, int relu, int training, int param_bf16, int stats_bf16, void* relu_mask, int num_sms, cudaStream_t stream);
+                          float momentum, int relu, int training, int param_bf16, int stats_bf16, void* relu_mask, int sums_ready, int num_sms,
+                          cudaStream_t stream);
 int rvn_batchnorm_backward(const void* dy, const void* y, const void* x, const void* gamma, const float* mean, const float* invstd,
                            float* sums, void* dx, void* dres, void* dgamma, void* dbeta, long long M, int C, int relu, int param_bf16,
                            int accumulate, const void* relu_mask, int num_sms, cudaStream_t stream);
@@ -184,7 +185,7 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
                                 const c10::optional<torch::Tensor>& dact_in, int64_t store_preact, int64_t block_n,
                                 int64_t aux_mode, const c10::optional<torch::Tensor>& out,
                                 const c10::optional<torch::Tensor>& b_copy_dst, const c10::optional<torch::Tensor>& bcopy_flags,
-                                int64_t bcopy_epoch, int64_t split_k) {
+                                int64_t bcopy_epoch, int64_t split_k, const c10::optional<torch::Tensor>& col_stats) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16,
               "gemm expects CUDA bf16 operands");
   c10::cuda::CUDAGuard guard(A.device());
@@ -226,7 +227,18 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   const bool reduce_out = dact_ptr != nullptr && aux_mode == 2 && out.has_value() && out->defined() &&
                           dact_ptr == out->data_ptr() && ld_dact == ldd && !store_preact && !(bias.has_value() && bias->defined()) && act == 0;
   if (reduce_out) dact_ptr = nullptr;
-  const bool explicit_tiling = block_n > 0 || split_k > 0;
+  // column statistics (sum, sum of squares of the bf16 output, ADDED into a [2, N] fp32 tensor): the BatchNorm that follows a
+  // pointwise convolution gets its batch statistics from this epilogue instead of reading the activation again
+  float* stats_ptr = nullptr;
+  if (col_stats.has_value() && col_stats->defined()) {
+    TORCH_CHECK(col_stats->scalar_type() == torch::kFloat32 && col_stats->is_contiguous() && col_stats->numel() == 2 * static_cast<int64_t>(N) &&
+                    col_stats->device() == A.device(), "col_stats must be a contiguous fp32 [2, N] tensor");
+    TORCH_CHECK(!reduce_out && dact_ptr == nullptr && !store_preact && bias_ptr == nullptr && act == 0 &&
+                    !(b_copy_dst.has_value() && b_copy_dst->defined()), "col_stats needs a plain store epilogue");
+    stats_ptr = col_stats->data_ptr<float>();
+    split_k = 1;
+  }
+  const bool explicit_tiling = block_n > 0 || (split_k > 0 && stats_ptr == nullptr);
   const double cost1 = choose_tiling(M, N, K, reduce_out, sm_count(), &block_n, &split_k);
   // plain epilogues (bias / activation, or accumulate-into-output) may run on the CTA-pair kernel when the wave model prefers it
   if (!explicit_tiling && dact_ptr == nullptr && !store_preact && !(b_copy_dst.has_value() && b_copy_dst->defined()) && M >= 256) {
@@ -234,7 +246,7 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
     const double cost2 = pair_tiling_cost(M, N, K, sm_count(), &bn2);
     if (cost2 < 0.97 * cost1) {
       check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
-                               reduce_out ? 1 : 0, bn2, sm_count(), cur_stream()),
+                               reduce_out ? 1 : 0, stats_ptr, bn2, sm_count(), cur_stream()),
             "gemm_bf16_2cta");
       std::vector<torch::Tensor> res2;
       res2.push_back(D.size(1) == N ? D : D.narrow(1, 0, N));
@@ -254,7 +266,7 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   check(rvn_gemm_bf16(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act),
                       dact_ptr, ld_dact, static_cast<int>(aux_mode), preact_ptr, store_preact ? static_cast<int>(P.stride(0)) : ldd,
                       static_cast<int>(store_preact), bcopy_ptr, ld_bcopy, flags_ptr, static_cast<unsigned>(bcopy_epoch), static_cast<int>(block_n),
-                      static_cast<int>(split_k), reduce_out ? 1 : 0, sm_count(),
+                      static_cast<int>(split_k), reduce_out ? 1 : 0, stats_ptr, sm_count(),
                       cur_stream()),
         "gemm_bf16");
   std::vector<torch::Tensor> res;
@@ -280,7 +292,7 @@ torch::Tensor gemm_2cta(const torch::Tensor& A, bool a_mn, const torch::Tensor& 
     TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->is_contiguous() && bias->numel() == N, "bad bias");
     bias_ptr = bias->data_ptr();
   }
-  check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act), 0,
+  check(rvn_gemm_bf16_2cta(A.data_ptr(), lda, a_mn, B.data_ptr(), ldb, b_mn, D.data_ptr(), ldd, M, N, K, bias_ptr, static_cast<int>(act), 0, nullptr,
                            block_n == 128 ? 128 : 256, sm_count(), cur_stream()),
         "gemm_bf16_2cta");
   return D.size(1) == N ? D : D.narrow(1, 0, N);
@@ -568,7 +580,8 @@ static void nhwc_strides(const torch::Tensor& x, long long* st) {
 }
 
 torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c10::optional<torch::Tensor>& bias, int64_t stride,
-                        int64_t pad, int64_t dil, bool relu, bool transposed, int64_t out_h, int64_t out_w, int64_t pad_w) {
+                        int64_t pad, int64_t dil, bool relu, bool transposed, int64_t out_h, int64_t out_w, int64_t pad_w,
+                        const c10::optional<torch::Tensor>& col_stats) {
   if (pad_w < 0) pad_w = pad;          // square padding unless a horizontal one is given (rectangular kernels)
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(w.is_contiguous() && x.dim() == 4 && w.dim() == 4 && x.scalar_type() == torch::kBFloat16 &&
@@ -592,9 +605,15 @@ torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c1
   const void* bias_ptr = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
   const int eff_pad = transposed ? static_cast<int>(dil * (R - 1) - pad) : static_cast<int>(pad);
   const int eff_pad_w = transposed ? static_cast<int>(dil * (S - 1) - pad_w) : static_cast<int>(pad_w);
+  float* stats_ptr = nullptr;          // per-channel sum / sum of squares of y, ADDED into a [2, Cout] fp32 tensor (BatchNorm statistics)
+  if (col_stats.has_value() && col_stats->defined()) {
+    TORCH_CHECK(col_stats->scalar_type() == torch::kFloat32 && col_stats->is_contiguous() && col_stats->numel() == 2 * static_cast<int64_t>(n_ch) &&
+                    col_stats->device() == x.device() && !relu, "col_stats must be a contiguous fp32 [2, Cout] tensor (no fused ReLU)");
+    stats_ptr = col_stats->data_ptr<float>();
+  }
   check(rvn_conv_forward_strided(x.data_ptr(), w.data_ptr(), y.data_ptr(), bias_ptr, relu, N, H, W, k_ch, Ho, Wo, n_ch, R, S,
-                                 static_cast<int>(stride), eff_pad, eff_pad_w, static_cast<int>(dil), transposed, xs[0], xs[1], xs[2], sm_count(),
-                                 cur_stream()),
+                                 static_cast<int>(stride), eff_pad, eff_pad_w, static_cast<int>(dil), transposed, xs[0], xs[1], xs[2], stats_ptr,
+                                 sm_count(), cur_stream()),
         "conv_forward");
   return y;
 }
@@ -669,7 +688,8 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
                                          const torch::Tensor& beta, const c10::optional<torch::Tensor>& mean_in,
                                          const c10::optional<torch::Tensor>& invstd_in, double eps, bool relu, bool training,
                                          const c10::optional<torch::Tensor>& running_mean, const c10::optional<torch::Tensor>& running_var,
-                                         const c10::optional<torch::Tensor>& batches_tracked, double momentum, bool want_mask) {
+                                         const c10::optional<torch::Tensor>& batches_tracked, double momentum, bool want_mask,
+                                         const c10::optional<torch::Tensor>& sums_in) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && x.scalar_type() == torch::kBFloat16, "batchnorm expects contiguous bf16 NHWC input");
   const int pbf = is_bf16_or_f32(gamma, "gamma");
@@ -680,7 +700,12 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
   auto y = torch::empty_like(x);
   torch::Tensor mean = training ? torch::empty({C}, f32) : mean_in.value();
   torch::Tensor invstd = training ? torch::empty({C}, f32) : invstd_in.value();
-  auto sums = torch::empty({2 * static_cast<int64_t>(C)}, f32);
+  // sums_in: the per-channel sum / sum of squares of x, already collected by the epilogue of the kernel that produced x
+  const bool sums_ready = training && sums_in.has_value() && sums_in->defined();
+  if (sums_ready)
+    TORCH_CHECK(sums_in->scalar_type() == torch::kFloat32 && sums_in->is_contiguous() && sums_in->numel() == 2 * static_cast<int64_t>(C) &&
+                    sums_in->device() == x.device(), "sums_in must be a contiguous fp32 [2, C] tensor");
+  auto sums = sums_ready ? *sums_in : torch::empty({2 * static_cast<int64_t>(C)}, f32);
   const void* res_ptr = (res.has_value() && res->defined()) ? res->data_ptr() : nullptr;
   if (res_ptr) TORCH_CHECK(res->is_contiguous() && res->numel() == x.numel(), "residual must match x");
   void *rm = nullptr, *rv = nullptr;
@@ -701,8 +726,8 @@ std::vector<torch::Tensor> batchnorm_fwd(const torch::Tensor& x, const c10::opti
   if (want_mask && relu) mask = torch::empty({static_cast<int64_t>(x.numel() / 8)}, x.options().dtype(torch::kUInt8));
   check(rvn_batchnorm_forward(x.data_ptr(), res_ptr, gamma.data_ptr(), beta.data_ptr(), rm, rv, nbt, mean.data_ptr<float>(),
                               invstd.data_ptr<float>(), sums.data_ptr<float>(), y.data_ptr(), M, C, static_cast<float>(eps),
-                              static_cast<float>(momentum), relu, training, pbf, sbf, mask.defined() ? mask.data_ptr() : nullptr, sm_count(),
-                              cur_stream()),
+                              static_cast<float>(momentum), relu, training, pbf, sbf, mask.defined() ? mask.data_ptr() : nullptr,
+                              sums_ready ? 1 : 0, sm_count(), cur_stream()),
         "batchnorm_fwd");
   if (mask.defined()) return {y, mean, invstd, mask};
   return {y, mean, invstd};
@@ -887,7 +912,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm, "bf16 tcgen05 GEMM with fused epilogue", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("aux_in") = py::none(), py::arg("store_preact") = false,
         py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none(),
-        py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0, py::arg("split_k") = 0);
+        py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0, py::arg("split_k") = 0, py::arg("col_stats") = py::none());
   m.def("gemm_2cta", &gemm_2cta, "bf16 tcgen05 GEMM on CTA pairs (cta_group::2)", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("block_n") = 256);
   m.def("layernorm_fwd", &layernorm_fwd);
@@ -903,12 +928,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("pack_f32", &pack_f32);
   m.def("rng_next", &rng_next);
   m.def("conv_nhwc", &conv_nhwc, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("relu"),
-        py::arg("transposed"), py::arg("out_h"), py::arg("out_w"), py::arg("pad_w") = -1);
+        py::arg("transposed"), py::arg("out_h"), py::arg("out_w"), py::arg("pad_w") = -1, py::arg("col_stats") = py::none());
   m.def("pool_fwd", &pool_fwd);
   m.def("pool_bwd", &pool_bwd);
   m.def("batchnorm_fwd", &batchnorm_fwd, py::arg("x"), py::arg("res"), py::arg("gamma"), py::arg("beta"), py::arg("mean_in"), py::arg("invstd_in"),
         py::arg("eps"), py::arg("relu"), py::arg("training"), py::arg("running_mean"), py::arg("running_var"), py::arg("batches_tracked"),
-        py::arg("momentum"), py::arg("want_mask") = false);
+        py::arg("momentum"), py::arg("want_mask") = false, py::arg("sums_in") = py::none());
   m.def("batchnorm_bwd", &batchnorm_bwd, py::arg("dy"), py::arg("y"), py::arg("x"), py::arg("gamma"), py::arg("mean"), py::arg("invstd"),
         py::arg("relu"), py::arg("want_dres"), py::arg("grad_gamma") = py::none(), py::arg("grad_beta") = py::none(),
         py::arg("relu_mask") = py::none());

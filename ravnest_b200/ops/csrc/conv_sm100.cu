@@ -43,6 +43,8 @@ struct ConvParams {
   int relu;
   long long xs_w, xs_h, xs_n;     // host only: element strides of the input's W / H / N dimensions (0 = dense NHWC).  They may
                                   // OVERLAP (xs_w < Cin): the small-Cin stem reads 8 neighbouring 8-channel pixels as one 64-wide K block
+  float* stats;                   // [2][Cout] fp32 or nullptr: per-channel sum / sum of squares of the (bf16) output are ADDED here
+                                  // by the epilogue — the batch statistics of the BatchNorm that follows, without a pass over y
 };
 
 // 4-D / 3-D TMA loads and the 4-D store
@@ -83,7 +85,7 @@ struct ConvSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int BN, bool B_MN>
+template <int BN, bool B_MN, bool STATS = false>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                const __grid_constant__ CUtensorMap map_y, const ConvParams p) {
@@ -218,9 +220,23 @@ rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t slab_counter = 0;
+    const int et = threadIdx.x - 128;
+    ColStatsAcc<BN> cstats;           // STATS instantiations only: per-channel sum / sum of squares of the output (BatchNorm)
+    int stats_co0 = -1;
+    if constexpr (STATS) cstats.clear();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int wo0, ho0, n0, co0;
       decode(tile, wo0, ho0, n0, co0);
+      bool row_ok = true;
+      if constexpr (STATS) {
+        if (co0 != stats_co0) {                              // the CTA moves to another channel block: publish what it has summed
+          if (stats_co0 >= 0) cstats.flush(p.stats, p.Cout, stats_co0, et);
+          stats_co0 = co0;
+        }
+        // patch rows outside the output image (clipped by the TMA store) may hold non-zero accumulators: keep them out of the sums
+        const int tw = row_in_tile % p.TW, th = (row_in_tile / p.TW) % p.TH, tn = row_in_tile / (p.TW * p.TH);
+        row_ok = row_in_tile < rows && wo0 + tw < p.Wo && ho0 + th < p.Ho && n0 + tn < p.N;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -258,6 +274,12 @@ rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const 
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
+          if constexpr (STATS) {
+            if (!row_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = 0.f;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             const int chunk = half * 4 + (i >> 3);
@@ -278,9 +300,17 @@ rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const 
           tma_store_4d(&map_y, buf, col0, wo0, ho0, n0);        // rows of the patch in (n, h, w) order; clipped at borders
           tma_store_commit();
         }
+        if constexpr (STATS) {                                  // column sums of the staged slab (the store only reads it too)
+          float ds, dq;
+          slab_col_stats<CV_EPI_THREADS>(buf, et, ds, dq);
+          cstats.add(slab, ds, dq);
+        }
         ++slab_counter;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (STATS) {
+      if (stats_co0 >= 0) cstats.flush(p.stats, p.Cout, stats_co0, et);
     }
     if (issuer) tma_store_wait_all();
   }
@@ -356,7 +386,7 @@ static void pick_patch(int Wo, int Ho, int N, int& TW, int& TH, int& TN) {
   }
 }
 
-template <int BN, bool B_MN>
+template <int BN, bool B_MN, bool STATS = false>
 static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int num_sms, cudaStream_t stream) {
   using L = ConvSmem<BN>;
   CUtensorMap mx, mw, my;
@@ -396,7 +426,7 @@ static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int 
     e |= make_map_nd(&my, y, 4, dims, st, box, es);
   }
   if (e != 0) return 1000 + e;
-  auto kern = rvn_conv_implicit_gemm_tcgen05<BN, B_MN>;
+  auto kern = rvn_conv_implicit_gemm_tcgen05<BN, B_MN, STATS>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return 2000;
@@ -415,11 +445,13 @@ static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int 
 // xs_w / xs_h / xs_n: element strides of x's W / H / N dimensions (0 = dense NHWC); the channel stride is always 1.
 extern "C" int rvn_conv_forward_strided(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin,
                                         int Ho, int Wo, int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed,
-                                        long long xs_w, long long xs_h, long long xs_n, int num_sms, cudaStream_t stream) {
+                                        long long xs_w, long long xs_h, long long xs_n, float* stats, int num_sms,
+                                        cudaStream_t stream) {
   rvn::ConvParams p{};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout;
   p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.pad_w = pad_w; p.dil = dil;
   p.xs_w = xs_w; p.xs_h = xs_h; p.xs_n = xs_n;
+  p.stats = transposed ? nullptr : stats;
   p.flip = transposed;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.relu = relu;
@@ -429,6 +461,11 @@ extern "C" int rvn_conv_forward_strided(const void* x, const void* w, void* y, c
     if (wide) return rvn::conv_launch<256, true>(x, w, y, p, num_sms, stream);
     return rvn::conv_launch<128, true>(x, w, y, p, num_sms, stream);
   }
+  if (stats != nullptr) {
+    if (relu) return -7;               // the statistics are those of the convolution output itself
+    if (wide) return rvn::conv_launch<256, false, true>(x, w, y, p, num_sms, stream);
+    return rvn::conv_launch<128, false, true>(x, w, y, p, num_sms, stream);
+  }
   if (wide) return rvn::conv_launch<256, false>(x, w, y, p, num_sms, stream);
   return rvn::conv_launch<128, false>(x, w, y, p, num_sms, stream);
 }
@@ -436,8 +473,8 @@ extern "C" int rvn_conv_forward_strided(const void* x, const void* w, void* y, c
 extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho,
                                 int Wo, int Cout, int R, int S, int stride, int pad, int pad_w, int dil, int transposed, int num_sms,
                                 cudaStream_t stream) {
-  return rvn_conv_forward_strided(x, w, y, bias, relu, N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, pad_w, dil, transposed, 0, 0, 0, num_sms,
-                                  stream);
+  return rvn_conv_forward_strided(x, w, y, bias, relu, N, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, pad_w, dil, transposed, 0, 0, 0, nullptr,
+                                  num_sms, stream);
 }
 
 // ================================================================================================ weight gradient

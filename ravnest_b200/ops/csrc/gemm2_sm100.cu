@@ -44,6 +44,7 @@ struct Params {
   int act;
   int reduce_out;                 // D += acc by TMA reduce-add (gradient accumulation into the bucket) instead of a store
   int num_m2_blocks, num_n_blocks, num_k_blocks;
+  float* stats;                   // [2][N] fp32 or nullptr: column sums / sums of squares of the bf16 output are ADDED here (BatchNorm)
 };
 
 template <int BN>
@@ -121,7 +122,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STATS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 rvn_gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                            const __grid_constant__ CUtensorMap map_d, const Params p) {
@@ -246,9 +247,18 @@ rvn_gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap map_a, const __gr
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t slab_counter = 0;
+    ColStatsAcc<BN> cstats;           // STATS instantiations only (see gemm_sm100.cu)
+    int stats_n0 = -1;
+    if constexpr (STATS) cstats.clear();
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m0 = (tile % p.num_m2_blocks) * 256 + static_cast<int>(rank) * BLOCK_M;
       const int n0 = (tile / p.num_m2_blocks) * BN;
+      if constexpr (STATS) {
+        if (n0 != stats_n0) {                             // the pair moves to another column block: publish what this CTA has summed
+          if (stats_n0 >= 0) cstats.flush(p.stats, p.N, stats_n0, threadIdx.x - 128);
+          stats_n0 = n0;
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -306,9 +316,17 @@ rvn_gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap map_a, const __gr
           if (p.reduce_out) tma_reduce_add_2d(&map_d, buf, col0, m0); else tma_store_2d(&map_d, buf, col0, m0);
           tma_store_commit();
         }
+        if constexpr (STATS) {  // column sums of the staged slab; rows beyond M are zero (TMA zero-fills the A tail, no bias / activation)
+          float ds, dq;
+          slab_col_stats<EPI_THREADS>(buf, threadIdx.x - 128, ds, dq);
+          cstats.add(slab, ds, dq);
+        }
         ++slab_counter;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (STATS) {
+      if (stats_n0 >= 0) cstats.flush(p.stats, p.N, stats_n0, threadIdx.x - 128);
     }
     if (issuer) tma_store_wait_all();
   }
@@ -345,7 +363,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STATS = false>
 static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, Params p, int num_sms, cudaStream_t stream) {
   using L = Smem<BN>;
   constexpr int BH = BN / 2;
@@ -358,7 +376,7 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
   p.num_m2_blocks = (p.M + 255) / 256;
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  auto kern = rvn_gemm_bf16_tcgen05_2cta<BN, A_MN, B_MN>;
+  auto kern = rvn_gemm_bf16_tcgen05_2cta<BN, A_MN, B_MN, STATS>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess) return 2000;
@@ -376,12 +394,18 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 
 // 2-CTA GEMM entry: D[M,N] = act(op(A) op(B)^T + bias); layouts as in rvn_gemm_bf16.  block_n in {128, 256}.
 extern "C" int rvn_gemm_bf16_2cta(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N, int K,
-                                  const void* bias, int act, int reduce_out, int block_n, int num_sms, cudaStream_t stream) {
+                                  const void* bias, int act, int reduce_out, float* stats, int block_n, int num_sms, cudaStream_t stream) {
   rvn::g2::Params p{};
+  if (stats != nullptr && (bias != nullptr || act != 0 || reduce_out || a_mn || b_mn)) return -7;     // forward layout, plain store only
+  p.stats = stats;
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.act = act;
   p.reduce_out = reduce_out;
+  if (stats != nullptr) {
+    if (block_n == 128) return rvn::g2::launch<128, false, false, true>(A, lda, B, ldb, D, ldd, p, num_sms, stream);
+    return rvn::g2::launch<256, false, false, true>(A, lda, B, ldb, D, ldd, p, num_sms, stream);
+  }
 #define RVN_D2(BN_)                                                                                              \
   if (!a_mn && !b_mn) return rvn::g2::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, p, num_sms, stream);       \
   if (!a_mn && b_mn) return rvn::g2::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, p, num_sms, stream);         \

@@ -48,6 +48,8 @@ struct GemmParams {
   int split_k;                    // >1: work unit = (tile, k-slice); only with reduce_out (partials are summed by the L2)
   int reduce_out;                 // D += acc through TMA reduce-add (cp.reduce.async.bulk.tensor .add on the bf16 map) instead of
                                   // store: gradient accumulation into the flat bucket without reading it, and split-K safe
+  float* stats;                   // [2][N] fp32 or nullptr: column sums / sums of squares of the bf16 output are ADDED here (the batch
+                                  // statistics of a following BatchNorm; plain store epilogues without split-K only)
 };
 
 template <int BN>
@@ -114,7 +116,7 @@ __device__ __forceinline__ float apply_dact(float z, int act) {
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STATS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_aux,
@@ -291,10 +293,21 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_expect_tx(aux_bar, SLAB_BYTES);
       tma_load_2d(staging + SLAB_BYTES, &map_aux, aux_bar, (blockIdx.x / p.num_m_blocks) * BN, (blockIdx.x % p.num_m_blocks) * BLOCK_M);
     }
+    // STATS instantiations (forward layout only) also collect the column statistics of the output: a separate kernel, so the
+    // epilogue of every other GEMM keeps its register allocation and instruction stream (the runtime-flag version cost BERT 5 %)
+    ColStatsAcc<BN> cstats;
+    int stats_n0 = -1;
+    if constexpr (STATS) cstats.clear();
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int tile = unit % num_tiles;
       const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
       const int n0 = (tile / p.num_m_blocks) * BN;
+      if constexpr (STATS) {
+        if (n0 != stats_n0) {                             // the CTA moves to another column block: publish what it has summed
+          if (stats_n0 >= 0) cstats.flush(p.stats, p.N, stats_n0, threadIdx.x - 128);
+          stats_n0 = n0;
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -411,9 +424,17 @@ rvn_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
           }
         }
+        if constexpr (STATS) {  // column sums of the staged slab; rows beyond M are zero (TMA zero-fills the A tail, no bias / activation)
+          float ds, dq;
+          slab_col_stats<EPI_THREADS>(buf_main, threadIdx.x - 128, ds, dq);
+          cstats.add(slab, ds, dq);
+        }
         ++slab_counter;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (STATS) {
+      if (stats_n0 >= 0) cstats.flush(p.stats, p.N, stats_n0, threadIdx.x - 128);
     }
     if (issuer) tma_store_wait_all();
   }
@@ -463,7 +484,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool STATS = false>
 static int launch(const void* A, int lda, const void* B, int ldb, void* D, int ldd, void* aux_out, int ld_auxout,
                   void* b_copy_dst, int ld_bcopy, GemmParams p, int num_sms, cudaStream_t stream) {
   if (p.bcopy_flags == nullptr) b_copy_dst = nullptr;
@@ -494,7 +515,7 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
   p.num_m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  auto kern = rvn_gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  auto kern = rvn_gemm_bf16_tcgen05<BN, A_MN, B_MN, STATS>;
   static bool configured = false;
   if (!configured) {
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
@@ -516,8 +537,11 @@ static int launch(const void* A, int lda, const void* B, int ldb, void* D, int l
 extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* D, int ldd, int M, int N,
                              int K, const void* bias, int act, const void* dact_in, int ld_dact, int aux_mode, void* preact_out,
                              int ld_preact, int preact_mode, void* b_copy_dst, int ld_bcopy, unsigned* bcopy_flags, unsigned bcopy_epoch, int block_n,
-                             int split_k, int reduce_out, int num_sms, cudaStream_t stream) {
+                             int split_k, int reduce_out, float* stats, int num_sms, cudaStream_t stream) {
   rvn::GemmParams p{};
+  p.stats = (split_k <= 1 && !reduce_out && bias == nullptr && act == 0 && dact_in == nullptr && preact_out == nullptr && !a_mn && !b_mn &&
+             b_copy_dst == nullptr) ? stats : nullptr;
+  if (stats != nullptr && p.stats == nullptr) return -7;     // column statistics: forward layout, plain store epilogue only
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.dact_in = static_cast<const __nv_bfloat16*>(dact_in);
@@ -529,6 +553,11 @@ extern "C" int rvn_gemm_bf16(const void* A, int lda, int a_mn, const void* B, in
   p.bcopy_epoch = bcopy_epoch;
   p.split_k = split_k;
   p.reduce_out = reduce_out;
+  if (p.stats != nullptr) {
+    if (block_n == 256) return rvn::launch<256, false, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);
+    if (block_n == 192) return rvn::launch<192, false, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);
+    return rvn::launch<128, false, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);
+  }
 #define RVN_DISPATCH(BN_)                                                                                              \
   if (!a_mn && !b_mn) return rvn::launch<BN_, false, false>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream); \
   if (!a_mn && b_mn) return rvn::launch<BN_, false, true>(A, lda, B, ldb, D, ldd, preact_out, ld_preact, b_copy_dst, ld_bcopy, p, num_sms, stream);   \

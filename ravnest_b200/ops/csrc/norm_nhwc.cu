@@ -374,13 +374,15 @@ static int bn_grid(size_t nvec, int C, int num_sms, int waves) {
 extern "C" int rvn_batchnorm_forward(const void* x, const void* res, const void* gamma, const void* beta, void* running_mean,
                                      void* running_var, long long* batches_tracked, float* mean, float* invstd, float* sums, void* y,
                                      long long M, int C, float eps, float momentum, int relu, int training, int param_bf16,
-                                     int stats_bf16, void* relu_mask, int num_sms, cudaStream_t stream) {
+                                     int stats_bf16, void* relu_mask, int sums_ready, int num_sms, cudaStream_t stream) {
   if (C % 8 != 0 || C > 4096) return -2;
   const size_t nvec = static_cast<size_t>(M) * C / 8;
   using T = const __nv_bfloat16*;
   if (training) {
-    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream);
-    rvn::rvn_bn_stats<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)x, sums, nvec, C);
+    if (!sums_ready) {       // (sums_ready: the producing GEMM / convolution epilogue already collected sum and sum of squares)
+      cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream);
+      rvn::rvn_bn_stats<<<bn_grid(nvec, C, num_sms, 4), 256, 2 * C * sizeof(float), stream>>>((T)x, sums, nvec, C);
+    }
     rvn::rvn_bn_finalize<<<(C + 127) / 128, 128, 0, stream>>>(sums, mean, invstd, running_mean, running_var, batches_tracked,
                                                                static_cast<float>(M), eps, momentum, C, stats_bf16);
   }

@@ -163,4 +163,57 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ------------------------------------------------------------------------------------------------ column statistics in the epilogue
+// BatchNorm's batch statistics (per-channel sum and sum of squares of the convolution output) taken from the producing kernel's
+// epilogue instead of a separate pass over the activation.  The epilogue stages every 128 x 64 bf16 slab in 128-byte swizzled smem
+// for the TMA store; after the staging barrier, thread t of the NT epilogue threads walks column t % 64 over its 128 / (NT / 64)
+// rows of that slab (a warp reads 32 neighbouring columns of one row: 64 contiguous bytes, conflict free), so the statistics are
+// those of the bf16 values BatchNorm will read.  Rows that must not count (M tail, patch rows outside the image) are staged as zeros.
+template <int NT>
+__device__ __forceinline__ void slab_col_stats(const uint8_t* buf, int t, float& s, float& q) {
+  constexpr int ROWS = 128 / (NT / 64);
+  const int col = t & 63, r0 = (t >> 6) * ROWS;
+  const uint32_t chunk = static_cast<uint32_t>(col >> 3), within = static_cast<uint32_t>(col & 7) * 2u;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < ROWS; r += 4) {
+    const int ra = r0 + r;
+    const float v0 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(buf + ra * 128 + ((chunk ^ (ra & 7)) << 4) + within));
+    const float v1 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(buf + (ra + 1) * 128 + ((chunk ^ ((ra + 1) & 7)) << 4) + within));
+    const float v2 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(buf + (ra + 2) * 128 + ((chunk ^ ((ra + 2) & 7)) << 4) + within));
+    const float v3 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(buf + (ra + 3) * 128 + ((chunk ^ ((ra + 3) & 7)) << 4) + within));
+    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1); q2 = fmaf(v2, v2, q2); q3 = fmaf(v3, v3, q3);
+  }
+  s = (s0 + s1) + (s2 + s3);
+  q = (q0 + q1) + (q2 + q3);
+}
+
+// per-thread running sums over the tiles of one n-block (column block); flushed with NT / 64 atomics per column when the CTA moves on
+template <int BN>
+struct ColStatsAcc {
+  float s[BN / 64], q[BN / 64];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < BN / 64; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  }
+  __device__ __forceinline__ void add(int slab, float ds, float dq) {
+#pragma unroll
+    for (int k = 0; k < BN / 64; ++k)
+      if (k == slab) { s[k] += ds; q[k] += dq; }
+  }
+  // stats: [2][N] fp32 (sums, then sums of squares)
+  __device__ __forceinline__ void flush(float* stats, int N, int n0, int t) {
+#pragma unroll
+    for (int k = 0; k < BN / 64; ++k) {
+      const int col = n0 + k * 64 + (t & 63);
+      if (col < N) {
+        atomicAdd(stats + col, s[k]);
+        atomicAdd(stats + N + col, q[k]);
+      }
+      s[k] = 0.f; q[k] = 0.f;
+    }
+  }
+};
+
 }  // namespace rvn

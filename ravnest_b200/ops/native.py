@@ -10,6 +10,8 @@ B^T when ``b_mn`` (B stored [K,N]).  So for ``y = x W^T``:
 import math
 from collections import Counter
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -484,13 +486,13 @@ class _ConvNHWC(torch.autograd.Function):
     ``weight`` is the [O, I, kh, kw] parameter itself; stored channels_last (ParamStore does) its OHWI view is free."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, weight, bias, stride, pad, dil, relu, pad_w=-1):
+    def forward(ctx, x_nhwc, weight, bias, stride, pad, dil, relu, pad_w=-1, stats=None):
         w_ohwi = weight.permute(0, 2, 3, 1)
         if not w_ohwi.is_contiguous():
             w_ohwi = w_ohwi.contiguous()
             calls['conv_weight_permute'] += 1
         pad_w = pad if pad_w < 0 else pad_w
-        y = C().conv_nhwc(x_nhwc, w_ohwi, bias, stride, pad, dil, relu, False, 0, 0, pad_w)
+        y = C().conv_nhwc(x_nhwc, w_ohwi, bias, stride, pad, dil, relu, False, 0, 0, pad_w, stats)
         calls['conv_fwd'] += 1
         ctx.cfg = (stride, pad, dil, relu)
         ctx.pad_w = pad_w
@@ -528,7 +530,7 @@ class _ConvNHWC(torch.autograd.Function):
             if need_dw:
                 dw = gw
             db = gb
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 class _Conv1x1(torch.autograd.Function):
@@ -537,10 +539,10 @@ class _Conv1x1(torch.autograd.Function):
     on the split-K wgrad kernel (pixel patches as the reduction dimension, fp32 atomics) instead of the TT GEMM."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, weight, bias):
+    def forward(ctx, x_nhwc, weight, bias, stats=None):
         n, h, w, c = x_nhwc.shape
         w2 = weight.reshape(weight.shape[0], c)
-        y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, bias, 0, None, False, 0)[0]
+        y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, bias, 0, None, False, 0, col_stats=stats)[0]
         calls['conv1x1_as_gemm'] += 1
         ctx.has_bias = bias is not None
         ctx.wgrad_acc = _wgrad_acc_of(weight)
@@ -562,7 +564,7 @@ class _Conv1x1(torch.autograd.Function):
             calls['conv_wgrad'] += 1
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy2, w2)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class _Conv1x1Fork(torch.autograd.Function):
@@ -574,10 +576,10 @@ class _Conv1x1Fork(torch.autograd.Function):
     fresh one), as ``nn.Conv2d(fork=True)`` in ``models/resnet.py`` does."""
 
     @staticmethod
-    def forward(ctx, x_nhwc, weight):
+    def forward(ctx, x_nhwc, weight, stats=None):
         n, h, w, c = x_nhwc.shape
         w2 = weight.reshape(weight.shape[0], c)
-        y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, None, 0, None, False, 0)[0]
+        y2 = C().gemm(x_nhwc.reshape(n * h * w, c), False, w2, False, None, 0, None, False, 0, col_stats=stats)[0]
         calls['conv1x1_as_gemm'] += 1
         ctx.wgrad_acc = _wgrad_acc_of(weight)
         ctx.set_materialize_grads(False)
@@ -609,7 +611,7 @@ class _Conv1x1Fork(torch.autograd.Function):
                 calls['conv_wgrad'] += 1
         elif ctx.needs_input_grad[0]:
             dx = dskip
-        return dx, dw
+        return dx, dw, None
 
 
 class _ConvSmallCin(torch.autograd.Function):
@@ -621,7 +623,7 @@ class _ConvSmallCin(torch.autograd.Function):
     gradient only (images carry no gradient)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, ph, pw):
+    def forward(ctx, x, weight, bias, stride, ph, pw, stats=None):
         n, cin, h, w = x.shape
         cout, _, kh, kw = weight.shape
         ho = (h + 2 * ph - kh) // stride + 1
@@ -634,7 +636,7 @@ class _ConvSmallCin(torch.autograd.Function):
         xv = _stem_view(xp, hv, wv)
         wrow = torch.zeros(cout, kh, 8, 8, dtype=torch.bfloat16, device=x.device)
         wrow[:, :, :kw, :cin] = weight.permute(0, 2, 3, 1)
-        y = C().conv_nhwc(xv, wrow.view(cout, kh, 1, 64), bias, stride, 0, 1, False, False, 0, 0, 0)
+        y = C().conv_nhwc(xv, wrow.view(cout, kh, 1, 64), bias, stride, 0, 1, False, False, 0, 0, 0, stats)
         calls['conv_stem'] += 1
         ctx.cfg = (stride, kh, kw, cin)
         ctx.has_bias = bias is not None
@@ -658,7 +660,7 @@ class _ConvSmallCin(torch.autograd.Function):
                 dw = d_ohwi.permute(0, 3, 1, 2).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(dy.view(-1, dy.shape[-1]), bias)
-        return None, dw, db, None, None, None
+        return None, dw, db, None, None, None, None
 
 
 _STEM_OVERLAP_OK = True
@@ -679,9 +681,25 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+def _with_bn_sums(y, sums):
+    """Attach the per-channel (sum, sum of squares) the producing kernel's epilogue collected to the activation object:
+    ``batch_norm_act`` on this very tensor then skips its statistics pass (BatchNorm = finalize + apply)."""
+    if sums is not None:
+        y._rvn_bn_sums = sums
+        calls['conv_bn_stats'] += 1
+    return y
+
+
+def _new_bn_sums(weight, bn_stats):
+    if bn_stats and BN_STATS_FROM_CONV:
+        return torch.zeros(2 * weight.shape[0], dtype=torch.float32, device=weight.device)
+    return None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, bn_stats=False):
     """NCHW-shaped, channels_last-strided tensors in and out (what torch modules exchange); inside, NHWC views feed either the
-    tcgen05 GEMM (pointwise convs: in NHWC a 1x1 conv IS ``[N*H*W, Cin] x [Cout, Cin]^T``) or the implicit-GEMM conv kernel."""
+    tcgen05 GEMM (pointwise convs: in NHWC a 1x1 conv IS ``[N*H*W, Cin] x [Cout, Cin]^T``) or the implicit-GEMM conv kernel.
+    ``bn_stats``: a training BatchNorm follows — the epilogue also sums y and y^2 per channel (see ``_with_bn_sums``)."""
     kh, kw = weight.shape[2], weight.shape[3]
     sh, sw = _pair(stride)
     dh, dw_ = _pair(dilation)
@@ -697,8 +715,9 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
             and dh == 1 and dw_ == 1 and weight.dtype == torch.bfloat16 and x.dtype in (torch.bfloat16, torch.float32)
             and not x.requires_grad and (bias is None or bias.dtype == torch.bfloat16)):
         # image stems (RGB / grey-scale): 8-channel zero-bordered pack + overlapping-stride TMA im2col, see _ConvSmallCin
-        y = _stem_apply(x, weight, bias, sh, ph, pw)
-        return y.permute(0, 3, 1, 2)
+        sums = _new_bn_sums(weight, bn_stats)
+        y = _stem_apply(x, weight, bias, sh, ph, pw, sums)
+        return _with_bn_sums(y.permute(0, 3, 1, 2), sums)
     if base_ok and kh == 1 and kw == 1 and ph == 0 and pw == 0 and not (strided and STRIDED_1X1_IMPLICIT and sh == sw and sh == 2):
         # (strided pointwise convs — ResNet's three downsample projections — take the implicit-GEMM kernel below: its TMA box load
         #  strides over the input pixels itself, where the sub-sampling slice here costs a strided copy forward and a fill + strided
@@ -707,35 +726,40 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
             x = x[:, :, ::sh, ::sw]
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight, bias)           # zero-copy NHWC view in, NHWC out
-        return y.permute(0, 3, 1, 2)                                      # NCHW-shaped, channels_last-strided
+        sums = _new_bn_sums(weight, bn_stats and bias is None)
+        y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight, bias, sums)     # zero-copy NHWC view in, NHWC out
+        return _with_bn_sums(y.permute(0, 3, 1, 2), sums)                 # NCHW-shaped, channels_last-strided
     if base_ok and sh == sw and dh == dw_ and sh in (1, 2) and IMPLICIT_GEMM_CONV and (kh == kw and ph == pw or RECTANGULAR_CONV):
         # square and rectangular (Inception's 1x7 / 7x1 / 1x3 / 3x1, separate vertical / horizontal padding) kernels
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), weight, bias, sh, ph, dh, False, pw)
-        return y.permute(0, 3, 1, 2)
+        sums = _new_bn_sums(weight, bn_stats)
+        y = _ConvNHWC.apply(x.permute(0, 2, 3, 1), weight, bias, sh, ph, dh, False, pw, sums)
+        return _with_bn_sums(y.permute(0, 3, 1, 2), sums)
     fallbacks['conv2d'] += 1
     return F.conv2d(x, weight, bias, stride, padding, dilation, groups)
 
 
-def _stem_apply(x, weight, bias, stride, ph, pw):
+def _stem_apply(x, weight, bias, stride, ph, pw, sums=None):
     global _STEM_OVERLAP_OK
     try:
-        return _ConvSmallCin.apply(x, weight, bias, stride, ph, pw)
+        return _ConvSmallCin.apply(x, weight, bias, stride, ph, pw, sums)
     except RuntimeError as exc:
         if not _STEM_OVERLAP_OK or 'conv_forward' not in str(exc):
             raise
         _STEM_OVERLAP_OK = False          # tensor-map encoder rejected the overlapping view: use the materialised one from now on
-        return _ConvSmallCin.apply(x, weight, bias, stride, ph, pw)
+        if sums is not None:
+            sums.zero_()
+        return _ConvSmallCin.apply(x, weight, bias, stride, ph, pw, sums)
 
 
-def conv1x1_fork(x, weight):
+def conv1x1_fork(x, weight, bn_stats=False):
     """``(conv1x1(x), x)`` for the block-opening pointwise convolution of a residual block (NCHW-shaped channels_last bf16)."""
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
-    y, skip = _Conv1x1Fork.apply(x.permute(0, 2, 3, 1), weight)
-    return y.permute(0, 3, 1, 2), skip.permute(0, 3, 1, 2)
+    sums = _new_bn_sums(weight, bn_stats)
+    y, skip = _Conv1x1Fork.apply(x.permute(0, 2, 3, 1), weight, sums)
+    return _with_bn_sums(y.permute(0, 3, 1, 2), sums), skip.permute(0, 3, 1, 2)
 
 
 def wgrad_flush(acc, grad):
@@ -749,6 +773,7 @@ NATIVE_CONV_WGRAD = True
 SMALL_CIN_STEM = True
 CONV_FORK_ACCUMULATE = True
 WGRAD_STAGING = True
+BN_STATS_FROM_CONV = os.environ.get('RAVNEST_BN_STATS_FROM_CONV', '1') != '0'      # BatchNorm statistics from the producer's epilogue
 STRIDED_1X1_IMPLICIT = True
 RECTANGULAR_CONV = True
 BN_RELU_BITMASK = True
@@ -760,9 +785,11 @@ class _BatchNormAct(torch.autograd.Function):
     are accumulated straight into the flat gradient bucket when the leaves carry one (no cast / add launches per layer)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu, eps, running_mean, running_var, batches_tracked, momentum):
+    def forward(ctx, x, weight, bias, residual, relu, eps, running_mean, running_var, batches_tracked, momentum, sums=None):
         outs = C().batchnorm_fwd(x, residual, weight, bias, None, None, eps, relu, True, running_mean, running_var,
-                                 batches_tracked, momentum, BN_RELU_BITMASK and relu)
+                                 batches_tracked, momentum, BN_RELU_BITMASK and relu, sums)
+        if sums is not None:
+            calls['batchnorm_stats_from_producer'] += 1
         y, mean, invstd = outs[0], outs[1], outs[2]
         mask = outs[3] if len(outs) > 3 else None          # ReLU sign bits: backward reads 1 byte per 8 elements instead of y
         calls['batchnorm_fwd'] += 1
@@ -781,13 +808,16 @@ class _BatchNormAct(torch.autograd.Function):
         calls['batchnorm_bwd'] += 1
         if ctx.has_res and not ctx.relu:
             dres = dy
-        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None
+        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None, None
 
 
 def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, relu=False, training=True, momentum=0.1, eps=1e-5,
                    num_batches_tracked=None):
     """x / residual / result: NCHW-shaped channels_last bf16 tensors.  Training mode updates the running statistics."""
     n, c, h, w = x.shape
+    sums = getattr(x, '_rvn_bn_sums', None) if (training and BN_STATS_FROM_CONV) else None     # collected by the producing epilogue
+    if sums is not None and sums.numel() != 2 * c:
+        sums = None
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     x2 = x.permute(0, 2, 3, 1)
@@ -798,7 +828,7 @@ def batch_norm_act(x, weight, bias, running_mean, running_var, residual=None, re
         r2 = residual.permute(0, 2, 3, 1)
     if training:
         y2 = _BatchNormAct.apply(x2, weight, bias, r2, relu, eps, running_mean, running_var,
-                                 num_batches_tracked if running_mean is not None else None, momentum)
+                                 num_batches_tracked if running_mean is not None else None, momentum, sums)
         if running_mean is None and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
     else:

@@ -439,6 +439,74 @@ def test_conv_wgrad_staging_and_flush():
         assert _rel_err(grads[name], p.grad) < 5e-2, name
 
 
+@pytest.mark.parametrize('N,C,H,W,K,kh,kw,stride,ph,pw', [
+    (4, 64, 56, 56, 64, 3, 3, 1, 1, 1),            # conv kernel, BN = 128 with 64 live columns
+    (5, 128, 28, 28, 512, 3, 3, 2, 1, 1),          # conv kernel, several channel blocks, stride 2, clipped patches
+    (3, 64, 17, 19, 96, 1, 7, 1, 0, 3),            # rectangular kernel, odd extents (patch rows outside the image)
+    (2, 256, 14, 14, 512, 1, 1, 2, 0, 0),          # strided pointwise convolution (conv kernel)
+    (6, 256, 14, 14, 64, 1, 1, 1, 0, 0),           # pointwise convolution: tcgen05 GEMM, M tail (1176 rows)
+    (100, 64, 56, 56, 256, 1, 1, 1, 0, 0),         # pointwise convolution large enough for the CTA-pair GEMM
+    (7, 512, 7, 7, 2048, 1, 1, 1, 0, 0),           # wide N: many column blocks per CTA
+    (3, 3, 64, 64, 64, 7, 7, 2, 3, 3)])            # image stem
+def test_conv_epilogue_collects_batchnorm_statistics(N, C, H, W, K, kh, kw, stride, ph, pw):
+    """``bn_stats=True``: the GEMM / convolution epilogue sums y and y^2 per output channel (of the bf16 values it stores) and
+    ``batch_norm_act`` consumes them instead of running its statistics kernel — same result as the two-pass BatchNorm."""
+    from ravnest_b200 import ops
+    from ravnest_b200.ops import native
+    torch.manual_seed(31)
+    x = _rand(N, C, H, W)
+    x = x if C < 8 else x.contiguous(memory_format=torch.channels_last)
+    w = _rand(K, C, kh, kw, scale=0.05).contiguous(memory_format=torch.channels_last)
+    y = ops.conv2d(x, w, None, stride, (ph, pw), 1, 1, bn_stats=True)
+    sums = getattr(y, '_rvn_bn_sums', None)
+    assert sums is not None and sums.shape == (2 * K,)
+    y_plain = ops.conv2d(x, w, None, stride, (ph, pw), 1, 1)
+    assert torch.equal(y, y_plain) and getattr(y_plain, '_rvn_bn_sums', None) is None
+    yf = y.float()
+    ref_s, ref_q = yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))
+    scale = float(yf.abs().mean()) * yf.numel() / K
+    assert float((sums[:K] - ref_s).abs().max()) < 2e-4 * scale, float((sums[:K] - ref_s).abs().max()) / scale
+    assert _rel_err(sums[K:], ref_q) < 1e-4
+    # BatchNorm on top: statistics from the epilogue vs its own statistics kernel
+    g, b = _rand(K).float().abs().add(0.5).to(torch.bfloat16), _rand(K)
+    outs = []
+    for t in (y, y_plain):
+        rm, rv = torch.zeros(K, device=DEV), torch.ones(K, device=DEV)
+        before = native.calls['batchnorm_stats_from_producer']
+        o = ops.batch_norm_act(t, g, b, rm, rv, None, True, True, 0.1, 1e-5)
+        outs.append((o, rm, rv, native.calls['batchnorm_stats_from_producer'] - before))
+    assert outs[0][3] == 1 and outs[1][3] == 0
+    assert _rel_err(outs[0][0], outs[1][0]) < 5e-3
+    assert _rel_err(outs[0][1], outs[1][1]) < 1e-3 and _rel_err(outs[0][2], outs[1][2]) < 1e-3
+
+
+def test_resnet_block_with_fused_statistics_matches_two_pass_batchnorm():
+    """A ResNet bottleneck pair (downsample + identity block: fork, staged statistics, fused BN+add+ReLU) with and without the
+    epilogue statistics: same loss and gradients."""
+    from ravnest_b200.models.resnet import Bottleneck
+    from ravnest_b200.ops import native
+    torch.manual_seed(32)
+    net = torch.nn.Sequential(Bottleneck(64, 64, 1, downsample=True), Bottleneck(256, 64), Bottleneck(256, 128, 2, downsample=True)).to(DEV, torch.bfloat16)
+    net = net.to(memory_format=torch.channels_last).train()
+    x = _rand(8, 64, 28, 28).contiguous(memory_format=torch.channels_last)
+    res = {}
+    for on in (True, False):
+        native.BN_STATS_FROM_CONV = on
+        net.zero_grad(set_to_none=True)
+        before = native.calls['batchnorm_stats_from_producer']
+        y = net(x)
+        loss = y.float().pow(2).mean()
+        loss.backward()
+        res[on] = (float(loss), {n: p.grad.float().clone() for n, p in net.named_parameters()},
+                   native.calls['batchnorm_stats_from_producer'] - before)
+    native.BN_STATS_FROM_CONV = True
+    assert res[True][2] == 11 and res[False][2] == 0           # 3 + 3 + 3 convolutions + 2 downsample projections
+    assert abs(res[True][0] - res[False][0]) < 1e-2 * abs(res[False][0])
+    floor = 1e-2 * max(float(g.norm()) for g in res[False][1].values())
+    for n, g in res[False][1].items():
+        assert float((res[True][1][n] - g).norm()) / (float(g.norm()) + floor) < 5e-2, n
+
+
 @pytest.mark.parametrize('N,C,H,W', [(8, 64, 56, 56), (4, 256, 28, 28), (3, 2048, 7, 7), (2, 48, 17, 17)])
 @pytest.mark.parametrize('relu,with_res', [(True, False), (True, True), (False, False)])
 def test_batchnorm_relu_add(N, C, H, W, relu, with_res):
