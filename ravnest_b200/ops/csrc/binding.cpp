@@ -44,6 +44,8 @@ int rvn_conv_forward_strided(const void* x, const void* w, void* y, const void* 
 int rvn_conv_wgrad_strided(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
                            int stride, int pad, int pad_w, int dil, long long xs_w, long long xs_h, long long xs_n, int num_sms,
                            cudaStream_t stream);
+int rvn_conv_dgrad_s2(const void* dy, const void* w, void* dx, int N, int Ho, int Wo, int Cout, int H, int W, int Cin, int R, int S, int pad,
+                      int pad_w, int num_sms, cudaStream_t stream);
 int rvn_stem_pack(const void* x, int x_is_bf16, void* out, int N, int C, int H, int W, int Hp, int Wp, int pad_h, int pad_w, long long sn,
                   long long sc, long long sh, long long sw, int num_sms, cudaStream_t stream);
 int rvn_wgrad_flush(float* acc, void* grad, int grad_is_bf16, size_t n, int num_sms, cudaStream_t stream);
@@ -238,7 +240,9 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
     stats_ptr = col_stats->data_ptr<float>();
     split_k = 1;
   }
-  const bool explicit_tiling = block_n > 0 || (split_k > 0 && stats_ptr == nullptr);
+  // RVN_STATS_PAIR=0: GEMMs that collect column statistics stay on the single-CTA kernel (its statistics pass is cheaper per tile)
+  static const bool stats_on_pair = [] { const char* e = std::getenv("RVN_STATS_PAIR"); return e == nullptr || std::atoi(e) != 0; }();
+  const bool explicit_tiling = block_n > 0 || (split_k > 0 && stats_ptr == nullptr) || (stats_ptr != nullptr && !stats_on_pair);
   const double cost1 = choose_tiling(M, N, K, reduce_out, sm_count(), &block_n, &split_k);
   // plain epilogues (bias / activation, or accumulate-into-output) may run on the CTA-pair kernel when the wave model prefers it
   if (!explicit_tiling && dact_ptr == nullptr && !store_preact && !(b_copy_dst.has_value() && b_copy_dst->defined()) && M >= 256) {
@@ -273,6 +277,16 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   res.push_back(D.size(1) == N ? D : D.narrow(1, 0, N));
   if (store_preact) res.push_back(P.size(1) == N ? P : P.narrow(1, 0, N));
   return res;
+}
+
+// would gemm() route a plain M x N x K product to the CTA-pair kernel?  (the caller may prefer not to fuse extra epilogue work there)
+bool gemm_prefers_pair(int64_t M, int64_t N, int64_t K) {
+  if (M < 256) return false;
+  int64_t bn = 0, sk = 0;
+  int bn2 = 256;
+  const double cost1 = choose_tiling(static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), false, sm_count(), &bn, &sk);
+  const double cost2 = pair_tiling_cost(static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), sm_count(), &bn2);
+  return cost2 < 0.97 * cost1;
 }
 
 // 2-CTA (cta_group::2, 256 x BN tile per CTA pair) GEMM: D = act(op(A) op(B)^T + bias).  Plain epilogue only (see gemm2_sm100.cu).
@@ -618,6 +632,23 @@ torch::Tensor conv_nhwc(const torch::Tensor& x, const torch::Tensor& w, const c1
   return y;
 }
 
+// data gradient of a stride-2 convolution: dy [N,Ho,Wo,Cout], w [Cout,R,S,Cin] -> dx [N,H,W,Cin] (four parity phases, conv_sm100.cu)
+torch::Tensor conv_dgrad_s2(const torch::Tensor& dy, const torch::Tensor& w, int64_t H, int64_t W, int64_t pad, int64_t pad_w) {
+  if (pad_w < 0) pad_w = pad;
+  c10::cuda::CUDAGuard guard(dy.device());
+  TORCH_CHECK(dy.is_contiguous() && w.is_contiguous() && dy.dim() == 4 && w.dim() == 4 && dy.scalar_type() == torch::kBFloat16 &&
+              w.scalar_type() == torch::kBFloat16 && dy.size(3) == w.size(0), "conv_dgrad_s2 expects contiguous bf16 dy [N,Ho,Wo,Cout], w [Cout,R,S,Cin]");
+  const int N = dy.size(0), Ho = dy.size(1), Wo = dy.size(2), Cout = dy.size(3);
+  const int R = w.size(1), S = w.size(2), Cin = w.size(3);
+  TORCH_CHECK(Cin % 8 == 0 && Cout % 8 == 0, "channel counts must be multiples of 8");
+  TORCH_CHECK((H + 2 * pad - R) / 2 + 1 == Ho && (W + 2 * pad_w - S) / 2 + 1 == Wo, "dy does not match a stride-2 convolution of an H x W input");
+  auto dx = (R == 1 || S == 1) ? torch::zeros({N, H, W, Cin}, dy.options()) : torch::empty({N, H, W, Cin}, dy.options());
+  check(rvn_conv_dgrad_s2(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), N, Ho, Wo, Cout, static_cast<int>(H), static_cast<int>(W), Cin, R, S,
+                          static_cast<int>(pad), static_cast<int>(pad_w), sm_count(), cur_stream()),
+        "conv_dgrad_s2");
+  return dx;
+}
+
 // dy [N,Ho,Wo,Cout], x [N,H,W,Cin] (NHWC bf16, x possibly a strided view) -> dW [Cout,R,S,Cin] fp32.  With `acc` (a contiguous fp32
 // tensor of that many elements, e.g. the stage's persistent weight-gradient accumulator) the gradient is ADDED into it and returned
 torch::Tensor conv_wgrad_nhwc(const torch::Tensor& dy, const torch::Tensor& x, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t dil,
@@ -913,6 +944,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("aux_in") = py::none(), py::arg("store_preact") = false,
         py::arg("block_n") = 0, py::arg("aux_mode") = 1, py::arg("out") = py::none(), py::arg("b_copy_dst") = py::none(),
         py::arg("bcopy_flags") = py::none(), py::arg("bcopy_epoch") = 0, py::arg("split_k") = 0, py::arg("col_stats") = py::none());
+  m.def("gemm_prefers_pair", &gemm_prefers_pair);
   m.def("gemm_2cta", &gemm_2cta, "bf16 tcgen05 GEMM on CTA pairs (cta_group::2)", py::arg("A"), py::arg("a_mn"), py::arg("B"), py::arg("b_mn"),
         py::arg("bias") = py::none(), py::arg("act") = 0, py::arg("block_n") = 256);
   m.def("layernorm_fwd", &layernorm_fwd);
@@ -939,6 +971,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("relu_mask") = py::none());
   m.def("conv_wgrad_nhwc", &conv_wgrad_nhwc, py::arg("dy"), py::arg("x"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"),
         py::arg("dil"), py::arg("pad_w") = -1, py::arg("acc") = py::none());
+  m.def("conv_dgrad_s2", &conv_dgrad_s2, "data gradient of a stride-2 convolution (four parity phases of the implicit-GEMM kernel)");
   m.def("stem_pack", &stem_pack, "zero-bordered 8-channel NHWC bf16 copy of an image batch");
   m.def("wgrad_flush", &wgrad_flush, "grad += acc; acc = 0");
   m.def("fmha_fwd", &fmha_fwd);

@@ -45,6 +45,12 @@ struct ConvParams {
                                   // OVERLAP (xs_w < Cin): the small-Cin stem reads 8 neighbouring 8-channel pixels as one 64-wide K block
   float* stats;                   // [2][Cout] fp32 or nullptr: per-channel sum / sum of squares of the (bf16) output are ADDED here
                                   // by the epilogue — the batch statistics of the BatchNorm that follows, without a pass over y
+  // one output-parity phase (a, b) of a STRIDE-2 data gradient (rvn_conv_dgrad_s2): dx[2h'+a, 2w'+b] only receives the filter taps
+  // r = r0 + 2i, s = s0 + 2j (r0 = (a + pad) % 2, ...), read from dy[h' + ch - i, w' + cw - j] — a stride-1 convolution of dy with a
+  // sub-sampled filter, written through a tensor map that addresses every second pixel of dx
+  int sub;                        // 1: phase mode
+  int r0, s0, Ra, Sb, ch, cw;
+  long long ys_w, ys_h, ys_n;     // host only: element strides of the output's W / H / N dimensions (0 = dense NHWC)
 };
 
 // 4-D / 3-D TMA loads and the 4-D store
@@ -106,7 +112,7 @@ rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const 
   const int warp = threadIdx.x >> 5;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int num_tiles = m_tiles * p.num_n_blocks;
-  const int num_k_blocks = p.R * p.S * p.cin_blocks;
+  const int num_k_blocks = (p.sub ? p.Ra * p.Sb : p.R * p.S) * p.cin_blocks;
   const int rows = p.TW * p.TH * p.TN;                    // valid rows of an A tile / output patch
   const uint32_t a_bytes = static_cast<uint32_t>(rows) * 128u;
 
@@ -160,16 +166,26 @@ rvn_conv_implicit_gemm_tcgen05(const __grid_constant__ CUtensorMap map_x, const 
         int wo0, ho0, n0, co0;
         decode(tile, wo0, ho0, n0, co0);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          const int tap = kb / p.cin_blocks;
+          int tap = kb / p.cin_blocks;
           const int c0 = (kb % p.cin_blocks) * CV_BLOCK_K;
-          int r = tap / p.S, s = tap % p.S;
-          if (p.flip) { r = p.R - 1 - r; s = p.S - 1 - s; }
+          int xw, xh;
+          if (p.sub) {                                           // stride-2 dgrad phase: sub-sampled filter, see ConvParams
+            const int i = tap / p.Sb, j = tap % p.Sb;
+            tap = (p.r0 + 2 * i) * p.S + (p.s0 + 2 * j);
+            xh = ho0 + p.ch - i;
+            xw = wo0 + p.cw - j;
+          } else {
+            int r = tap / p.S, s = tap % p.S;
+            if (p.flip) { r = p.R - 1 - r; s = p.S - 1 - s; }
+            xw = wo0 * p.stride + s * p.dil - p.pad_w;
+            xh = ho0 * p.stride + r * p.dil - p.pad;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], a_bytes + L::B_BYTES);
           // input patch of this tap: coordinates may be negative / beyond the image -> TMA zero fill == padding
-          tma_load_4d(sa, &map_x, &full_bar[stage], c0, wo0 * p.stride + s * p.dil - p.pad_w, ho0 * p.stride + r * p.dil - p.pad, n0);
+          tma_load_4d(sa, &map_x, &full_bar[stage], c0, xw, xh, n0);
           if constexpr (!B_MN) {
             tma_load_3d(sb, &map_w, &full_bar[stage], c0, tap, co0);                       // {64 ci, 1 tap, BN co}
           } else {
@@ -420,7 +436,8 @@ static int conv_launch(const void* x, const void* w, void* y, ConvParams p, int 
   }
   {   // y: [N, Ho, Wo, Cout] -> dims (Cout, Wo, Ho, N), box {64, TW, TH, TN}
     const uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.N};
-    const uint64_t st[3] = {(uint64_t)p.Cout, (uint64_t)p.Wo * p.Cout, (uint64_t)p.Ho * p.Wo * p.Cout};
+    uint64_t st[3] = {(uint64_t)p.Cout, (uint64_t)p.Wo * p.Cout, (uint64_t)p.Ho * p.Wo * p.Cout};
+    if (p.ys_w > 0) { st[0] = (uint64_t)p.ys_w; st[1] = (uint64_t)p.ys_h; st[2] = (uint64_t)p.ys_n; }
     const uint32_t box[4] = {64u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
     const uint32_t es[4] = {1u, 1u, 1u, 1u};
     e |= make_map_nd(&my, y, 4, dims, st, box, es);
@@ -468,6 +485,40 @@ extern "C" int rvn_conv_forward_strided(const void* x, const void* w, void* y, c
   }
   if (wide) return rvn::conv_launch<256, false>(x, w, y, p, num_sms, stream);
   return rvn::conv_launch<128, false>(x, w, y, p, num_sms, stream);
+}
+
+// Data gradient of a STRIDE-2 convolution y = conv(x, w; stride 2, pad, pad_w), dilation 1:
+//   dx[n, h, w, ci] = sum over (r, s, co) with (h + pad - r), (w + pad_w - s) even of dy[n, (h + pad - r) / 2, (w + pad_w - s) / 2, co] * w[co, r, s, ci]
+// Split by the parity (a, b) of (h, w): every phase is a stride-1 convolution of dy with the filter taps of matching parity, i.e. one
+// launch of the implicit-GEMM kernel (transposed / MN-major weights, as the stride-1 dgrad) whose output tensor map steps over every
+// second pixel of dx.  No zero-insertion, no scatter: each dx element is written exactly once (phases without taps — 1x1 filters —
+// stay zero: the caller zero-fills dx when R == 1 or S == 1).  dy [N,Ho,Wo,Cout], w [Cout,R,S,Cin], dx [N,H,W,Cin].
+extern "C" int rvn_conv_dgrad_s2(const void* dy, const void* w, void* dx, int N, int Ho, int Wo, int Cout, int H, int W, int Cin, int R,
+                                 int S, int pad, int pad_w, int num_sms, cudaStream_t stream) {
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int Ha = (H - a + 1) / 2, Wb = (W - b + 1) / 2;
+      if (Ha <= 0 || Wb <= 0) continue;
+      rvn::ConvParams p{};
+      p.sub = 1;
+      p.r0 = (a + pad) % 2;
+      p.s0 = (b + pad_w) % 2;
+      p.Ra = p.r0 < R ? (R - p.r0 + 1) / 2 : 0;
+      p.Sb = p.s0 < S ? (S - p.s0 + 1) / 2 : 0;
+      if (p.Ra == 0 || p.Sb == 0) continue;                 // no tap reaches this phase
+      p.ch = (a + pad - p.r0) / 2;
+      p.cw = (b + pad_w - p.s0) / 2;
+      p.N = N; p.H = Ho; p.W = Wo; p.Cin = Cout;            // GEMM K = channels of dy
+      p.Ho = Ha; p.Wo = Wb; p.Cout = Cin;                   // GEMM N = channels of dx
+      p.R = R; p.S = S; p.stride = 1; p.pad = 0; p.pad_w = 0; p.dil = 1;
+      p.ys_w = 2LL * Cin; p.ys_h = 2LL * W * Cin; p.ys_n = static_cast<long long>(H) * W * Cin;
+      void* base = static_cast<__nv_bfloat16*>(dx) + (static_cast<long long>(a) * W + b) * Cin;
+      const long long m_tiles = (static_cast<long long>(N) * Ha * Wb + 127) / 128;
+      const bool wide = Cin >= 256 && m_tiles * ((Cin + 255) / 256) >= num_sms;
+      const int rc = wide ? rvn::conv_launch<256, true>(dy, w, base, p, num_sms, stream) : rvn::conv_launch<128, true>(dy, w, base, p, num_sms, stream);
+      if (rc != 0) return rc;
+    }
+  return 0;
 }
 
 extern "C" int rvn_conv_forward(const void* x, const void* w, void* y, const void* bias, int relu, int N, int H, int W, int Cin, int Ho,

@@ -481,8 +481,8 @@ def _wgrad_acc_of(weight):
 
 
 class _ConvNHWC(torch.autograd.Function):
-    """Implicit-GEMM convolution (ops/csrc/conv_sm100.cu) on NHWC activations: forward, stride-1 data gradient and the split-K
-    weight gradient run on the tcgen05 kernels; stride-2 data gradients still go through cuDNN (tracked in DESIGN.md).
+    """Implicit-GEMM convolution (ops/csrc/conv_sm100.cu) on NHWC activations: forward, data gradient (stride 1 directly, stride 2
+    as four parity phases) and the split-K weight gradient all run on the tcgen05 kernels.
     ``weight`` is the [O, I, kh, kw] parameter itself; stored channels_last (ParamStore does) its OHWI view is free."""
 
     @staticmethod
@@ -515,6 +515,9 @@ class _ConvNHWC(torch.autograd.Function):
         if native_dx:
             dx = C().conv_nhwc(dy, w, None, 1, pad, dil, False, True, x.shape[1], x.shape[2], pad_w)
             calls['conv_dgrad'] += 1
+        elif need_dx and stride == 2 and dil == 1 and STRIDE2_DGRAD:
+            dx = _dgrad_s2(dy, w, x.shape[1], x.shape[2], pad, pad_w)
+            native_dx = dx is not None
         if need_dw and NATIVE_CONV_WGRAD:
             dw = _conv_wgrad_into(weight, ctx.wgrad_acc, dy, x, w.shape[1], w.shape[2], stride, pad, dil, pad_w)
             calls['conv_wgrad'] += 1
@@ -531,6 +534,27 @@ class _ConvNHWC(torch.autograd.Function):
                 dw = gw
             db = gb
         return dx, dw, db, None, None, None, None, None, None
+
+
+_S2_ODD_HEIGHT_OK = True
+
+
+def _dgrad_s2(dy, w, H, W, pad, pad_w):
+    """Data gradient of a stride-2 convolution as four parity phases of the implicit-GEMM kernel (conv_sm100.cu: rvn_conv_dgrad_s2);
+    every phase writes dx through a tensor map that steps over every second pixel.  For an odd input height the image stride is not
+    a multiple of that map's row stride; should the driver's encoder refuse such a map, those shapes go back to the library path."""
+    global _S2_ODD_HEIGHT_OK
+    if H % 2 and not _S2_ODD_HEIGHT_OK:
+        return None
+    try:
+        dx = C().conv_dgrad_s2(dy, w, H, W, pad, pad_w)
+    except RuntimeError as exc:
+        if H % 2 == 0 or 'conv_dgrad_s2 (code 1' not in str(exc):
+            raise
+        _S2_ODD_HEIGHT_OK = False
+        return None
+    calls['conv_dgrad_s2'] += 1
+    return dx
 
 
 class _Conv1x1(torch.autograd.Function):
@@ -690,10 +714,18 @@ def _with_bn_sums(y, sums):
     return y
 
 
-def _new_bn_sums(weight, bn_stats):
-    if bn_stats and BN_STATS_FROM_CONV:
-        return torch.zeros(2 * weight.shape[0], dtype=torch.float32, device=weight.device)
-    return None
+def _new_bn_sums(weight, bn_stats, gemm_rows=0):
+    """[2, Cout] fp32 accumulator for the producing epilogue, or None.  ``gemm_rows``: the convolution runs as a plain GEMM with
+    that many rows; policy 'skip_pair' leaves BatchNorm its own statistics pass where that GEMM is routed to the CTA-pair kernel
+    (short-K pointwise convolutions are epilogue bound there: the fused statistics cost more than the separate kernel)."""
+    if not (bn_stats and BN_STATS_FROM_CONV):
+        return None
+    if gemm_rows and BN_STATS_GEMM_POLICY != 'all':
+        if BN_STATS_GEMM_POLICY == 'none':
+            return None
+        if BN_STATS_GEMM_POLICY == 'skip_pair' and C().gemm_prefers_pair(gemm_rows, weight.shape[0], weight.shape[1]):
+            return None
+    return torch.zeros(2 * weight.shape[0], dtype=torch.float32, device=weight.device)
 
 
 def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, bn_stats=False):
@@ -726,7 +758,7 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, bn_s
             x = x[:, :, ::sh, ::sw]
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
-        sums = _new_bn_sums(weight, bn_stats and bias is None)
+        sums = _new_bn_sums(weight, bn_stats and bias is None, x.shape[0] * x.shape[2] * x.shape[3])
         y = _Conv1x1.apply(x.permute(0, 2, 3, 1), weight, bias, sums)     # zero-copy NHWC view in, NHWC out
         return _with_bn_sums(y.permute(0, 3, 1, 2), sums)                 # NCHW-shaped, channels_last-strided
     if base_ok and sh == sw and dh == dw_ and sh in (1, 2) and IMPLICIT_GEMM_CONV and (kh == kw and ph == pw or RECTANGULAR_CONV):
@@ -757,7 +789,7 @@ def conv1x1_fork(x, weight, bn_stats=False):
     """``(conv1x1(x), x)`` for the block-opening pointwise convolution of a residual block (NCHW-shaped channels_last bf16)."""
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
-    sums = _new_bn_sums(weight, bn_stats)
+    sums = _new_bn_sums(weight, bn_stats, x.shape[0] * x.shape[2] * x.shape[3])
     y, skip = _Conv1x1Fork.apply(x.permute(0, 2, 3, 1), weight, sums)
     return _with_bn_sums(y.permute(0, 3, 1, 2), sums), skip.permute(0, 3, 1, 2)
 
@@ -771,9 +803,11 @@ def wgrad_flush(acc, grad):
 IMPLICIT_GEMM_CONV = True
 NATIVE_CONV_WGRAD = True
 SMALL_CIN_STEM = True
+STRIDE2_DGRAD = os.environ.get('RAVNEST_STRIDE2_DGRAD', '1') != '0'
 CONV_FORK_ACCUMULATE = True
 WGRAD_STAGING = True
 BN_STATS_FROM_CONV = os.environ.get('RAVNEST_BN_STATS_FROM_CONV', '1') != '0'      # BatchNorm statistics from the producer's epilogue
+BN_STATS_GEMM_POLICY = os.environ.get('RAVNEST_BN_STATS_GEMM', 'all')              # pointwise (GEMM) convolutions: all | skip_pair | none
 STRIDED_1X1_IMPLICIT = True
 RECTANGULAR_CONV = True
 BN_RELU_BITMASK = True

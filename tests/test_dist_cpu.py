@@ -112,6 +112,21 @@ def test_inception_three_stage_pipeline_over_gloo(workdir, free_ports):
 
 
 @pytest.mark.slow
+def test_resnet_four_stage_pipeline_over_gloo(workdir, free_ports):
+    """BASELINE.json config #2's pipeline shape on CPU: ResNet-50 cut into 4 stages by the reference's parameter shares
+    (cluster_formation.py:23-25).  The cuts land inside bottleneck blocks, where an identity block's opening convolution hands out
+    ``(conv1(x), x)`` (nn.Conv2d(fork=True)): stages exchange the unpacked tensors, one of them skipping a stage."""
+    rv.set_seed(11)
+    rv.clusterize(models.resnet50(num_classes=10), example_args=(torch.rand(2, 3, 32, 32),), topology={'stages': 4, 'replicas': 1},
+                  proportions=[0.2, 0.2, 0.2, 0.4], balance='params', node_configs=rv.default_gpu_configs(4), base_dir=str(workdir))
+    res = _run_multi(workdir, 29000 + free_ports(1)[0] % 900, 4, ['--model', 'resnet', '--epochs', '2'])
+    assert [r['node_type'] for r in res] == ['root', 'stem', 'stem', 'leaf']
+    assert all(r['finite'] and r['n_backwards'] == 6 for r in res)
+    losses = [float(l) for l in open(os.path.join(str(workdir), 'losses_3.txt'))]
+    assert len(losses) == 6 and all(l == l for l in losses)
+
+
+@pytest.mark.slow
 def test_sorter_eight_stage_pipeline_over_gloo(workdir, free_ports):
     """BASELINE.json config #5 on CPU: the minGPT sorter as an 8-stage pure pipeline, one node per stage, tensor labels."""
     rv.set_seed(11)
