@@ -159,3 +159,54 @@ def test_transfer_watchdog_flags_stalled_and_failed_transfers():
     found = wd.check_once(now)
     assert sorted(l for l, _ in found) == ['backward', 'forward']
     assert any('pending for 100 s' in why for _, why in found) and any('ncclRemoteError' in why for _, why in found)
+
+
+def test_conv2d_fusion_hints_are_inert_off_the_native_path():
+    """``fork`` / ``bn_stats`` change neither parameters nor numerics; on CPU they fall back to plain PyTorch ops."""
+    from ravnest_b200 import nn as rnn, ops
+    torch.manual_seed(0)
+    plain, hinted = torch.nn.Conv2d(8, 16, 1, bias=False), rnn.Conv2d(8, 16, 1, bias=False, fork=True, bn_stats=True)
+    hinted.load_state_dict(plain.state_dict())
+    assert list(hinted.state_dict()) == list(plain.state_dict())
+    x = torch.randn(2, 8, 5, 5, requires_grad=True)
+    y, skip = hinted(x)
+    assert skip is x and torch.allclose(y, plain(x))
+    (y.sum() + (skip * 2).sum()).backward()
+    xr = x.detach().clone().requires_grad_(True)
+    (plain(xr).sum() + (xr * 2).sum()).backward()
+    assert torch.allclose(x.grad, xr.grad)
+    assert getattr(ops.conv2d(x, plain.weight, bn_stats=True), '_rvn_bn_sums', None) is None
+    for bad in (dict(kernel_size=3, padding=1), dict(kernel_size=1, stride=2), dict(kernel_size=1, bias=True)):
+        with pytest.raises(ValueError):
+            rnn.Conv2d(8, 16, fork=True, **{'bias': False, **bad})
+
+
+def test_wgrad_staging_is_a_cuda_only_feature():
+    """On CPU the stage keeps the plain path: no fp32 accumulator, ``flush_wgrad`` is a no-op, leaves still accumulate into the bucket."""
+    from ravnest_b200.runtime.param_store import ParamStore
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Flatten(), torch.nn.Linear(4 * 36, 2))
+    store = ParamStore(model, 'cpu', n_slots=2)
+    assert store.enable_wgrad_staging() is False and store.wgrad_acc is None
+    store.flush_wgrad()
+    leaf = store.make_leaf(store.current.flat.clone(), 0)
+    assert leaf.requires_grad and leaf.grad.data_ptr() == store.grad_views[0].data_ptr() and not hasattr(leaf, '_rvn_wgrad_acc')
+    slot = store.acquire()
+    torch.func.functional_call(model, slot.param_dict, (torch.randn(2, 3, 8, 8),)).sum().backward()
+    assert float(store.grad.abs().sum()) > 0
+    store.zero_grad(discard_staged=True)
+    assert float(store.grad.abs().sum()) == 0
+
+
+def test_clusterize_pass_data_selects_how_the_model_is_sized(tmp_path):
+    """reference operations/utils.py:393-412: shape-only sizing by default, the caller's tensor with ``pass_data=True``."""
+    from ravnest_b200 import models
+    seen = []
+    x = torch.full((4, 1, 8, 8), 7.0)
+    for flag in (False, True):
+        rv.set_seed(3)
+        seen.clear()
+        model = models.CNN_Net()
+        model.register_forward_pre_hook(lambda _m, args: seen.append(float(args[0].flatten()[0])))     # (not seen by the FX trace)
+        rv.clusterize(model, example_args=(x,), pass_data=flag, base_dir=str(tmp_path / 'nd_{}'.format(int(flag))),
+                      node_configs=rv.default_gpu_configs(3))
+        assert (seen[0] == 7.0) is flag          # the first real forward is the sizing pass
