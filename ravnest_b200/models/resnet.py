@@ -31,7 +31,7 @@ class Bottleneck(nn.Module):
             self.downsample = nn.Sequential(rnn.Conv2d(inplanes, out, 1, stride=stride, bias=False, bn_stats=True), rnn.BatchNorm2d(out))
 
     def forward(self, x):
-        if self.conv1.fork:
+        if getattr(self.conv1, 'fork', False):
             both = self.conv1(x)
             y, identity = both[0], both[1]
         else:

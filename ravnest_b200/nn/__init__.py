@@ -113,8 +113,9 @@ class Conv2d(nn.Conv2d):
             raise ValueError('fork=True needs a bias-free, stride-1, ungrouped 1x1 convolution')
 
     def forward(self, x):
-        stats = self.bn_stats and self.training
-        if self.fork:
+        # (getattr: stage modules pickled before these hints existed still load and run)
+        stats = getattr(self, 'bn_stats', False) and self.training
+        if getattr(self, 'fork', False):
             return ops.conv1x1_fork(x, self.weight, stats)
         if isinstance(self.padding, str) or self.padding_mode != 'zeros':
             return super().forward(x)
