@@ -209,7 +209,6 @@ std::vector<torch::Tensor> gemm(const torch::Tensor& A, bool a_mn, const torch::
   const void* bias_ptr = nullptr;
   if (bias.has_value() && bias->defined()) {
     TORCH_CHECK(bias->scalar_type() == torch::kBFloat16 && bias->is_contiguous() && bias->numel() == N, "bad bias");
-    TORCH_CHECK(N % 8 == 0 || true, "");
     bias_ptr = bias->data_ptr();
   }
   const void* dact_ptr = nullptr;
